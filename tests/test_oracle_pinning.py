@@ -1,0 +1,110 @@
+"""Pin the CPU oracle against the reference's own known answers.
+
+* operator identities of ``fibergen --test`` (fg:23946-23974, fg:24086-24182, fg:24460-24583)
+  on the reference's grids 2x1x1 and 41x33x11 with L=(1,1,1) and L=(41,33,11) (fg:27259-27273),
+  reference material mu_0=1324.3, lambda_0=324.2 (fg:24007-24008), tolerance sqrt(eps) (fg:23502);
+* closed-form 3-layer laminate of demo/elasticity/laminate (fg:26405-26446);
+* homogeneous medium => one iteration, eps == E.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import fg_oracle as fo
+
+TOL = math.sqrt(np.finfo(float).eps)
+GRIDS = [((2, 1, 1), (1., 1., 1.)), ((41, 33, 11), (1., 1., 1.)), ((41, 33, 11), (41., 33., 11.))]
+MU0, LAM0 = 1324.3, 324.2
+
+
+def lame(E, nu):
+    return E * nu / ((1 + nu) * (1 - 2 * nu)), E / (2 * (1 + nu))
+
+
+def mk(n, L, mode, scheme):
+    s = fo.LSSolver(*n, *L, mode=mode, gamma_scheme=scheme)
+    s.set_reference(MU0 if mode != "heat" else 1.0, LAM0 if mode != "heat" else 0.0)
+    s.setBCProjector(fo.Id4(s.dim))
+    return s
+
+
+@pytest.mark.parametrize("n,L", GRIDS)
+def test_heat_staggered_identity(n, L):
+    s = mk(n, L, "heat", "staggered")
+    rng = np.random.default_rng(1)
+    tau = rng.random((3,) + n)
+    z = np.zeros(3)
+    tau = s._GammaOperatorStaggered(z, s.mu_0, s.lambda_0, tau, 1.0)
+    org = tau.copy()
+    t = s.calcStressConst(s.mu_0, s.lambda_0, tau)
+    f = s.divOperatorStaggered(t)
+    u = s.ifft(s.G0OperatorFourierStaggered(s.mu_0, s.lambda_0, s.fft(f), 1.0))
+    t = s.epsOperatorStaggered(z, u)
+    assert np.linalg.norm(np.abs(t - org).reshape(3, -1).max(axis=1)) <= TOL
+
+
+@pytest.mark.parametrize("n,L", GRIDS)
+@pytest.mark.parametrize("mode", ["elasticity", "hyperelasticity"])
+def test_collocated_identity(n, L, mode):
+    s = mk(n, L, mode, "collocated")
+    d = s.dim
+    rng = np.random.default_rng(2)
+    tau = rng.random((d,) + n)
+    z = np.zeros(d)
+    tau = s.GammaOperator(z, s.mu_0, s.lambda_0, tau, 1.0)
+    org = tau.copy()
+    t = s.calcStressConst(s.mu_0, s.lambda_0, tau)
+    t = s.GammaOperator(z, s.mu_0, s.lambda_0, t, 1.0)
+    assert np.linalg.norm(np.abs(t - org).reshape(d, -1).max(axis=1)) <= TOL
+
+
+@pytest.mark.parametrize("n,L", GRIDS)
+@pytest.mark.parametrize("mode", ["elasticity", "hyperelasticity"])
+def test_staggered_identity(n, L, mode):
+    s = mk(n, L, mode, "staggered")
+    d = s.dim
+    rng = np.random.default_rng(3)
+    z = np.zeros(d)
+    tau = s.epsOperatorStaggered(z, rng.random((3,) + n))
+    org = tau.copy()
+    t = s.calcStressConst(s.mu_0, s.lambda_0, tau)
+    f = s.divOperatorStaggered(t)
+    u = s.ifft(s.G0OperatorFourierStaggered(s.mu_0, s.lambda_0, s.fft(f), 1.0))
+    t = s.epsOperatorStaggered(z, u)
+    assert np.linalg.norm(np.abs(t - org).reshape(d, -1).max(axis=1)) <= TOL
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(tol=1e-10), dict(tol=1e-10, gamma_scheme="collocated"),
+                                dict(tol=1e-9, method="basic", error_estimator="sigma"),
+                                dict(tol=1e-9, method="polarization", error_estimator="sigma")])
+def test_laminate_demo_closed_form(kw):
+    """demo/elasticity/laminate/project.xml: 10x1x1, layers at 0.2/0.3/0.5"""
+    s = fo.LSSolver(10, 1, 1, mode="elasticity", **kw)
+    phis = np.zeros((3, 10, 1, 1))
+    phis[0, :2] = 1
+    phis[1, 2:5] = 1
+    phis[2, 5:] = 1
+    layers = []
+    for k, (E, nu, phi) in enumerate([(100, .4, .2), (25, .25, .3), (50, .3, .5)]):
+        lam, mu = lame(E, nu)
+        s.add_phase("layer%d" % (k + 1), fo.LinearIsotropic(mu, lam), phis[k])
+        layers.append((phi, lam, mu))
+    _, Cv = s.calc_effective_properties()
+    Ca = fo.calc_isotropic_laminate(layers)
+    tol = 1e-9 if kw.get("method", "cg") == "cg" else 1e-6
+    assert np.abs(Cv - Ca).max() / np.abs(Ca).max() < tol
+
+
+@pytest.mark.parametrize("method", ["cg", "basic"])
+def test_homogeneous_one_iteration(method):
+    s = fo.LSSolver(8, 6, 5, mode="elasticity", method=method, error_estimator="residual" if method == "cg" else "epsilon")
+    lam, mu = lame(3.0, 0.3)
+    s.add_phase("m", fo.LinearIsotropic(mu, lam), np.ones((8, 6, 5)))
+    E = np.array([1., 0.5, -0.2, 0.1, 0.3, 0.7])
+    s.setStrain(E)
+    s.run()
+    assert np.allclose(s.epsilon, E.reshape(-1, 1, 1, 1), atol=1e-14)
+    Sm = s.calcMeanStress()
+    assert np.allclose(Sm, fo.LinearIsotropic(mu, lam).PK1(E.reshape(6, 1), 1.0)[:, 0], rtol=1e-13)
+    assert len(s.residuals) <= 2
