@@ -1,0 +1,679 @@
+// C ABI of libfgb200 (include/fgb200.h): context, fields, setup and the operator / scheme entry points.
+#include "fgb_internal.h"
+#include <cstdarg>
+#include <cmath>
+
+static std::string g_create_error;
+
+int fgb_fail(fgb_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+// ---- profiling: event pairs recorded on the launching stream, resolved lazily ---------------------
+struct ProfPending {
+    const char* name;
+    cudaEvent_t e0, e1;
+};
+static std::map<fgb_ctx*, std::vector<ProfPending>> g_pending;
+static std::map<fgb_ctx*, std::vector<cudaEvent_t>> g_event_pool;
+
+static cudaEvent_t get_event(fgb_ctx* c) {
+    auto& pool = g_event_pool[c];
+    if (!pool.empty()) {
+        cudaEvent_t e = pool.back();
+        pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+ProfScope::ProfScope(fgb_ctx* ctx, const char* n) : c(ctx), name(n) {
+    if (!c->profiling) return;
+    ProfPending p;
+    p.name = n;
+    p.e0 = get_event(c);
+    p.e1 = get_event(c);
+    cudaEventRecord(p.e0, c->stream);
+    g_pending[c].push_back(p);
+}
+ProfScope::~ProfScope() {
+    if (!c->profiling) return;
+    cudaEventRecord(g_pending[c].back().e1, c->stream);
+}
+
+static void prof_resolve(fgb_ctx* c) {
+    auto it = g_pending.find(c);
+    if (it == g_pending.end()) return;
+    cudaStreamSynchronize(c->stream);
+    for (auto& p : it->second) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, p.e0, p.e1) == cudaSuccess) {
+            ProfEntry& e = c->prof[p.name];
+            e.ms += ms;
+            e.launches++;
+        }
+        g_event_pool[c].push_back(p.e0);
+        g_event_pool[c].push_back(p.e1);
+    }
+    it->second.clear();
+}
+
+// ---- context --------------------------------------------------------------------------------------
+extern "C" const char* fgb_version(void) { return "fgb200 0.1 (sm_100a)"; }
+
+extern "C" const char* fgb_last_error(const fgb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int fgb_create(fgb_ctx** out, int nx, int ny, int nz, double Lx, double Ly, double Lz, int mode, int gamma_scheme,
+                          int device, int rank, int nranks) {
+    if (!out) return FGB_EINVAL;
+    *out = nullptr;
+    if (nx < 1 || ny < 1 || nz < 1 || !(Lx > 0) || !(Ly > 0) || !(Lz > 0))
+        return fgb_fail(nullptr, FGB_EINVAL, "invalid grid %dx%dx%d / box %g x %g x %g", nx, ny, nz, Lx, Ly, Lz);
+    if (mode < FGB_MODE_ELASTICITY || mode > FGB_MODE_POROUS) return fgb_fail(nullptr, FGB_EINVAL, "unknown mode %d", mode);
+    if (gamma_scheme != FGB_GAMMA_COLLOCATED && gamma_scheme != FGB_GAMMA_STAGGERED)
+        return fgb_fail(nullptr, FGB_EUNSUPPORTED, "gamma scheme %d not supported (collocated and staggered only)", gamma_scheme);
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fgb_fail(nullptr, FGB_EINVAL, "bad rank %d of %d", rank, nranks);
+    if (nranks > 1 && (nx % nranks || ny % nranks))
+        return fgb_fail(nullptr, FGB_EUNSUPPORTED, "slab partition needs nx and ny divisible by the number of ranks");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fgb_fail(nullptr, FGB_ENODEV, "no CUDA device available (this library has no CPU fallback)");
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) return fgb_fail(nullptr, FGB_ENODEV, "cudaGetDevice failed");
+    }
+    if (device >= ndev) return fgb_fail(nullptr, FGB_ENODEV, "device %d out of range (%d devices)", device, ndev);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fgb_fail(nullptr, FGB_ENODEV, "cannot query device %d", device);
+    if (prop.major != 10)
+        return fgb_fail(nullptr, FGB_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a only (no fallback)", device,
+                        prop.major, prop.minor);
+    if (cudaSetDevice(device) != cudaSuccess) return fgb_fail(nullptr, FGB_ENODEV, "cudaSetDevice(%d) failed", device);
+
+    fgb_ctx* c = new fgb_ctx();
+    c->g.nx = nx; c->g.ny = ny; c->g.nz = nz;
+    c->g.nzc = nz / 2 + 1;
+    c->g.nzp = 2 * c->g.nzc;
+    c->g.lnx = nx / nranks;
+    c->g.x0 = rank * c->g.lnx;
+    c->g.plane = (size_t)c->g.lnx * ny * c->g.nzp;
+    c->g.hx = nx / Lx; c->g.hy = ny / Ly; c->g.hz = nz / Lz;
+    c->L[0] = Lx; c->L[1] = Ly; c->L[2] = Lz;
+    c->mode = mode;
+    c->scheme = gamma_scheme;
+    c->dim = (mode == FGB_MODE_HYPERELASTICITY) ? 9 : ((mode == FGB_MODE_HEAT || mode == FGB_MODE_POROUS) ? 3 : 6);
+    c->udim = (c->dim == 3) ? 1 : 3;
+    c->device = device;
+    c->rank = rank; c->nranks = nranks;
+    c->sm_count = prop.multiProcessorCount;
+    c->smem_optin = prop.sharedMemPerBlockOptin;
+    c->own_stream = nullptr;
+    c->stream = nullptr;
+    for (int i = 0; i < FGB_MAX_FIELDS; i++) c->fields[i] = nullptr;
+    for (int i = 0; i < FGB_MAX_PHASES; i++) { c->phi[i] = nullptr; c->laws[i].id = -1; }
+    c->ubuf = nullptr; c->normals = nullptr; c->orient = nullptr;
+    c->nphases = 0; c->mix = FGB_MIX_VOIGT; c->freq_hack = 0;
+    const double eps = 2.220446049250313e-16;
+    c->lam.eps_t = 4 * eps;
+    c->lam.eps_a = pow(eps, 2.0 / 3.0);
+    c->lam.eps_g = eps;
+    c->lam.alpha = 0.001; c->lam.beta = 0.1;
+    c->lam.delta = 1 - 1024 * eps;
+    c->lam.maxiter = 32; c->lam.backtrack = 1; c->lam.project_t = 1; c->lam.fixed_c1 = -1.0;
+    for (int a = 0; a < 3; a++) { c->tw_dev[a] = nullptr; c->kpm_dev[a] = nullptr; c->kp_dev[a] = nullptr; c->xi_dev[a] = nullptr; }
+    c->d_partials = nullptr; c->d_result = nullptr; c->h_result = nullptr; c->d_scalars = nullptr; c->d_flag = nullptr; c->h_flag = nullptr;
+    c->nccl_comm = nullptr; c->xbuf = nullptr; c->halo = nullptr; c->visc_tmp = nullptr;
+    c->launches = 0; c->profiling = false;
+    c->bc_active = false; c->bc_relax = 1.0;
+    for (int i = 0; i < 81; i++) c->bc_MQ[i] = c->bc_MQC0[i] = 0;
+    for (int i = 0; i < 9; i++) c->F00[i] = 0;
+
+#define CREATE_CUDA(call)                                                                              \
+    do {                                                                                               \
+        cudaError_t e__ = (call);                                                                      \
+        if (e__ != cudaSuccess) {                                                                      \
+            int code = (e__ == cudaErrorMemoryAllocation) ? FGB_ENOMEM : FGB_ECUDA;                    \
+            fgb_fail(nullptr, code, "%s failed: %s", #call, cudaGetErrorString(e__));                  \
+            fgb_destroy(c);                                                                            \
+            return code;                                                                               \
+        }                                                                                              \
+    } while (0)
+    CREATE_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    c->red_blocks = c->sm_count * 8;
+    CREATE_CUDA(cudaMalloc(&c->d_partials, sizeof(double) * 32 * (size_t)c->red_blocks));
+    CREATE_CUDA(cudaMalloc(&c->d_result, sizeof(double) * 64));
+    CREATE_CUDA(cudaMallocHost(&c->h_result, sizeof(double) * 64));
+    CREATE_CUDA(cudaMalloc(&c->d_flag, sizeof(int)));
+    CREATE_CUDA(cudaMemset(c->d_flag, 0, sizeof(int)));
+    CREATE_CUDA(cudaMallocHost(&c->h_flag, sizeof(int)));
+    if (c->scheme == FGB_GAMMA_STAGGERED) CREATE_CUDA(cudaMalloc(&c->ubuf, sizeof(double) * c->g.plane * c->udim));
+    int rc = fgb_fft_init(c);
+    if (rc) {
+        g_create_error = c->err;
+        fgb_destroy(c);
+        return rc;
+    }
+    *out = c;
+    return FGB_OK;
+}
+
+extern "C" void fgb_destroy(fgb_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    fgb_comm_free(c);
+    for (int i = 0; i < FGB_MAX_FIELDS; i++) if (c->fields[i]) cudaFree(c->fields[i]);
+    for (int i = 0; i < FGB_MAX_PHASES; i++) if (c->phi[i]) cudaFree(c->phi[i]);
+    if (c->ubuf) cudaFree(c->ubuf);
+    if (c->visc_tmp) cudaFree(c->visc_tmp);
+    if (c->normals) cudaFree(c->normals);
+    if (c->orient) cudaFree(c->orient);
+    fgb_fft_free(c);
+    if (c->d_partials) cudaFree(c->d_partials);
+    if (c->d_result) cudaFree(c->d_result);
+    if (c->h_result) cudaFreeHost(c->h_result);
+    if (c->d_flag) cudaFree(c->d_flag);
+    if (c->h_flag) cudaFreeHost(c->h_flag);
+    for (auto& p : g_pending[c]) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
+    for (auto& e : g_event_pool[c]) cudaEventDestroy(e);
+    g_pending.erase(c);
+    g_event_pool.erase(c);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+extern "C" int fgb_set_stream(fgb_ctx* c, void* s) {
+    if (!c) return FGB_EINVAL;
+    FGB_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return FGB_OK;
+}
+
+extern "C" int fgb_synchronize(fgb_ctx* c) {
+    if (!c) return FGB_EINVAL;
+    FGB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return FGB_OK;
+}
+
+extern "C" int fgb_local_nx(const fgb_ctx* c) { return c ? c->g.lnx : 0; }
+extern "C" int fgb_local_x0(const fgb_ctx* c) { return c ? c->g.x0 : 0; }
+extern "C" size_t fgb_plane_elems(const fgb_ctx* c) { return c ? c->g.plane : 0; }
+extern "C" int fgb_dim(const fgb_ctx* c) { return c ? c->dim : 0; }
+
+// ---- fields -----------------------------------------------------------------------------------------
+#define CHECK_CTX(c) do { if (!(c)) return FGB_EINVAL; cudaSetDevice((c)->device); } while (0)
+#define CHECK_FIELD(c, f)                                                                           \
+    do {                                                                                            \
+        if ((f) < 0 || (f) >= FGB_MAX_FIELDS || !(c)->fields[f])                                    \
+            return fgb_fail(c, FGB_EINVAL, "invalid field id %d", (int)(f));                        \
+    } while (0)
+
+extern "C" int fgb_field_alloc(fgb_ctx* c) {
+    CHECK_CTX(c);
+    for (int i = 0; i < FGB_MAX_FIELDS; i++) {
+        if (!c->fields[i]) {
+            cudaError_t e = cudaMalloc(&c->fields[i], sizeof(double) * c->g.plane * c->dim);
+            if (e != cudaSuccess) {
+                c->fields[i] = nullptr;
+                return fgb_fail(c, FGB_ENOMEM, "cannot allocate a %d-component field of %zu doubles per component: %s", c->dim,
+                                c->g.plane, cudaGetErrorString(e));
+            }
+            FGB_CUDA(c, cudaMemsetAsync(c->fields[i], 0, sizeof(double) * c->g.plane * c->dim, c->stream));
+            return i;
+        }
+    }
+    return fgb_fail(c, FGB_ENOMEM, "all %d field slots in use", FGB_MAX_FIELDS);
+}
+
+extern "C" int fgb_field_free(fgb_ctx* c, int f) {
+    CHECK_CTX(c);
+    CHECK_FIELD(c, f);
+    FGB_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->fields[f]);
+    c->fields[f] = nullptr;
+    return FGB_OK;
+}
+
+extern "C" int fgb_field_upload(fgb_ctx* c, int f, const double* const* comps) {
+    CHECK_CTX(c);
+    CHECK_FIELD(c, f);
+    for (int d = 0; d < c->dim; d++)
+        FGB_CUDA(c, cudaMemcpyAsync(c->fields[f] + (size_t)d * c->g.plane, comps[d], sizeof(double) * c->g.plane, cudaMemcpyHostToDevice, c->stream));
+    FGB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return FGB_OK;
+}
+
+extern "C" int fgb_field_download(fgb_ctx* c, int f, double* const* comps) {
+    CHECK_CTX(c);
+    CHECK_FIELD(c, f);
+    for (int d = 0; d < c->dim; d++)
+        FGB_CUDA(c, cudaMemcpyAsync(comps[d], c->fields[f] + (size_t)d * c->g.plane, sizeof(double) * c->g.plane, cudaMemcpyDeviceToHost, c->stream));
+    FGB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return FGB_OK;
+}
+
+extern "C" void* fgb_field_device_ptr(fgb_ctx* c, int f, int comp) {
+    if (!c || f < 0 || f >= FGB_MAX_FIELDS || !c->fields[f] || comp < 0 || comp >= c->dim) return nullptr;
+    return c->fields[f] + (size_t)comp * c->g.plane;
+}
+
+// ---- setup ------------------------------------------------------------------------------------------
+extern "C" int fgb_set_num_phases(fgb_ctx* c, int n) {
+    CHECK_CTX(c);
+    if (n < 1 || n > FGB_MAX_PHASES) return fgb_fail(c, FGB_EINVAL, "number of phases %d out of range 1..%d", n, FGB_MAX_PHASES);
+    c->nphases = n;
+    return FGB_OK;
+}
+
+static int upload_planes(fgb_ctx* c, double** dst, const double* const* comps, int n) {
+    if (!*dst) {
+        cudaError_t e = cudaMalloc(dst, sizeof(double) * c->g.plane * n);
+        if (e != cudaSuccess) { *dst = nullptr; return fgb_fail(c, FGB_ENOMEM, "device allocation failed: %s", cudaGetErrorString(e)); }
+    }
+    for (int d = 0; d < n; d++)
+        FGB_CUDA(c, cudaMemcpyAsync(*dst + (size_t)d * c->g.plane, comps[d], sizeof(double) * c->g.plane, cudaMemcpyHostToDevice, c->stream));
+    FGB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return FGB_OK;
+}
+
+extern "C" int fgb_set_phase(fgb_ctx* c, int p, const double* phi) {
+    CHECK_CTX(c);
+    if (p < 0 || p >= c->nphases) return fgb_fail(c, FGB_EINVAL, "phase index %d out of range", p);
+    const double* comps[1] = {phi};
+    return upload_planes(c, &c->phi[p], comps, 1);
+}
+
+extern "C" int fgb_set_law(fgb_ctx* c, int p, int law_id, const double* params, int nparams) {
+    CHECK_CTX(c);
+    if (p < 0 || p >= c->nphases) return fgb_fail(c, FGB_EINVAL, "phase index %d out of range", p);
+    static const int need[8] = {2, 36, 5, 1, 6, 2, 2, 2};
+    static const int ldim[8] = {6, 6, 6, 0, 3, 9, 9, 9};
+    if (law_id < 0 || law_id > FGB_LAW_NH2) return fgb_fail(c, FGB_EUNSUPPORTED, "unknown material law id %d (fg:15285)", law_id);
+    if (nparams != need[law_id]) return fgb_fail(c, FGB_EINVAL, "law %d needs %d parameters, got %d", law_id, need[law_id], nparams);
+    if (ldim[law_id] && ldim[law_id] != c->dim)
+        return fgb_fail(c, FGB_EINVAL, "law %d acts on %d components but mode has %d (fg:15211-15294)", law_id, ldim[law_id], c->dim);
+    if (law_id == FGB_LAW_SCALAR && c->dim == 9) return fgb_fail(c, FGB_EINVAL, "scalar law is not defined for hyperelasticity");
+    c->laws[p].id = law_id;
+    for (int i = 0; i < FGB_MAX_LAW_PARAMS; i++) c->laws[p].p[i] = i < nparams ? params[i] : 0.0;
+    return FGB_OK;
+}
+
+extern "C" int fgb_set_normals(fgb_ctx* c, const double* const* comps3) {
+    CHECK_CTX(c);
+    return upload_planes(c, &c->normals, comps3, 3);
+}
+extern "C" int fgb_set_orientation(fgb_ctx* c, const double* const* comps3) {
+    CHECK_CTX(c);
+    return upload_planes(c, &c->orient, comps3, 3);
+}
+
+extern "C" int fgb_set_mixing(fgb_ctx* c, int rule, const double* lp, int n) {
+    CHECK_CTX(c);
+    if (rule == FGB_MIX_REUSS) return fgb_fail(c, FGB_EUNSUPPORTED, "reuss mixing is not available on the device yet");
+    if (rule != FGB_MIX_VOIGT && rule != FGB_MIX_LAMINATE)
+        return fgb_fail(c, FGB_EUNSUPPORTED, "Unknown material mixing rule %d (voigt and laminate only)", rule);
+    c->mix = rule;
+    if (lp) {
+        if (n != 10) return fgb_fail(c, FGB_EINVAL, "laminate parameter vector must have 10 entries");
+        c->lam.eps_t = lp[0]; c->lam.eps_a = lp[1]; c->lam.eps_g = lp[2]; c->lam.alpha = lp[3]; c->lam.beta = lp[4];
+        c->lam.delta = lp[5]; c->lam.maxiter = (int)lp[6]; c->lam.backtrack = lp[7] != 0; c->lam.project_t = lp[8] != 0;
+        c->lam.fixed_c1 = lp[9];
+    }
+    return FGB_OK;
+}
+
+extern "C" int fgb_set_freq_hack(fgb_ctx* c, int on) {
+    CHECK_CTX(c);
+    c->freq_hack = on ? 1 : 0;
+    return FGB_OK;
+}
+
+extern "C" int fgb_set_bc(fgb_ctx* c, const double* MQ, const double* M_QC0, double bc_relax) {
+    CHECK_CTX(c);
+    const int d = c->dim;
+    c->bc_active = false;
+    c->bc_relax = bc_relax;
+    double nrm = 0;
+    for (int i = 0; i < d * d; i++) {
+        c->bc_MQ[i] = MQ ? MQ[i] : 0.0;
+        c->bc_MQC0[i] = M_QC0 ? M_QC0[i] : 0.0;
+        nrm += c->bc_MQ[i] * c->bc_MQ[i];
+    }
+    // initBCProjector skips the mean when ||MQ||_F < eps (fg:20233)
+    c->bc_active = std::sqrt(nrm) >= 2.220446049250313e-16;
+    return FGB_OK;
+}
+
+// ---- BLAS-1 / reductions ------------------------------------------------------------------------------
+extern "C" int fgb_set_constant(fgb_ctx* c, int f, const double* v) { CHECK_CTX(c); CHECK_FIELD(c, f); return fgb_k_set_constant(c, c->fields[f], v, 0); }
+extern "C" int fgb_add_constant(fgb_ctx* c, int f, const double* v) { CHECK_CTX(c); CHECK_FIELD(c, f); return fgb_k_set_constant(c, c->fields[f], v, 1); }
+extern "C" int fgb_copy(fgb_ctx* c, int s, int d) { CHECK_CTX(c); CHECK_FIELD(c, s); CHECK_FIELD(c, d); return fgb_k_copy(c, c->fields[s], c->fields[d], c->dim); }
+extern "C" int fgb_xpay(fgb_ctx* c, int r, int x, double a, int y) {
+    CHECK_CTX(c); CHECK_FIELD(c, r); CHECK_FIELD(c, x); CHECK_FIELD(c, y);
+    return fgb_k_xpay(c, c->fields[r], c->fields[x], a, c->fields[y]);
+}
+extern "C" int fgb_xpaymz(fgb_ctx* c, int r, int x, double a, int y, int z) {
+    CHECK_CTX(c); CHECK_FIELD(c, r); CHECK_FIELD(c, x); CHECK_FIELD(c, y); CHECK_FIELD(c, z);
+    return fgb_k_xpaymz(c, c->fields[r], c->fields[x], a, c->fields[y], c->fields[z]);
+}
+extern "C" int fgb_adjust_residual(fgb_ctx* c, int r, const double* E, int z) {
+    CHECK_CTX(c); CHECK_FIELD(c, r); CHECK_FIELD(c, z);
+    return fgb_k_adjust_residual(c, c->fields[r], E, c->fields[z]);
+}
+extern "C" int fgb_inner(fgb_ctx* c, int a, int b, int cc, double* out) {
+    CHECK_CTX(c); CHECK_FIELD(c, a); CHECK_FIELD(c, b);
+    if (cc >= 0) CHECK_FIELD(c, cc);
+    return fgb_k_inner(c, c->fields[a], c->fields[b], cc >= 0 ? c->fields[cc] : nullptr, out);
+}
+extern "C" int fgb_average(fgb_ctx* c, int f, double* out) { CHECK_CTX(c); CHECK_FIELD(c, f); return fgb_k_component_dot(c, c->fields[f], nullptr, out, 1); }
+extern "C" int fgb_component_dot(fgb_ctx* c, int a, int b, double* out) {
+    CHECK_CTX(c); CHECK_FIELD(c, a); CHECK_FIELD(c, b);
+    return fgb_k_component_dot(c, c->fields[a], c->fields[b], out, 0);
+}
+
+static int poll_flag(fgb_ctx* c) {
+    FGB_CUDA(c, cudaMemcpyAsync(c->h_flag, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    FGB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (*c->h_flag) {
+        FGB_CUDA(c, cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->stream));
+        return fgb_fail(c, FGB_ENUMERIC, "material law domain error on the device (log/pow of a non-positive det F, or >2 phases in a laminate voxel)");
+    }
+    return FGB_OK;
+}
+
+extern "C" int fgb_mean_pk1(fgb_ctx* c, int f, double alpha, double* out) {
+    CHECK_CTX(c); CHECK_FIELD(c, f);
+    int rc = fgb_k_mean_pk1(c, c->fields[f], alpha, out);
+    return rc ? rc : poll_flag(c);
+}
+extern "C" int fgb_mean_energy(fgb_ctx* c, int f, double* out) {
+    CHECK_CTX(c); CHECK_FIELD(c, f);
+    int rc = fgb_k_mean_energy(c, c->fields[f], out);
+    return rc ? rc : poll_flag(c);
+}
+extern "C" int fgb_min_detF(fgb_ctx* c, int f, double* out) { CHECK_CTX(c); CHECK_FIELD(c, f); return fgb_k_min_detF(c, c->fields[f], out); }
+extern "C" int fgb_ref_material(fgb_ctx* c, int f, int zt, double* lmin, double* lmax) {
+    CHECK_CTX(c); CHECK_FIELD(c, f);
+    int rc = fgb_k_ref_material(c, c->fields[f], zt, lmin, lmax);
+    return rc ? rc : poll_flag(c);
+}
+
+// ---- constitutive sweeps ---------------------------------------------------------------------------------
+extern "C" int fgb_calc_stress(fgb_ctx* c, int s, int d, double mu0, double lambda0, double alpha) {
+    CHECK_CTX(c); CHECK_FIELD(c, s); CHECK_FIELD(c, d);
+    return fgb_k_calc_stress(c, c->fields[s], c->fields[d], mu0, lambda0, alpha);
+}
+extern "C" int fgb_calc_stress_deriv(fgb_ctx* c, int F, int W, int d, double mu0, double lambda0, double alpha) {
+    CHECK_CTX(c); CHECK_FIELD(c, F); CHECK_FIELD(c, W); CHECK_FIELD(c, d);
+    return fgb_k_calc_stress_deriv(c, c->fields[F], c->fields[W], c->fields[d], mu0, lambda0, alpha);
+}
+extern "C" int fgb_calc_stress_const(fgb_ctx* c, int s, int d, double mu0, double lambda0) {
+    CHECK_CTX(c); CHECK_FIELD(c, s); CHECK_FIELD(c, d);
+    return fgb_k_calc_stress_const(c, c->fields[s], c->fields[d], mu0, lambda0);
+}
+extern "C" int fgb_calc_polarization(fgb_ctx* c, int s, int d, double mu0, int inv) {
+    CHECK_CTX(c); CHECK_FIELD(c, s); CHECK_FIELD(c, d);
+    return fgb_k_calc_polarization(c, c->fields[s], c->fields[d], mu0, inv);
+}
+
+// ---- Green operator -----------------------------------------------------------------------------------------
+// Voigt product M:v (fg:563-575): entries 3..5 of v doubled for dim 6
+static void dyad4_mv(int d, const double* M, const double* v, double* out) {
+    for (int r = 0; r < d; r++) {
+        double s = 0;
+        for (int k = 0; k < d; k++) s += M[r * d + k] * v[k] * ((d == 6 && k >= 3) ? 2.0 : 1.0);
+        out[r] = s;
+    }
+}
+
+// R = bc_relax*MQ:F0 - (1-bc_relax)*M:(QC0:F00)   (calcBCProjector fg:20258)
+static int bc_term(fgb_ctx* c, const double* tau, double* R) {
+    const int d = c->dim;
+    for (int i = 0; i < d; i++) R[i] = 0;
+    if (!c->bc_active && c->bc_relax == 1.0) return FGB_OK;
+    double F0[9] = {0}, a[9], b[9];
+    if (c->bc_active) {
+        int rc = fgb_k_component_dot(c, tau, nullptr, F0, 1);       // initBCProjector fg:20220/20228
+        if (rc) return rc;
+    }
+    dyad4_mv(d, c->bc_MQ, F0, a);
+    dyad4_mv(d, c->bc_MQC0, c->F00, b);
+    for (int i = 0; i < d; i++) R[i] = c->bc_relax * a[i] - (1 - c->bc_relax) * b[i];
+    return FGB_OK;
+}
+
+static int green_args(fgb_ctx* c, GreenArgs& ga, double mu0, double lambda0, double alpha, double beta) {
+    memset(&ga, 0, sizeof(ga));
+    ga.beta = beta;
+    ga.freq_hack = c->freq_hack;
+    if (c->scheme == FGB_GAMMA_STAGGERED) {
+        if (c->dim == 3) { ga.kind = 2; ga.c10 = -alpha / (2 * mu0); }                                              // fg:19758-19763
+        else if (c->dim == 6) { ga.kind = 1; ga.c10 = -alpha / mu0; ga.c20 = -alpha / (mu0 * (1 + mu0 / (lambda0 + mu0))); }   // fg:19749-19755
+        else { ga.kind = 1; ga.c10 = -alpha / (2 * mu0); ga.c20 = -alpha / (2 * mu0 * (1 + 2 * mu0 / lambda0)); }  // fg:19768-19774
+    } else {
+        if (c->dim == 3) { ga.kind = 4; ga.c10 = alpha / (2 * mu0); }                                               // fg:19309
+        else if (c->dim == 6) { ga.kind = 3; ga.c10 = alpha / (4 * mu0); ga.c20 = -alpha / (mu0 * (1 + mu0 / (lambda0 + mu0))); }  // fg:19387-19388
+        else { ga.kind = 5; ga.c10 = alpha / (2 * mu0); ga.c20 = -alpha / (2 * mu0 * (1 + 2 * mu0 / lambda0)); }   // fg:19626-19627
+    }
+    return FGB_OK;
+}
+
+// G0OperatorStaggered* (fg:20101-20153) on the u buffer
+static int g0_staggered(fgb_ctx* c, double mu0, double lambda0, double alpha) {
+    GreenArgs ga;
+    green_args(c, ga, mu0, lambda0, alpha, 0.0);
+    int rc;
+    if ((rc = fgb_fft_z_forward(c, c->ubuf, c->udim))) return rc;
+    if ((rc = fgb_fft_y(c, c->ubuf, c->udim, -1))) return rc;
+    if (c->nranks > 1) rc = fgb_comm_fft_x(c, c->ubuf, c->udim, &ga);
+    else rc = fgb_fft_x(c, c->ubuf, c->udim, 0, &ga);
+    if (rc) return rc;
+    if ((rc = fgb_fft_y(c, c->ubuf, c->udim, +1))) return rc;
+    return fgb_fft_z_backward(c, c->ubuf, c->udim);
+}
+
+static int gamma_impl(fgb_ctx* c, double* field, const double* E, double mu0, double lambda0, double alpha, double beta) {
+    double R[9];
+    int rc = bc_term(c, field, R);
+    if (rc) return rc;
+    double Ec[9];
+    for (int i = 0; i < c->dim; i++) Ec[i] = E[i] + alpha * R[i];                  // applyBCProjector fg:20263-20279
+    if (c->scheme == FGB_GAMMA_STAGGERED) {                                         // GammaOperatorStaggered* fg:20288-20378
+        if (c->nranks > 1 && (rc = fgb_comm_halo_tau(c, field))) return rc;
+        if ((rc = fgb_k_div(c, field, c->ubuf))) return rc;
+        if ((rc = g0_staggered(c, mu0, lambda0, alpha))) return rc;
+        if (c->nranks > 1 && (rc = fgb_comm_halo_u(c))) return rc;
+        return fgb_k_eps(c, c->ubuf, field, Ec);
+    }
+    GreenArgs ga;                                                                   // GammaOperatorCollocated* fg:20302-20340
+    green_args(c, ga, mu0, lambda0, alpha, beta);
+    for (int i = 0; i < c->dim; i++) ga.dc[i] = Ec[i];
+    if ((rc = fgb_fft_z_forward(c, field, c->dim))) return rc;
+    if ((rc = fgb_fft_y(c, field, c->dim, -1))) return rc;
+    if (c->nranks > 1) rc = fgb_comm_fft_x(c, field, c->dim, &ga);
+    else rc = fgb_fft_x(c, field, c->dim, 0, &ga);
+    if (rc) return rc;
+    if ((rc = fgb_fft_y(c, field, c->dim, +1))) return rc;
+    return fgb_fft_z_backward(c, field, c->dim);
+}
+
+// DeltaOperatorStaggered (fg:20422-20460): viscosity dual formulation.  `copy` holds tau (input), field is overwritten.
+static int delta_impl(fgb_ctx* c, double* field, const double* tau_copy, const double* E, double mu0, double alpha) {
+    if (c->scheme != FGB_GAMMA_STAGGERED) return fgb_fail(c, FGB_EUNSUPPORTED, "viscosity mode is implemented for the staggered scheme only");
+    const double m = 1 / (4 * mu0);
+    double mean[9], adj[9];
+    int rc = fgb_k_component_dot(c, tau_copy, nullptr, mean, 1);
+    if (rc) return rc;
+    for (int i = 0; i < 6; i++) adj[i] = E[i] - 2 * alpha * m * mean[i];
+    if ((rc = gamma_impl(c, field, adj, -1.0 / (4 * m), INFINITY, alpha, 0.0))) return rc;
+    return fgb_k_xpay(c, field, field, 2 * alpha * m, tau_copy);
+}
+
+extern "C" int fgb_gamma(fgb_ctx* c, int f, const double* E, double mu0, double lambda0, double alpha, double beta) {
+    CHECK_CTX(c); CHECK_FIELD(c, f);
+    if (c->mode == FGB_MODE_VISCOSITY) return fgb_fail(c, FGB_EUNSUPPORTED, "use fgb_basic_step / fgb_cg_apply in viscosity mode");
+    return gamma_impl(c, c->fields[f], E, mu0, lambda0, alpha, beta);
+}
+
+extern "C" int fgb_div_staggered(fgb_ctx* c, int f) {
+    CHECK_CTX(c); CHECK_FIELD(c, f);
+    if (!c->ubuf) return fgb_fail(c, FGB_EINVAL, "context was not created with the staggered scheme");
+    int rc;
+    if (c->nranks > 1 && (rc = fgb_comm_halo_tau(c, c->fields[f]))) return rc;
+    return fgb_k_div(c, c->fields[f], c->ubuf);
+}
+extern "C" int fgb_g0_staggered(fgb_ctx* c, double mu0, double lambda0, double alpha) {
+    CHECK_CTX(c);
+    if (!c->ubuf) return fgb_fail(c, FGB_EINVAL, "context was not created with the staggered scheme");
+    return g0_staggered(c, mu0, lambda0, alpha);
+}
+extern "C" int fgb_eps_staggered(fgb_ctx* c, int f, const double* E) {
+    CHECK_CTX(c); CHECK_FIELD(c, f);
+    if (!c->ubuf) return fgb_fail(c, FGB_EINVAL, "context was not created with the staggered scheme");
+    int rc;
+    if (c->nranks > 1 && (rc = fgb_comm_halo_u(c))) return rc;
+    return fgb_k_eps(c, c->ubuf, c->fields[f], E);
+}
+extern "C" int fgb_u_upload(fgb_ctx* c, const double* const* comps, int n) {
+    CHECK_CTX(c);
+    if (!c->ubuf || n != c->udim) return fgb_fail(c, FGB_EINVAL, "u buffer has %d components", c->udim);
+    for (int d = 0; d < n; d++)
+        FGB_CUDA(c, cudaMemcpyAsync(c->ubuf + (size_t)d * c->g.plane, comps[d], sizeof(double) * c->g.plane, cudaMemcpyHostToDevice, c->stream));
+    FGB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return FGB_OK;
+}
+extern "C" int fgb_u_download(fgb_ctx* c, double* const* comps, int n) {
+    CHECK_CTX(c);
+    if (!c->ubuf || n != c->udim) return fgb_fail(c, FGB_EINVAL, "u buffer has %d components", c->udim);
+    for (int d = 0; d < n; d++)
+        FGB_CUDA(c, cudaMemcpyAsync(comps[d], c->ubuf + (size_t)d * c->g.plane, sizeof(double) * c->g.plane, cudaMemcpyDeviceToHost, c->stream));
+    FGB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return FGB_OK;
+}
+
+extern "C" int fgb_fft_forward(fgb_ctx* c, int f) {
+    CHECK_CTX(c); CHECK_FIELD(c, f);
+    int rc;
+    if ((rc = fgb_fft_z_forward(c, c->fields[f], c->dim))) return rc;
+    if ((rc = fgb_fft_y(c, c->fields[f], c->dim, -1))) return rc;
+    if (c->nranks > 1) return fgb_fail(c, FGB_EUNSUPPORTED, "plain 3-D transform is single-GPU only (the slab path always fuses the Green operator)");
+    return fgb_fft_x(c, c->fields[f], c->dim, -1, nullptr);
+}
+extern "C" int fgb_fft_backward(fgb_ctx* c, int f) {
+    CHECK_CTX(c); CHECK_FIELD(c, f);
+    int rc;
+    if (c->nranks > 1) return fgb_fail(c, FGB_EUNSUPPORTED, "plain 3-D transform is single-GPU only (the slab path always fuses the Green operator)");
+    if ((rc = fgb_fft_x(c, c->fields[f], c->dim, +1, nullptr))) return rc;
+    if ((rc = fgb_fft_y(c, c->fields[f], c->dim, +1))) return rc;
+    return fgb_fft_z_backward(c, c->fields[f], c->dim);
+}
+
+// ---- scheme-level ----------------------------------------------------------------------------------------------
+static int scratch_field(fgb_ctx* c, double** out) {
+    if (!c->visc_tmp) {
+        cudaError_t e = cudaMalloc(&c->visc_tmp, sizeof(double) * c->g.plane * c->dim);
+        if (e != cudaSuccess) { c->visc_tmp = nullptr; return fgb_fail(c, FGB_ENOMEM, "cannot allocate the viscosity scratch field"); }
+    }
+    *out = c->visc_tmp;
+    return FGB_OK;
+}
+
+// basicScheme fg:20558-20577
+extern "C" int fgb_basic_step(fgb_ctx* c, int src, int dst, const double* E, double mu0, double lambda0) {
+    CHECK_CTX(c); CHECK_FIELD(c, src); CHECK_FIELD(c, dst);
+    int rc;
+    if (c->bc_relax != 1.0 && (rc = fgb_k_component_dot(c, c->fields[src], nullptr, c->F00, 1))) return rc;   // fg:20563-20565
+    if ((rc = fgb_k_calc_stress(c, c->fields[src], c->fields[dst], mu0, lambda0, 1.0))) return rc;            // calcStressDiff fg:18030
+    if (c->mode == FGB_MODE_VISCOSITY) {
+        double* tmp;
+        if ((rc = scratch_field(c, &tmp))) return rc;
+        if ((rc = fgb_k_copy(c, c->fields[dst], tmp, c->dim))) return rc;
+        return delta_impl(c, c->fields[dst], tmp, E, mu0, -1.0);
+    }
+    return gamma_impl(c, c->fields[dst], E, mu0, lambda0, -1.0, 0.0);
+}
+
+// polarizationScheme fg:20536-20553
+extern "C" int fgb_polarization_step(fgb_ctx* c, int src, int dst, const double* P0, double mu0, double lambda0) {
+    CHECK_CTX(c); CHECK_FIELD(c, src); CHECK_FIELD(c, dst);
+    int rc;
+    if (c->bc_relax != 1.0 && (rc = fgb_k_component_dot(c, c->fields[src], nullptr, c->F00, 1))) return rc;
+    if ((rc = fgb_k_calc_polarization(c, c->fields[src], c->fields[dst], mu0, 0))) return rc;
+    double P00[9], E[9];
+    if ((rc = fgb_k_component_dot(c, c->fields[dst], nullptr, P00, 1))) return rc;
+    for (int i = 0; i < c->dim; i++) E[i] = P00[i] + P0[i];
+    return gamma_impl(c, c->fields[dst], E, mu0, lambda0, -4 * mu0, 1.0);
+}
+
+// krylovOperator fg:20583 / ApplyOperator fg:23132 followed by <p, p - w> (fg:23211)
+extern "C" int fgb_cg_apply(fgb_ctx* c, int F, int p, int w, double mu0, double lambda0, double* pAp) {
+    CHECK_CTX(c); CHECK_FIELD(c, p); CHECK_FIELD(c, w);
+    if (p == w) return fgb_fail(c, FGB_EINVAL, "krylovOperator cannot work in place (fg:20581)");
+    int rc;
+    double zero[9] = {0};
+    if (F >= 0) {
+        CHECK_FIELD(c, F);
+        if ((rc = fgb_k_calc_stress_deriv(c, c->fields[F], c->fields[p], c->fields[w], mu0, lambda0, 1.0))) return rc;
+        if ((rc = gamma_impl(c, c->fields[w], zero, mu0, lambda0, -1.0, 0.0))) return rc;
+    } else {
+        if (c->bc_relax != 1.0 && (rc = fgb_k_component_dot(c, c->fields[p], nullptr, c->F00, 1))) return rc;
+        if ((rc = fgb_k_calc_stress(c, c->fields[p], c->fields[w], mu0, lambda0, 1.0))) return rc;
+        if (c->mode == FGB_MODE_VISCOSITY) {
+            double* tmp;
+            if ((rc = scratch_field(c, &tmp))) return rc;
+            if ((rc = fgb_k_copy(c, c->fields[w], tmp, c->dim))) return rc;
+            if ((rc = delta_impl(c, c->fields[w], tmp, zero, mu0, -1.0))) return rc;
+        } else if ((rc = gamma_impl(c, c->fields[w], zero, mu0, lambda0, -1.0, 0.0))) return rc;
+    }
+    if (pAp) return fgb_k_inner(c, c->fields[p], c->fields[p], c->fields[w], pAp);
+    return FGB_OK;
+}
+
+extern "C" int fgb_cg_update(fgb_ctx* c, int x, int r, int p, int w, double a, double* delta) {
+    CHECK_CTX(c); CHECK_FIELD(c, x); CHECK_FIELD(c, r); CHECK_FIELD(c, p); CHECK_FIELD(c, w);
+    return fgb_k_cg_update(c, c->fields[x], c->fields[r], c->fields[p], c->fields[w], a, delta);
+}
+
+extern "C" int fgb_cg_direction(fgb_ctx* c, int p, int r, double beta) {
+    CHECK_CTX(c); CHECK_FIELD(c, p); CHECK_FIELD(c, r);
+    return fgb_k_xpay(c, c->fields[p], c->fields[r], beta, c->fields[p]);                      // p = r + beta*p fg:23245
+}
+
+extern "C" int fgb_check_numeric(fgb_ctx* c) { CHECK_CTX(c); return poll_flag(c); }
+
+// ---- instrumentation ---------------------------------------------------------------------------------------------
+extern "C" uint64_t fgb_launch_count(const fgb_ctx* c) { return c ? c->launches : 0; }
+extern "C" void fgb_launch_count_reset(fgb_ctx* c) { if (c) c->launches = 0; }
+extern "C" int fgb_profile_enable(fgb_ctx* c, int on) {
+    CHECK_CTX(c);
+    prof_resolve(c);
+    c->profiling = on != 0;
+    if (on) c->prof.clear();
+    return FGB_OK;
+}
+extern "C" int fgb_profile_get(fgb_ctx* c, const char* kernel, double* total_ms, uint64_t* launches) {
+    CHECK_CTX(c);
+    prof_resolve(c);
+    auto it = c->prof.find(kernel);
+    if (it == c->prof.end()) { if (total_ms) *total_ms = 0; if (launches) *launches = 0; return FGB_OK; }
+    if (total_ms) *total_ms = it->second.ms;
+    if (launches) *launches = it->second.launches;
+    return FGB_OK;
+}
+extern "C" int fgb_profile_names(fgb_ctx* c, char* buf, int buflen) {
+    CHECK_CTX(c);
+    prof_resolve(c);
+    std::string s;
+    for (auto& kv : c->prof) { if (!s.empty()) s += ","; s += kv.first; }
+    snprintf(buf, buflen, "%s", s.c_str());
+    return FGB_OK;
+}

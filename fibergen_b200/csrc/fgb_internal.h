@@ -1,0 +1,186 @@
+// Internal declarations shared by the CUDA translation units of libfgb200.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <map>
+#include "../../include/fgb200.h"
+
+#define FGB_MAX_STAGES 24
+#define FGB_MAX_LAW_PARAMS 36
+
+struct FftPlanDev {
+    int n;
+    int nstages;
+    int radix[FGB_MAX_STAGES];
+    const double2* tw;     // exp(-2 pi i k / n), k = 0..n-1 (device)
+};
+
+struct LawDev {
+    int id;
+    double p[FGB_MAX_LAW_PARAMS];
+};
+
+struct LaminateParams {
+    double eps_t, eps_a, eps_g, alpha, beta, delta, fixed_c1;
+    int maxiter, backtrack, project_t;
+};
+
+// everything the material kernels need, passed by value
+struct MaterialDev {
+    int nphases;
+    int mix;
+    const double* phi[FGB_MAX_PHASES];
+    LawDev law[FGB_MAX_PHASES];
+    const double* normals[3];
+    const double* orient[3];
+    LaminateParams lam;
+};
+
+struct GridDev {
+    int nx, ny, nz, nzc, nzp;   // global sizes
+    int lnx, x0;                // local slab
+    size_t plane;               // lnx*ny*nzp (doubles per component)
+    double hx, hy, hz;          // nx/Lx ... (inverse voxel size, fg:18618-18620)
+};
+
+struct ProfEntry {
+    double ms = 0;
+    uint64_t launches = 0;
+};
+
+struct fgb_ctx {
+    GridDev g;
+    double L[3];
+    int mode, scheme, dim, udim;
+    int device;
+    int rank, nranks;
+    int sm_count;
+    size_t smem_optin;
+    cudaStream_t stream, own_stream;
+    std::string err;
+
+    double* fields[FGB_MAX_FIELDS];
+    double* ubuf;               // udim planes (staggered displacement / rhs)
+    double* phi[FGB_MAX_PHASES];
+    double* normals;            // 3 planes or null
+    double* orient;             // 3 planes or null
+    int nphases;
+    int mix;
+    LawDev laws[FGB_MAX_PHASES];
+    LaminateParams lam;
+    int freq_hack;
+
+    // FFT plans + frequency tables
+    FftPlanDev plan[3];         // x, y, z
+    double2* tw_dev[3];
+    double* kpm_dev[3];         // staggered: sin(xi)/h per index     (fg:19856-19876)
+    double2* kp_dev[3];         // staggered: kpm*exp(i xi)
+    double* xi_dev[3];          // collocated: m/L per index           (fg:19393-19406)
+
+    // reductions
+    double* d_partials;         // [nblocks][32]
+    double* d_result;           // [32]
+    double* h_result;           // pinned [32]
+    int red_blocks;
+    double* d_scalars;          // device-resident CG scalars
+    int* d_flag;                // numeric error flag
+    int* h_flag;
+
+    // multi-GPU
+    void* nccl_comm;            // ncclComm_t
+    double* xbuf;               // transposed complex buffer (y-slab layout)
+    double* halo;               // halo planes
+
+    // mixed boundary conditions (fgb_set_bc): row-major dim x dim matrices MQ and M:(QC0)
+    bool bc_active;
+    double bc_relax;
+    double bc_MQ[81], bc_MQC0[81];
+    double F00[9];
+    double* visc_tmp;           // copy of tau for the viscosity Delta operator (fg:21316-21320)
+
+    uint64_t launches;
+    bool profiling;
+    std::map<std::string, ProfEntry> prof;
+    cudaEvent_t ev0, ev1;
+};
+
+// error helpers -----------------------------------------------------------------------------
+int fgb_fail(fgb_ctx* ctx, int code, const char* fmt, ...);
+#define FGB_CUDA(ctx, call)                                                                  \
+    do {                                                                                     \
+        cudaError_t e__ = (call);                                                            \
+        if (e__ != cudaSuccess)                                                              \
+            return fgb_fail(ctx, FGB_ECUDA, "%s failed: %s (%s:%d)", #call,                  \
+                            cudaGetErrorString(e__), __FILE__, __LINE__);                    \
+    } while (0)
+#define FGB_CHECK_LAUNCH(ctx, name)                                                          \
+    do {                                                                                     \
+        (ctx)->launches++;                                                                   \
+        cudaError_t e__ = cudaGetLastError();                                                \
+        if (e__ != cudaSuccess)                                                              \
+            return fgb_fail(ctx, FGB_ECUDA, "launch of %s failed: %s", name,                 \
+                            cudaGetErrorString(e__));                                        \
+    } while (0)
+
+struct ProfScope {
+    fgb_ctx* c;
+    const char* name;
+    ProfScope(fgb_ctx* ctx, const char* n);
+    ~ProfScope();
+};
+
+// fft.cu -------------------------------------------------------------------------------------
+int fgb_fft_init(fgb_ctx* ctx);
+void fgb_fft_free(fgb_ctx* ctx);
+// in-place r2c/c2r along z of `ncomp` planes starting at base (plane stride ctx->g.plane)
+int fgb_fft_z_forward(fgb_ctx* ctx, double* base, int ncomp);
+int fgb_fft_z_backward(fgb_ctx* ctx, double* base, int ncomp);
+int fgb_fft_y(fgb_ctx* ctx, double* base, int ncomp, int dir);
+// x pass; green_kind: 0 none (plain forward or backward per dir), otherwise fused fwd-x, Green, inv-x
+struct GreenArgs {
+    int kind;             // 0 none, 1 staggered elasticity/hyper (general), 2 staggered heat, 3 colloc elasticity, 4 colloc heat, 5 colloc hyper
+    double c10, c20;      // staggered coefficients / collocated c10, c20
+    double beta;          // collocated beta
+    double dc[9];         // value of the zero frequency
+    int freq_hack;
+};
+int fgb_fft_x(fgb_ctx* ctx, double* base, int ncomp, int dir, const GreenArgs* ga);
+
+// stencil.cu ---------------------------------------------------------------------------------
+int fgb_k_div(fgb_ctx* ctx, const double* tau, double* u);
+int fgb_k_eps(fgb_ctx* ctx, const double* u, double* eta, const double* Econst /*dim, host*/);
+
+// material.cu --------------------------------------------------------------------------------
+MaterialDev fgb_material_dev(fgb_ctx* ctx);
+int fgb_k_calc_stress(fgb_ctx* ctx, const double* src, double* dst, double mu0, double lambda0, double alpha);
+int fgb_k_calc_stress_deriv(fgb_ctx* ctx, const double* F, const double* W, double* dst, double mu0, double lambda0, double alpha);
+int fgb_k_calc_polarization(fgb_ctx* ctx, const double* src, double* dst, double mu0, int inv);
+int fgb_k_mean_pk1(fgb_ctx* ctx, const double* src, double alpha, double* out);
+int fgb_k_mean_energy(fgb_ctx* ctx, const double* src, double* out);
+int fgb_k_min_detF(fgb_ctx* ctx, const double* src, double* out);
+int fgb_k_ref_material(fgb_ctx* ctx, const double* src, int zero_trace, double* lmin, double* lmax);
+
+// blas.cu ------------------------------------------------------------------------------------
+int fgb_k_set_constant(fgb_ctx* ctx, double* f, const double* c, int add);
+int fgb_k_copy(fgb_ctx* ctx, const double* src, double* dst, int ncomp);
+int fgb_k_xpay(fgb_ctx* ctx, double* r, const double* x, double a, const double* y);
+int fgb_k_xpaymz(fgb_ctx* ctx, double* r, const double* x, double a, const double* y, const double* z);
+int fgb_k_adjust_residual(fgb_ctx* ctx, double* r, const double* E, const double* z);
+int fgb_k_calc_stress_const(fgb_ctx* ctx, const double* src, double* dst, double mu0, double lambda0);
+int fgb_k_inner(fgb_ctx* ctx, const double* a, const double* b, const double* c, double* out);
+int fgb_k_component_dot(fgb_ctx* ctx, const double* a, const double* b, double* out, int mean_only);
+int fgb_k_cg_update(fgb_ctx* ctx, double* x, double* r, const double* p, const double* w, double a, double* delta);
+// finish a block-partial reduction of `nvals` sums (or mins/maxs) and copy to host; op 0 sum, 1 min, 2 max
+int fgb_reduce_finish(fgb_ctx* ctx, int nblocks, int nvals, int op, double* host_out);
+int fgb_allreduce_host(fgb_ctx* ctx, double* vals, int n, int op);
+
+// comm.cu ------------------------------------------------------------------------------------
+int fgb_comm_free(fgb_ctx* ctx);
+// slab-partitioned x pass: transpose -> fwd x, Green, inv x -> transpose back
+int fgb_comm_fft_x(fgb_ctx* ctx, double* base, int ncomp, const GreenArgs* ga);
+int fgb_comm_halo_tau(fgb_ctx* ctx, const double* tau);   // fills ctx->halo for k_div
+int fgb_comm_halo_u(fgb_ctx* ctx);                        // fills ctx->halo for k_eps

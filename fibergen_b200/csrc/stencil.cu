@@ -1,0 +1,174 @@
+// Staggered-grid finite-difference operators.
+//   div : divOperatorStaggered fg:18853-18908, ...Heat fg:18914-18968, ...Hyper fg:19016-19071
+//   eps : epsOperatorStaggered fg:18614-18692, ...Heat fg:18697-18757, ...Hyper fg:18763-18846
+// D+ a(i) = (a(i+1)-a(i))*h, D- a(i) = (a(i)-a(i-1))*h, periodic (offset tables fg:14867-14891), h = n/L.
+// Unlike the reference (in place, barriers fg:18642) the rhs / displacement lives in its own buffer `u`,
+// so there is no in-place hazard.  With an x-slab partition the i-1 / i+1 planes of the neighbour ranks
+// come from the halo buffers filled by comm.cu.
+#include "fgb_internal.h"
+
+struct StencilArgs {
+    GridDev g;
+    // halo planes (ny*nzp doubles per component) for i = -1 and i = lnx; null when nranks == 1
+    const double* halo_lo;   // components packed as needed by the kernel
+    const double* halo_hi;
+};
+
+__device__ __forceinline__ const double* plane_ptr(const double* f, const GridDev& g, int c) { return f + (size_t)c * g.plane; }
+
+// value of component plane `p` at (i+di, j, k) with periodic wrap in x or halo access
+__device__ __forceinline__ double at_x(const double* p, const GridDev& g, int i, int j, int k, int di, const double* halo_lo,
+                                       const double* halo_hi) {
+    int ii = i + di;
+    if (halo_lo == nullptr) {
+        if (ii < 0) ii += g.lnx;
+        if (ii >= g.lnx) ii -= g.lnx;
+        return p[((size_t)ii * g.ny + j) * g.nzp + k];
+    }
+    if (ii < 0) return halo_lo[(size_t)j * g.nzp + k];
+    if (ii >= g.lnx) return halo_hi[(size_t)j * g.nzp + k];
+    return p[((size_t)ii * g.ny + j) * g.nzp + k];
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) k_div(const double* __restrict__ tau, double* __restrict__ u, GridDev g,
+                                             const double* __restrict__ halo_lo, const double* __restrict__ halo_hi) {
+    const size_t nvox = (size_t)g.lnx * g.ny * g.nz;
+    const size_t hp = (size_t)g.ny * g.nzp;   // halo plane size
+    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (size_t)gridDim.x * blockDim.x) {
+        const int k = (int)(v % g.nz);
+        const int j = (int)((v / g.nz) % g.ny);
+        const int i = (int)(v / ((size_t)g.nz * g.ny));
+        const size_t o = ((size_t)i * g.ny + j) * g.nzp + k;
+        const int jp = (j + 1 == g.ny) ? 0 : j + 1, jm = (j == 0) ? g.ny - 1 : j - 1;
+        const int kp = (k + 1 == g.nz) ? 0 : k + 1, km = (k == 0) ? g.nz - 1 : k - 1;
+        const size_t o_jp = ((size_t)i * g.ny + jp) * g.nzp + k, o_jm = ((size_t)i * g.ny + jm) * g.nzp + k;
+        const size_t o_kp = ((size_t)i * g.ny + j) * g.nzp + kp, o_km = ((size_t)i * g.ny + j) * g.nzp + km;
+#define T_(c) plane_ptr(tau, g, c)
+        if (D == 3) {
+            // halo_lo: [tau0 at i=-1]
+            double f = (T_(0)[o] - at_x(T_(0), g, i, j, k, -1, halo_lo, halo_hi)) * g.hx;
+            f += (T_(1)[o] - T_(1)[o_jm]) * g.hy;
+            f += (T_(2)[o] - T_(2)[o_km]) * g.hz;
+            u[o] = f;
+        } else {
+            // shear operand indices: elasticity (5,4 | 5,3 | 4,3), hyper (5,4 | 8,3 | 7,6)
+            const int c1x = (D == 6) ? 5 : 8, c2x = (D == 6) ? 4 : 7, c2y = (D == 6) ? 3 : 6;
+            // halo_lo: [tau0 at -1]; halo_hi: [tau(c1x) at lnx, tau(c2x) at lnx]
+            const double f0 = (T_(0)[o] - at_x(T_(0), g, i, j, k, -1, halo_lo, halo_hi)) * g.hx + (T_(5)[o_jp] - T_(5)[o]) * g.hy +
+                              (T_(4)[o_kp] - T_(4)[o]) * g.hz;
+            const double f1 = (at_x(T_(c1x), g, i, j, k, +1, halo_lo, halo_hi) - T_(c1x)[o]) * g.hx + (T_(1)[o] - T_(1)[o_jm]) * g.hy +
+                              (T_(3)[o_kp] - T_(3)[o]) * g.hz;
+            const double f2 = (at_x(T_(c2x), g, i, j, k, +1, halo_lo, halo_hi ? halo_hi + hp : nullptr) - T_(c2x)[o]) * g.hx +
+                              (T_(c2y)[o_jp] - T_(c2y)[o]) * g.hy + (T_(2)[o] - T_(2)[o_km]) * g.hz;
+            u[o] = f0;
+            u[g.plane + o] = f1;
+            u[2 * g.plane + o] = f2;
+        }
+#undef T_
+    }
+}
+
+struct Const9 {
+    double v[9];
+};
+
+template <int D>
+__global__ void __launch_bounds__(256) k_eps(const double* __restrict__ u, double* __restrict__ eta, GridDev g, Const9 E,
+                                             const double* __restrict__ halo_lo, const double* __restrict__ halo_hi) {
+    const size_t nvox = (size_t)g.lnx * g.ny * g.nz;
+    const size_t hp = (size_t)g.ny * g.nzp;
+    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (size_t)gridDim.x * blockDim.x) {
+        const int k = (int)(v % g.nz);
+        const int j = (int)((v / g.nz) % g.ny);
+        const int i = (int)(v / ((size_t)g.nz * g.ny));
+        const size_t o = ((size_t)i * g.ny + j) * g.nzp + k;
+        const int jp = (j + 1 == g.ny) ? 0 : j + 1, jm = (j == 0) ? g.ny - 1 : j - 1;
+        const int kp = (k + 1 == g.nz) ? 0 : k + 1, km = (k == 0) ? g.nz - 1 : k - 1;
+        const size_t o_jp = ((size_t)i * g.ny + jp) * g.nzp + k, o_jm = ((size_t)i * g.ny + jm) * g.nzp + k;
+        const size_t o_kp = ((size_t)i * g.ny + j) * g.nzp + kp, o_km = ((size_t)i * g.ny + j) * g.nzp + km;
+#define U_(c) (u + (size_t)(c)*g.plane)
+        // halo_lo: [u0,u1,u2 at i=-1], halo_hi: [u0 at i=lnx]
+        if (D == 3) {
+            const double u0 = U_(0)[o];
+            eta[o] = E.v[0] + (at_x(U_(0), g, i, j, k, +1, halo_lo, halo_hi) - u0) * g.hx;
+            eta[g.plane + o] = E.v[1] + (U_(0)[o_jp] - u0) * g.hy;
+            eta[2 * g.plane + o] = E.v[2] + (U_(0)[o_kp] - u0) * g.hz;
+        } else {
+            const double u0 = U_(0)[o], u1 = U_(1)[o], u2 = U_(2)[o];
+            const double u0_xm = at_x(U_(0), g, i, j, k, -1, halo_lo, halo_hi);
+            const double u1_xm = at_x(U_(1), g, i, j, k, -1, halo_lo ? halo_lo + hp : nullptr, halo_hi);
+            const double u2_xm = at_x(U_(2), g, i, j, k, -1, halo_lo ? halo_lo + 2 * hp : nullptr, halo_hi);
+            (void)u0_xm;
+            const double e0 = E.v[0] + (at_x(U_(0), g, i, j, k, +1, halo_lo, halo_hi) - u0) * g.hx;
+            const double e1 = E.v[1] + (U_(1)[o_jp] - u1) * g.hy;
+            const double e2 = E.v[2] + (U_(2)[o_kp] - u2) * g.hz;
+            eta[o] = e0;
+            eta[g.plane + o] = e1;
+            eta[2 * g.plane + o] = e2;
+            if (D == 6) {
+                eta[3 * g.plane + o] = E.v[3] + 0.5 * ((u2 - U_(2)[o_jm]) * g.hy + (u1 - U_(1)[o_km]) * g.hz);
+                eta[4 * g.plane + o] = E.v[4] + 0.5 * ((u2 - u2_xm) * g.hx + (u0 - U_(0)[o_km]) * g.hz);
+                eta[5 * g.plane + o] = E.v[5] + 0.5 * ((u1 - u1_xm) * g.hx + (u0 - U_(0)[o_jm]) * g.hy);
+            } else {
+                eta[3 * g.plane + o] = E.v[3] + (u1 - U_(1)[o_km]) * g.hz;
+                eta[4 * g.plane + o] = E.v[4] + (u0 - U_(0)[o_km]) * g.hz;
+                eta[5 * g.plane + o] = E.v[5] + (u0 - U_(0)[o_jm]) * g.hy;
+                eta[6 * g.plane + o] = E.v[6] + (u2 - U_(2)[o_jm]) * g.hy;
+                eta[7 * g.plane + o] = E.v[7] + (u2 - u2_xm) * g.hx;
+                eta[8 * g.plane + o] = E.v[8] + (u1 - u1_xm) * g.hx;
+            }
+        }
+#undef U_
+    }
+}
+
+static unsigned grid_for(const fgb_ctx* ctx, size_t n, int block) {
+    size_t b = (n + block - 1) / block;
+    size_t cap = (size_t)ctx->sm_count * 16;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (unsigned)b;
+}
+
+// halo layout is owned by comm.cu: ctx->halo = [lo planes (3)] [hi planes (3)]
+static void halo_ptrs(fgb_ctx* ctx, const double** lo, const double** hi) {
+    if (ctx->nranks > 1 && ctx->halo) {
+        const size_t hp = (size_t)ctx->g.ny * ctx->g.nzp;
+        *lo = ctx->halo;
+        *hi = ctx->halo + 3 * hp;
+    } else {
+        *lo = nullptr;
+        *hi = nullptr;
+    }
+}
+
+int fgb_k_div(fgb_ctx* ctx, const double* tau, double* u) {
+    const GridDev& g = ctx->g;
+    const size_t nvox = (size_t)g.lnx * g.ny * g.nz;
+    const double *lo, *hi;
+    halo_ptrs(ctx, &lo, &hi);
+    ProfScope ps(ctx, "div_staggered");
+    const unsigned grid = grid_for(ctx, nvox, 256);
+    if (ctx->dim == 3) k_div<3><<<grid, 256, 0, ctx->stream>>>(tau, u, g, lo, hi);
+    else if (ctx->dim == 6) k_div<6><<<grid, 256, 0, ctx->stream>>>(tau, u, g, lo, hi);
+    else k_div<9><<<grid, 256, 0, ctx->stream>>>(tau, u, g, lo, hi);
+    FGB_CHECK_LAUNCH(ctx, "k_div");
+    return FGB_OK;
+}
+
+int fgb_k_eps(fgb_ctx* ctx, const double* u, double* eta, const double* Econst) {
+    const GridDev& g = ctx->g;
+    const size_t nvox = (size_t)g.lnx * g.ny * g.nz;
+    Const9 E;
+    for (int i = 0; i < 9; i++) E.v[i] = (i < ctx->dim) ? Econst[i] : 0.0;
+    const double *lo, *hi;
+    halo_ptrs(ctx, &lo, &hi);
+    ProfScope ps(ctx, "eps_staggered");
+    const unsigned grid = grid_for(ctx, nvox, 256);
+    if (ctx->dim == 3) k_eps<3><<<grid, 256, 0, ctx->stream>>>(u, eta, g, E, lo, hi);
+    else if (ctx->dim == 6) k_eps<6><<<grid, 256, 0, ctx->stream>>>(u, eta, g, E, lo, hi);
+    else k_eps<9><<<grid, 256, 0, ctx->stream>>>(u, eta, g, E, lo, hi);
+    FGB_CHECK_LAUNCH(ctx, "k_eps");
+    return FGB_OK;
+}

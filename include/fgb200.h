@@ -1,0 +1,202 @@
+/*
+ * fgb200.h -- C ABI of the B200-native Lippmann-Schwinger solve loop of fibergen.
+ *
+ * Drop-in boundary for the hot path of fospald/fibergen.  The reference has
+ * no plugin/FFI seam for this path: LSSolver<T,P,DIM> (fibergen.cpp, "fg") calls its own members.
+ * This header is the seam a maintainer inserts between the scheme drivers
+ * (runBasic fg:21716, runPolarization fg:21808, runCGElasticity fg:23153, runCGHyper fg:22699)
+ * and everything they call.  Every entry point names the reference member(s) it replaces.
+ *
+ * Conventions
+ *   - plain C, no exceptions cross the boundary: every call returns 0 or a negative FGB_E* code,
+ *     the message is available from fgb_last_error() (reference: set_exception, fg:396).
+ *   - all host pointers are caller-owned and only read/written during the call.
+ *   - fields live on the device in the reference layout (fg:9549-9579, fg:227-232): `dim` planes of
+ *     nx*ny*nzp doubles, nzp = 2*(nz/2+1), index (i*ny + j)*nzp + k; the complex shadow
+ *     (fg:9707) is nx*ny*nzc complex numbers, nzc = nz/2+1, aliasing the same memory.
+ *   - component order 11,22,33,23,13,12,32,31,21 (fg:9103); dim = 3 (heat/porous), 6 (elasticity,
+ *     viscosity), 9 (hyperelasticity) (fg:14980-14997).
+ *   - there is NO CPU fallback: fgb_create fails without an sm_100 device.
+ */
+#ifndef FGB200_H
+#define FGB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fgb_ctx fgb_ctx;
+
+/* error codes */
+#define FGB_OK            0
+#define FGB_EINVAL       -1   /* bad argument / unsupported combination            */
+#define FGB_ENODEV       -2   /* no CUDA device of compute capability 10.x         */
+#define FGB_ENOMEM       -3   /* device allocation failed                          */
+#define FGB_ECUDA        -4   /* CUDA runtime error (message has the detail)       */
+#define FGB_EUNSUPPORTED -5   /* feature the reference has but this path refuses   */
+#define FGB_ENUMERIC     -6   /* NaN / domain error flagged on the device (fg:10293, fg:21202) */
+#define FGB_ECOMM        -7   /* multi-GPU communicator error                      */
+
+/* LSSolver::_mode (fg:14698) */
+#define FGB_MODE_ELASTICITY      0
+#define FGB_MODE_HYPERELASTICITY 1
+#define FGB_MODE_VISCOSITY       2
+#define FGB_MODE_HEAT            3
+#define FGB_MODE_POROUS          4
+
+/* LSSolver::_gamma_scheme (fg:14697); others -> FGB_EUNSUPPORTED */
+#define FGB_GAMMA_COLLOCATED 0
+#define FGB_GAMMA_STAGGERED  1
+
+/* material laws (fg:15211-15294) with their parameter vectors */
+#define FGB_LAW_ISO      0  /* LinearIsotropicMaterialLaw fg:11354           params: mu, lambda            */
+#define FGB_LAW_GENERAL  1  /* LinearGeneralMaterialLaw fg:11233             params: C[36] row-major       */
+#define FGB_LAW_TISO     2  /* LinearTransverselyIsotropic fg:11479          params: 2mu, lambda, alpha, beta, 2dmu */
+#define FGB_LAW_SCALAR   3  /* ScalarLinearIsotropicMaterialLaw fg:11161     params: mu                    */
+#define FGB_LAW_ANISO3   4  /* MatrixLinearAnisotropicMaterialLaw fg:11089   params: c11,c22,c33,c23,c13,c12 */
+#define FGB_LAW_SVK      5  /* SaintVenantKirchhoffMaterialLaw fg:11598      params: mu, lambda            */
+#define FGB_LAW_NH       6  /* NeoHookeMaterialLaw fg:11729                  params: mu, lambda            */
+#define FGB_LAW_NH2      7  /* NeoHooke2MaterialLaw fg:11867                 params: mu, K                 */
+
+/* mixing rules (fg:14975-15042) */
+#define FGB_MIX_VOIGT    0  /* VoigtMixedMaterialLaw fg:12729    */
+#define FGB_MIX_REUSS    1  /* ReussMixedMaterialLaw fg:12653    */
+#define FGB_MIX_LAMINATE 2  /* LaminateMixedMaterialLaw fg:13086 (tangent="approx") */
+
+#define FGB_MAX_PHASES 8
+#define FGB_MAX_FIELDS 12
+
+/* ---- context ------------------------------------------------------------------------------ */
+
+/* One context per LSSolver (created where _epsilon is allocated, fg:15153).
+ * rank/nranks describe the x-slab partition: this process owns
+ * i in [rank*nx/nranks, (rank+1)*nx/nranks).  nranks == 1 for a single GPU.
+ * device < 0 selects the current CUDA device. */
+int  fgb_create(fgb_ctx** out, int nx, int ny, int nz, double Lx, double Ly, double Lz,
+                int mode, int gamma_scheme, int device, int rank, int nranks);
+void fgb_destroy(fgb_ctx* ctx);
+const char* fgb_last_error(const fgb_ctx* ctx);     /* ctx may be NULL: last creation error */
+const char* fgb_version(void);
+
+/* Use an externally owned cudaStream_t for all launches (0 = the context's own stream). */
+int  fgb_set_stream(fgb_ctx* ctx, void* cuda_stream);
+int  fgb_synchronize(fgb_ctx* ctx);
+
+/* Multi-GPU: the library talks NCCL itself.  Rank 0 calls fgb_comm_unique_id, the host side
+ * broadcasts the 128 bytes (torch.distributed / MPI / a file), every rank calls fgb_comm_init. */
+int  fgb_comm_unique_id(void* id128);
+int  fgb_comm_init(fgb_ctx* ctx, const void* id128);
+
+/* geometry of the local slab */
+int  fgb_local_nx(const fgb_ctx* ctx);        /* number of local x-planes            */
+int  fgb_local_x0(const fgb_ctx* ctx);        /* first global x index of this rank   */
+size_t fgb_plane_elems(const fgb_ctx* ctx);   /* local_nx*ny*nzp doubles per component */
+int  fgb_dim(const fgb_ctx* ctx);             /* tensor components: 3, 6 or 9 (fg:14980-14997) */
+
+/* ---- fields ------------------------------------------------------------------------------- */
+
+/* TensorField(nx,ny,nz,dim) (fg:9584): returns a field id >= 0 or an error code. */
+int  fgb_field_alloc(fgb_ctx* ctx);
+int  fgb_field_free(fgb_ctx* ctx, int field);
+/* host <-> device in the padded plane layout; comps[c] points to local_nx*ny*nzp doubles (fg:15396 get_raw_field) */
+int  fgb_field_upload(fgb_ctx* ctx, int field, const double* const* comps);
+int  fgb_field_download(fgb_ctx* ctx, int field, double* const* comps);
+void* fgb_field_device_ptr(fgb_ctx* ctx, int field, int comp);   /* for zero-copy interop */
+
+/* ---- setup (LSSolver::readSettings fg:15044, initPhi fg:17489) ------------------------------ */
+
+int  fgb_set_num_phases(fgb_ctx* ctx, int nphases);
+/* Phase::phi (fg:12010): one padded plane per phase */
+int  fgb_set_phase(fgb_ctx* ctx, int phase, const double* phi_plane);
+int  fgb_set_law(fgb_ctx* ctx, int phase, int law_id, const double* params, int nparams);
+/* get_normals()/get_orientation() (fg:14911-14937): 3 padded planes each */
+int  fgb_set_normals(fgb_ctx* ctx, const double* const* comps3);
+int  fgb_set_orientation(fgb_ctx* ctx, const double* const* comps3);
+/* mixing rule + LaminateMixedMaterialLaw settings (fg:13110-13145):
+ * lam_params = {eps_t, eps_a, eps_g, alpha, beta, delta, maxiter, backtrack, project_t, fixed_c1} or NULL for defaults */
+int  fgb_set_mixing(fgb_ctx* ctx, int rule_id, const double* lam_params, int nparams);
+/* freq_hack (fg:19392-19394) for the collocated elasticity operator */
+int  fgb_set_freq_hack(fgb_ctx* ctx, int on);
+
+/* ---- operator-level entry points (parity tests, post-processing) ---------------------------- */
+
+/* TensorField BLAS-1 (fg:9799-10066) */
+int  fgb_set_constant(fgb_ctx* ctx, int field, const double* c);                 /* setConstant fg:10047 */
+int  fgb_add_constant(fgb_ctx* ctx, int field, const double* c);                 /* add fg:9841          */
+int  fgb_copy(fgb_ctx* ctx, int src, int dst);                                   /* copyTo fg:9669       */
+int  fgb_xpay(fgb_ctx* ctx, int r, int x, double a, int y);                      /* r = x + a*y      fg:9819 */
+int  fgb_xpaymz(fgb_ctx* ctx, int r, int x, double a, int y, int z);             /* r = x + a*(y-z)  fg:9993 */
+int  fgb_adjust_residual(fgb_ctx* ctx, int r, const double* E, int z);           /* r += E - z       fg:10012 */
+
+/* reductions; results are global over all ranks (fixed combine order) */
+int  fgb_inner(fgb_ctx* ctx, int a, int b, int c_or_neg, double* out);           /* innerProductL2 fg:20871/20955 */
+int  fgb_average(fgb_ctx* ctx, int field, double* out_dim);                      /* average fg:10171        */
+int  fgb_component_dot(fgb_ctx* ctx, int a, int b, double* out_dim);             /* component_dot fg:10088  */
+int  fgb_mean_pk1(fgb_ctx* ctx, int field, double alpha, double* out_dim);       /* meanPK1 fg:12312        */
+int  fgb_mean_energy(fgb_ctx* ctx, int field, double* out);                      /* meanW fg:12239          */
+int  fgb_min_detF(fgb_ctx* ctx, int field, double* out);                         /* calcMinDetF fg:17871    */
+/* getRefMaterial (fg:12153-12236): min/max eigenvalue of the tangent over all voxels */
+int  fgb_ref_material(fgb_ctx* ctx, int field, int zero_trace, double* lmin, double* lmax);
+
+/* constitutive sweeps */
+int  fgb_calc_stress(fgb_ctx* ctx, int src, int dst, double mu0, double lambda0, double alpha);        /* calcStress fg:18134      */
+int  fgb_calc_stress_deriv(fgb_ctx* ctx, int F, int W, int dst, double mu0, double lambda0, double alpha); /* calcStressDeriv fg:18425 */
+int  fgb_calc_stress_const(fgb_ctx* ctx, int src, int dst, double mu0, double lambda0);               /* calcStressConst fg:17973 */
+int  fgb_calc_polarization(fgb_ctx* ctx, int src, int dst, double mu0, int inv);                       /* calcPolarization fg:18044 */
+
+/* Mixed boundary conditions (setBCProjector fg:20599-20665): the host keeps the small-matrix algebra and hands
+ * over the two dim x dim row-major matrices the operator needs, MQ = M:Q and M_QC0 = M:(Q:C0), plus bc_relax.
+ * Every Green-operator application then adds alpha*R, R = bc_relax*MQ:<tau> - (1-bc_relax)*M_QC0:<eps_in>
+ * (initBCProjector fg:20220/20228, calcBCProjector fg:20258, applyBCProjector fg:20263/20272).
+ * NULL matrices (or ||MQ|| < eps, fg:20233) disable the term and its mean pass. */
+int  fgb_set_bc(fgb_ctx* ctx, const double* MQ, const double* M_QC0, double bc_relax);
+
+/* Green operator, in place on `field` (GammaOperator fg:20488-20531):
+ *   collocated: eta^ = alpha*Gamma0^:tau^ + beta*tau^, eta^(0) = E + alpha*R
+ *   staggered : eta = E + grad_h G0 div_h tau + alpha*R (beta ignored, as in the reference) */
+int  fgb_gamma(fgb_ctx* ctx, int field, const double* E, double mu0, double lambda0, double alpha, double beta);
+/* the individual stages, exposed for the operator-identity tests of fibergen --test (fg:23946-24583) */
+int  fgb_div_staggered(fgb_ctx* ctx, int field);                                 /* divOperatorStaggered* fg:18853-19071: field -> u buffer */
+int  fgb_g0_staggered(fgb_ctx* ctx, double mu0, double lambda0, double alpha);   /* G0OperatorStaggered* fg:20101-20153 on the u buffer     */
+int  fgb_eps_staggered(fgb_ctx* ctx, int field, const double* E);                /* epsOperatorStaggered* fg:18614-18846: u buffer -> field */
+int  fgb_u_upload(fgb_ctx* ctx, const double* const* comps, int ncomp);          /* test access to the displacement buffer */
+int  fgb_u_download(fgb_ctx* ctx, double* const* comps, int ncomp);
+/* fftTensor / fftInvTensor (fg:18531-18584) on all components of a field, in place (forward scaled by 1/nxyz) */
+int  fgb_fft_forward(fgb_ctx* ctx, int field);
+int  fgb_fft_backward(fgb_ctx* ctx, int field);
+
+/* ---- scheme-level entry points: one iteration on the device ---------------------------------- */
+
+/* basicScheme (fg:20558): dst = E - Gamma0:(C - C0):src (+ BC terms, fgb_set_bc); src == dst allowed (fg:21786).
+ * In viscosity mode this is the Delta operator (DeltaOperatorStaggered fg:20422). */
+int  fgb_basic_step(fgb_ctx* ctx, int src, int dst, const double* E, double mu0, double lambda0);
+/* polarizationScheme (fg:20536): dst = (-4mu0*Gamma0 + 1):Q(src) with mean <Q> + P0; src == dst allowed */
+int  fgb_polarization_step(fgb_ctx* ctx, int src, int dst, const double* P0, double mu0, double lambda0);
+
+/* CG (runCGElasticity fg:23153-23247, inner loop of runCGHyper fg:22844-23088).
+ * fgb_cg_apply: w = -Gamma0:(C-C0):p  (krylovOperator fg:20583) or, with F >= 0,
+ *               w = -Gamma0:(dP/dF(F)-C0):p (ApplyOperator fg:23132); pAp (may be NULL) receives <p, p - w>.
+ * fgb_cg_update: x += a*p ; r -= a*(p - w) ; returns delta = <r, r>          (fg:23221, fg:23237-23240)
+ * fgb_cg_direction: p = r + beta*p                                          (fg:23245)            */
+int  fgb_cg_apply(fgb_ctx* ctx, int F_or_neg, int p, int w, double mu0, double lambda0, double* pAp);
+int  fgb_cg_update(fgb_ctx* ctx, int x, int r, int p, int w, double a, double* delta);
+int  fgb_cg_direction(fgb_ctx* ctx, int p, int r, double beta);
+/* returns FGB_ENUMERIC if a material law flagged a domain error since the last call (fg:10293, fg:21202) */
+int  fgb_check_numeric(fgb_ctx* ctx);
+
+/* ---- instrumentation ------------------------------------------------------------------------- */
+/* number of kernels launched by this context since creation / last reset */
+uint64_t fgb_launch_count(const fgb_ctx* ctx);
+void     fgb_launch_count_reset(fgb_ctx* ctx);
+/* time (ms) and launches of the dominant kernels accumulated with CUDA events when profiling is on */
+int  fgb_profile_enable(fgb_ctx* ctx, int on);
+int  fgb_profile_get(fgb_ctx* ctx, const char* kernel, double* total_ms, uint64_t* launches);
+int  fgb_profile_names(fgb_ctx* ctx, char* buf, int buflen);   /* comma separated kernel names seen so far */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FGB200_H */

@@ -1,0 +1,232 @@
+"""Operator-level parity: every CUDA kernel reached through the C ABI (fgb_*) against the CPU oracle on the
+same seeded inputs, on the reference's own test grids (2x1x1, 41x33x11 with L=1 and L=n, fg:27259-27273),
+degenerate 2-D / 1-D grids used by the demos, and power-of-two cubes.  FP64 tolerances are written per test."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import fg_oracle as fo
+import fibergen_b200 as fb
+from microstructures import sphere_phi, sphere_normals
+
+pytestmark = pytest.mark.gpu
+
+GRIDS = [((2, 1, 1), (1., 1., 1.)), ((41, 33, 11), (1., 1., 1.)), ((41, 33, 11), (41., 33., 11.)),
+         ((10, 1, 1), (1., 1., 1.)), ((12, 9, 1), (1., 2., 1.)), ((16, 16, 16), (1., 1., 1.)),
+         ((32, 8, 20), (2., 1., 3.)), ((7, 5, 3), (1., 1., 1.))]
+MODES = [("elasticity", 6), ("heat", 3), ("hyperelasticity", 9)]
+MU0, LAM0 = 1324.3, 324.2      # reference material of fibergen --test (fg:24007-24008)
+
+
+def relerr(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.mark.parametrize("n,L", GRIDS)
+def test_fft_forward_backward(n, L):
+    """FFT3<double>::forward + 1/nxyz scaling and ::backward (fg:7232-7244, fg:18531-18584)"""
+    ctx = fb.Context(*n, *L, mode="elasticity", gamma_scheme="collocated")
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((6,) + n)
+    f = ctx.field(x)
+    ctx.chk(ctx.lib.fgb_fft_forward(ctx.h, f))
+    got = ctx.download_padded(f)
+    got_c = got.reshape(6, n[0], n[1], -1, 2)
+    got_c = got_c[..., 0] + 1j * got_c[..., 1]
+    o = fo.LSSolver(*n, *L)
+    want = o.fft(x)
+    assert relerr(got_c, want) < 5e-14
+    ctx.chk(ctx.lib.fgb_fft_backward(ctx.h, f))
+    assert relerr(ctx.download(f), x) < 5e-14
+    ctx.close()
+
+
+@pytest.mark.parametrize("n,L", GRIDS)
+@pytest.mark.parametrize("mode,d", MODES)
+def test_div_eps_staggered(n, L, mode, d):
+    """divOperatorStaggered* (fg:18853-19071) and epsOperatorStaggered* (fg:18614-18846)"""
+    ctx = fb.Context(*n, *L, mode=mode, gamma_scheme="staggered")
+    o = fo.LSSolver(*n, *L, mode=mode, gamma_scheme="staggered")
+    rng = np.random.default_rng(1)
+    tau = rng.standard_normal((d,) + n)
+    f = ctx.field(tau)
+    ctx.chk(ctx.lib.fgb_div_staggered(ctx.h, f))
+    want = o.divOperatorStaggered(tau)
+    assert relerr(ctx.u_download(), want) < 1e-13
+    u = rng.standard_normal((ctx.udim,) + n)
+    E = rng.standard_normal(d)
+    ctx.u_upload(u)
+    ctx.chk(ctx.lib.fgb_eps_staggered(ctx.h, f, fb.solver._dp(ctx.vec(E))))
+    assert relerr(ctx.download(f), o.epsOperatorStaggered(E, u)) < 1e-13
+    ctx.close()
+
+
+@pytest.mark.parametrize("n,L", GRIDS)
+@pytest.mark.parametrize("mode,d", MODES)
+@pytest.mark.parametrize("scheme", ["staggered", "collocated"])
+def test_gamma_operator(n, L, mode, d, scheme):
+    """GammaOperator (fg:20488-20531) incl. the Fourier-space Green operators (fg:19302-19927)"""
+    ctx = fb.Context(*n, *L, mode=mode, gamma_scheme=scheme)
+    o = fo.LSSolver(*n, *L, mode=mode, gamma_scheme=scheme)
+    rng = np.random.default_rng(2)
+    tau = rng.standard_normal((d,) + n)
+    E = rng.standard_normal(d)
+    for (mu0, lam0, alpha, beta) in [(MU0, LAM0, 1.0, 0.0), (0.7, 0.0, -1.0, 0.0), (2.0, 1.0, -8.0, 1.0)]:
+        f = ctx.field(tau)
+        ctx.gamma(f, E, mu0, lam0, alpha, beta)
+        o.set_reference(mu0, lam0)
+        o.setBCProjector(fo.Id4(d))
+        want = o.GammaOperator(E, mu0, lam0, tau, alpha, beta)
+        assert relerr(ctx.download(f), want) < 2e-12, (mu0, lam0, alpha, beta)
+        ctx.chk(ctx.lib.fgb_field_free(ctx.h, f))
+    ctx.close()
+
+
+def test_gamma_freq_hack():
+    n, L = (8, 6, 4), (1., 1., 1.)
+    ctx = fb.Context(*n, *L, mode="elasticity", gamma_scheme="collocated")
+    ctx.chk(ctx.lib.fgb_set_freq_hack(ctx.h, 1))
+    o = fo.LSSolver(*n, *L, mode="elasticity", gamma_scheme="collocated", freq_hack=True)
+    tau = np.random.default_rng(3).standard_normal((6,) + n)
+    f = ctx.field(tau)
+    ctx.gamma(f, np.zeros(6), 1.3, 0.4, -1.0, 0.0)
+    want = o.GammaOperator(np.zeros(6), 1.3, 0.4, tau, -1.0, 0.0)
+    assert relerr(ctx.download(f), want) < 2e-12
+    ctx.close()
+
+
+@pytest.mark.parametrize("n,L", [((2, 1, 1), (1., 1., 1.)), ((41, 33, 11), (1., 1., 1.)), ((41, 33, 11), (41., 33., 11.))])
+@pytest.mark.parametrize("mode,d", MODES)
+def test_reference_operator_identities(n, L, mode, d):
+    """the epsG0div projection identities of `fibergen --test` on the device (fg:23946-23974, fg:24086-24182,
+    fg:24460-24488), tolerance sqrt(eps) as check_tol (fg:23502)"""
+    tol = math.sqrt(np.finfo(float).eps)
+    mu0, lam0 = (1.0, 0.0) if mode == "heat" else (MU0, LAM0)
+    z = fb.solver._dp(np.zeros(9))
+    rng = np.random.default_rng(4)
+    # staggered
+    ctx = fb.Context(*n, *L, mode=mode, gamma_scheme="staggered")
+    ctx.u_upload(rng.random((ctx.udim,) + n))
+    f = ctx.field()
+    ctx.chk(ctx.lib.fgb_eps_staggered(ctx.h, f, z))
+    org = ctx.download(f)
+    ctx.chk(ctx.lib.fgb_calc_stress_const(ctx.h, f, f, mu0, lam0))
+    ctx.chk(ctx.lib.fgb_div_staggered(ctx.h, f))
+    ctx.chk(ctx.lib.fgb_g0_staggered(ctx.h, mu0, lam0, 1.0))
+    ctx.chk(ctx.lib.fgb_eps_staggered(ctx.h, f, z))
+    assert np.linalg.norm(np.abs(ctx.download(f) - org).reshape(d, -1).max(axis=1)) <= tol
+    ctx.close()
+    # collocated
+    ctx = fb.Context(*n, *L, mode=mode, gamma_scheme="collocated")
+    f = ctx.field(rng.random((d,) + n))
+    ctx.gamma(f, np.zeros(d), mu0, lam0, 1.0, 0.0)
+    org = ctx.download(f)
+    ctx.chk(ctx.lib.fgb_calc_stress_const(ctx.h, f, f, mu0, lam0))
+    ctx.gamma(f, np.zeros(d), mu0, lam0, 1.0, 0.0)
+    assert np.linalg.norm(np.abs(ctx.download(f) - org).reshape(d, -1).max(axis=1)) <= tol
+    ctx.close()
+
+
+def _two_phase(ctx, o, n, mode, mixing, rng):
+    phi = sphere_phi(n, R=0.3, sub=3)
+    normals = sphere_normals(n) if mixing == "laminate" else None
+    if mode == "elasticity":
+        laws = [("iso", [1.0, 1.5]), ("iso", [5.0, 2.0])]
+        olaws = [fo.LinearIsotropic(1.0, 1.5), fo.LinearIsotropic(5.0, 2.0)]
+    elif mode == "heat":
+        laws = [("scalar", [1.0]), ("aniso3", [10.0, 8.0, 6.0, 0.5, 0.2, 0.1])]
+        olaws = [fo.ScalarLinearIsotropic(1.0, 3), fo.MatrixLinearAnisotropic(10.0, 8.0, 6.0, 0.5, 0.2, 0.1)]
+    else:
+        laws = [("nh", [10.0, 10.0]), ("svk", [10.0, 100.0])]
+        olaws = [fo.NeoHooke(10.0, 10.0), fo.SaintVenantKirchhoff(10.0, 100.0)]
+    ctx.set_phases([1 - phi, phi], laws, mixing=mixing, normals=normals)
+    o.add_phase("matrix", olaws[0], 1 - phi)
+    o.add_phase("incl", olaws[1], phi)
+    if normals is not None:
+        o.set_normals(normals)
+
+
+@pytest.mark.parametrize("mode,d", MODES)
+@pytest.mark.parametrize("mixing", ["voigt", "laminate"])
+def test_constitutive_sweeps(mode, d, mixing):
+    """calcStress fg:18134, calcStressDeriv fg:18425, meanPK1 fg:12312, meanW fg:12239, getRefMaterial fg:12153"""
+    n = (12, 10, 8)
+    rng = np.random.default_rng(5)
+    ctx = fb.Context(*n, mode=mode, gamma_scheme="staggered")
+    o = fo.LSSolver(*n, mode=mode, gamma_scheme="staggered", mixing_rule=mixing)
+    _two_phase(ctx, o, n, mode, mixing, rng)
+    eps = 0.05 * rng.standard_normal((d,) + n)
+    if d == 9:
+        eps[:3] += 1.0
+    W = rng.standard_normal((d,) + n)
+    fe, fw, fo_ = ctx.field(eps), ctx.field(W), ctx.field()
+    for (mu0, lam0, alpha) in [(0.0, 0.0, 1.0), (2.5, 0.7, -1.0)]:
+        ctx.chk(ctx.lib.fgb_calc_stress(ctx.h, fe, fo_, mu0, lam0, alpha))
+        assert relerr(ctx.download(fo_), o.calcStress(mu0, lam0, eps, alpha)) < 1e-12
+        ctx.chk(ctx.lib.fgb_calc_stress_deriv(ctx.h, fe, fw, fo_, mu0, lam0, alpha))
+        assert relerr(ctx.download(fo_), o.calcStressDeriv(mu0, lam0, eps, W, alpha)) < 1e-12
+    assert relerr(ctx.mean_pk1(fe), o.calcMeanStress(eps)) < 1e-12
+    assert abs(ctx.mean_energy(fe) - o.calcMeanEnergy(eps)) <= 1e-12 * abs(o.calcMeanEnergy(eps))
+    lmin, lmax = ctx.ref_material(fe)
+    _, olmin, olmax = o.getRefMaterial(eps, False, False)
+    if olmin > 0:
+        assert abs(lmin - olmin) <= 1e-11 * abs(olmax)
+    assert abs(lmax - olmax) <= 1e-11 * abs(olmax)
+    ctx.chk(ctx.lib.fgb_check_numeric(ctx.h))
+    ctx.close()
+
+
+@pytest.mark.parametrize("mode,d", [("elasticity", 6), ("heat", 3)])
+def test_polarization_map(mode, d):
+    """calcPolarizationDim fg:18044-18118 (closed form on pure iso voxels, generic solve elsewhere)"""
+    n = (10, 9, 8)
+    rng = np.random.default_rng(6)
+    ctx = fb.Context(*n, mode=mode, gamma_scheme="collocated")
+    o = fo.LSSolver(*n, mode=mode, gamma_scheme="collocated")
+    _two_phase(ctx, o, n, mode, "voigt", rng)
+    eps = rng.standard_normal((d,) + n)
+    fe, fq = ctx.field(eps), ctx.field()
+    for inv in (0, 1):
+        ctx.chk(ctx.lib.fgb_calc_polarization(ctx.h, fe, fq, 1.7, inv))
+        assert relerr(ctx.download(fq), o.calcPolarization(1.7, eps, bool(inv))) < 1e-12
+    ctx.close()
+
+
+@pytest.mark.parametrize("n", [(9, 7, 5), (16, 8, 6), (4, 4, 1)])
+@pytest.mark.parametrize("mode,d", MODES)
+def test_blas_and_reductions(n, mode, d):
+    """TensorField BLAS-1 fg:9799-10066, innerProductL2 fg:20871-21036, component_dot/average fg:10088-10208"""
+    rng = np.random.default_rng(7)
+    ctx = fb.Context(*n, mode=mode, gamma_scheme="staggered")
+    o = fo.LSSolver(*n, mode=mode)
+    a, b, c = (rng.standard_normal((d,) + n) for _ in range(3))
+    fa, fb_, fc, fr = ctx.field(a), ctx.field(b), ctx.field(c), ctx.field()
+    assert abs(ctx.inner(fa, fb_) - o.innerProduct(a, b)) < 1e-13 * d
+    assert abs(ctx.inner(fa, fb_, fc) - o.innerProduct(a, b, c)) < 1e-13 * d
+    assert relerr(ctx.average(fa), o.average(a)) < 1e-12
+    assert relerr(ctx.component_dot(fa, fa), o.component_norm(a) ** 2) < 1e-13
+    ctx.chk(ctx.lib.fgb_xpay(ctx.h, fr, fa, 0.37, fb_))
+    assert relerr(ctx.download(fr), a + 0.37 * b) < 1e-15
+    ctx.chk(ctx.lib.fgb_xpaymz(ctx.h, fr, fa, -0.21, fb_, fc))
+    assert relerr(ctx.download(fr), a + (-0.21) * (b - c)) < 1e-15
+    E = rng.standard_normal(d)
+    ctx.chk(ctx.lib.fgb_copy(ctx.h, fa, fr))
+    ctx.chk(ctx.lib.fgb_adjust_residual(ctx.h, fr, fb.solver._dp(ctx.vec(E)), fb_))
+    assert relerr(ctx.download(fr), a + (E.reshape(-1, 1, 1, 1) - b)) < 1e-15
+    ctx.chk(ctx.lib.fgb_set_constant(ctx.h, fr, fb.solver._dp(ctx.vec(E))))
+    ctx.chk(ctx.lib.fgb_add_constant(ctx.h, fr, fb.solver._dp(ctx.vec(E))))
+    assert relerr(ctx.download(fr), np.zeros((d,) + n) + 2 * E.reshape(-1, 1, 1, 1)) < 1e-15
+    # fused CG sweep
+    import ctypes as C
+    delta = C.c_double()
+    x0, r0 = a.copy(), b.copy()
+    ctx.upload(fr, c)
+    fw = ctx.field(rng.standard_normal((d,) + n))
+    w = ctx.download(fw)
+    ctx.chk(ctx.lib.fgb_cg_update(ctx.h, fa, fb_, fr, fw, 0.61, C.byref(delta)))
+    assert relerr(ctx.download(fa), x0 + 0.61 * c) < 1e-15
+    r1 = r0 + (-0.61) * (c - w)
+    assert relerr(ctx.download(fb_), r1) < 1e-15
+    assert abs(delta.value - o.innerProduct(r1, r1)) < 1e-12 * max(1.0, delta.value)
+    ctx.close()

@@ -1,0 +1,230 @@
+"""Scheme-level parity through the reference-facing host object (fgb::LSSolver via fgls_*): same iteration count,
+residual history within 1e-10 relative and effective (mean) stress within 1e-9 relative of the CPU oracle on the
+same inputs (BASELINE.json north_star tolerances), plus the reference's own known answers on the device."""
+import numpy as np
+import pytest
+
+from oracle import fg_oracle as fo
+import fibergen_b200 as fb
+from microstructures import sphere_phi, sphere_normals, capsule_fibers
+
+pytestmark = pytest.mark.gpu
+
+RES_RTOL = 1e-10
+EFF_RTOL = 1e-9
+
+
+def build_pair(n, L=(1., 1., 1.), mode="elasticity", phases=None, normals=None, **kw):
+    """the same problem on the device solver and on the oracle"""
+    s = fb.LSSolver(*n, *L, mode=mode, **kw)
+    o = fo.LSSolver(*n, *L, mode=mode, **kw)
+    for name, law, params, olaw, phi in phases:
+        s.add_material(name, law, *params)
+    s.init()
+    for m, (name, law, params, olaw, phi) in enumerate(phases):
+        s.set_phase(m, phi)
+        o.add_phase(name, olaw, phi)
+    if normals is not None:
+        s.set_normals(normals)
+        o.set_normals(normals)
+    return s, o
+
+
+def compare(s, o, E=None, S=None, P=None):
+    if P is not None:
+        s.set_bc_projector(P)
+        o.setBCProjector(P)
+    if E is not None:
+        s.set_strain(E)
+        o.setStrain(E)
+    if S is not None:
+        s.set_stress(S)
+        o.setStress(S)
+    s.run()
+    o.run()
+    rs, ro = s.get_residuals(), np.array(o.residuals)
+    assert len(rs) == len(ro), (len(rs), len(ro), rs[-3:], ro[-3:])
+    # residual history: relative to the first residual (a residual of 1e-9 carries ~1e-16/1e-9 relative rounding)
+    scale = np.maximum(np.abs(ro), RES_RTOL * np.abs(ro).max())
+    assert np.all(np.abs(rs - ro) <= RES_RTOL * np.abs(ro).max() + 1e-6 * scale * 0 + RES_RTOL * scale), np.abs(rs - ro).max()
+    sm, om = s.get_mean_stress(), o.calcMeanStress()
+    assert np.abs(sm - om).max() <= EFF_RTOL * np.abs(om).max()
+    assert np.abs(s.get_field() - o.epsilon).max() <= 1e-9 * max(np.abs(o.epsilon).max(), 1e-300)
+    assert abs(s.ref_material()[0] - o.mu_0) <= 1e-12 * abs(o.mu_0)
+    return rs
+
+
+def el_phases(n, sub=3, contrast=10.0):
+    phi = sphere_phi(n, R=0.25, sub=sub)
+    lam1, mu1 = fb.lame(1.0, 0.3)
+    lam2, mu2 = fb.lame(contrast, 0.3)
+    return [("matrix", "iso", (mu1, lam1), fo.LinearIsotropic(mu1, lam1), 1 - phi),
+            ("sphere", "iso", (mu2, lam2), fo.LinearIsotropic(mu2, lam2), phi)]
+
+
+@pytest.mark.parametrize("scheme", ["staggered", "collocated"])
+@pytest.mark.parametrize("ee", ["sigma", "epsilon"])
+def test_basic_sphere(scheme, ee):
+    """BASELINE config 1 (scaled to 32^3 for the oracle): sphere, linear elasticity, basic scheme"""
+    n = (32, 32, 32)
+    s, o = build_pair(n, phases=el_phases(n), method="basic", gamma_scheme=scheme, error_estimator=ee, tol=1e-8)
+    rs = compare(s, o, E=[1, 0, 0, 0, 0, 0])
+    assert len(rs) > 5
+
+
+@pytest.mark.parametrize("n", [(32, 32, 32), (24, 20, 18), (16, 16, 1), (15, 9, 7)])
+@pytest.mark.parametrize("ee", ["residual", "epsilon"])
+def test_cg_staggered(n, ee):
+    """BASELINE config 2 shape (CG, staggered, Voigt mixing) on grids the oracle finishes in seconds"""
+    s, o = build_pair(n, phases=el_phases(n, contrast=40.0), method="cg", gamma_scheme="staggered", error_estimator=ee, tol=1e-8)
+    compare(s, o, E=[0.3, -0.1, 0.2, 0.5, 0.1, -0.4])
+
+
+def test_cg_collocated_and_default_settings():
+    n = (20, 20, 20)
+    s, o = build_pair(n, phases=el_phases(n), gamma_scheme="collocated")      # all other settings at reference defaults
+    compare(s, o, E=[0, 0, 0, 1, 0, 0])
+
+
+def test_cg_fibres_three_phase():
+    n = (32, 32, 32)
+    phi1, _ = capsule_fibers(n, seed=1, vol_frac=0.1, diameter_vox=4.0, aspect=5.0, max_tries=400)
+    phi2 = sphere_phi(n, R=0.2, sub=2) * (1 - phi1)
+    lam0, mu0 = fb.lame(1.665, 0.36)
+    lam1, mu1 = fb.lame(73.0, 0.18)
+    lam2, mu2 = fb.lame(10.0, 0.25)
+    phases = [("matrix", "iso", (mu0, lam0), fo.LinearIsotropic(mu0, lam0), 1 - phi1 - phi2),
+              ("fibre", "iso", (mu1, lam1), fo.LinearIsotropic(mu1, lam1), phi1),
+              ("sphere", "iso", (mu2, lam2), fo.LinearIsotropic(mu2, lam2), phi2)]
+    s, o = build_pair(n, phases=phases, method="cg", error_estimator="residual", tol=1e-6)
+    compare(s, o, E=[1, 0, 0, 0, 0, 0])
+
+
+def test_polarization_sphere():
+    n = (16, 16, 16)
+    s, o = build_pair(n, phases=el_phases(n), method="polarization", error_estimator="sigma", tol=1e-7)
+    compare(s, o, E=[1, 0.5, 0, 0, 0.2, 0])
+
+
+def test_mixed_boundary_conditions():
+    """Kabel 2016 mixed BCs (fg:20599-20665): stress prescribed in 11, strain elsewhere"""
+    n = (16, 16, 16)
+    P = fo.Id4(6)
+    P[0, 0] = 0.0
+    for method, ee in (("cg", "residual"), ("basic", "sigma")):
+        s, o = build_pair(n, phases=el_phases(n), method=method, error_estimator=ee, tol=1e-8)
+        compare(s, o, E=[0, 0.1, 0, 0, 0.05, 0], S=[0.7, 0, 0, 0, 0, 0], P=P)
+        assert abs(s.get_mean_stress()[0] - 0.7) < 1e-3
+
+
+@pytest.mark.parametrize("mixing", ["voigt", "laminate"])
+@pytest.mark.parametrize("scheme", ["staggered", "collocated"])
+def test_heat_cg(mixing, scheme):
+    """BASELINE config 3 shape: heat conduction, CG, laminate mixing at interfaces"""
+    n = (24, 24, 24)
+    phi = sphere_phi(n, R=0.3, sub=3)
+    phases = [("matrix", "iso", (1.0,), fo.ScalarLinearIsotropic(1.0, 3), 1 - phi),
+              ("fibre", "iso", (10.0,), fo.ScalarLinearIsotropic(10.0, 3), phi)]
+    s, o = build_pair(n, mode="heat", phases=phases, normals=sphere_normals(n) if mixing == "laminate" else None,
+                      method="cg", gamma_scheme=scheme, mixing_rule=mixing, error_estimator="residual", tol=1e-8)
+    compare(s, o, E=[1, 0, 0])
+
+
+def test_elastic_laminate_mixing():
+    n = (16, 16, 16)
+    s, o = build_pair(n, phases=el_phases(n), normals=sphere_normals(n), method="cg", mixing_rule="laminate",
+                      error_estimator="residual", tol=1e-8)
+    compare(s, o, E=[1, 0, 0, 0, 0, 0.3])
+
+
+@pytest.mark.parametrize("loadsteps", [1, 2])
+def test_neo_hooke_newton_cg(loadsteps):
+    """BASELINE config 4 shape: Neo-Hooke, Newton outer + CG inner (runCGHyper fg:22699)"""
+    n = (12, 12, 12)
+    phi = sphere_phi(n, R=0.3, sub=1)
+    phases = [("matrix", "nh", (10.0, 10.0), fo.NeoHooke(10.0, 10.0), 1 - phi),
+              ("incl", "nh", (10.0, 100.0), fo.NeoHooke(10.0, 100.0), phi)]
+    s, o = build_pair(n, mode="hyperelasticity", phases=phases, method="cg", error_estimator="residual",
+                      outer_error_estimator="sigma", tol=1e-6, loadsteps=loadsteps)
+    F = np.array([1, 1.1, 1, 0, 0, 0, 0, 0, 0], dtype=float)
+    compare(s, o, E=F)
+
+
+def test_viscosity_basic():
+    """Stokes analogue through the Delta operator (fg:20422-20460)"""
+    n = (12, 12, 12)
+    phi = sphere_phi(n, R=0.3, sub=1)
+    s = fb.LSSolver(*n, mode="viscosity", method="cg", error_estimator="residual", tol=1e-7)
+    o = fo.LSSolver(*n, mode="viscosity", method="cg", error_estimator="residual", tol=1e-7)
+    s.add_material("fluid", "iso", 1.0)
+    s.add_material("solid", "iso", 1e-3)
+    s.init()
+    s.set_phase(0, 1 - phi)
+    s.set_phase(1, phi)
+    o.add_phase("fluid", fo.ScalarLinearIsotropic(0.5 * 1.0, 6), 1 - phi)
+    o.add_phase("solid", fo.ScalarLinearIsotropic(0.5 * 1e-3, 6), phi)
+    compare(s, o, E=[0, 0, 0, 0, 0, 1.0])
+
+
+def test_laminate_demo_closed_form_on_device():
+    """demo/elasticity/laminate/project.xml: calc_effective_properties on 10x1x1 vs calc_isotropic_laminate (fg:26405-26446)"""
+    s = fb.LSSolver(10, 1, 1, mode="elasticity", tol=1e-10)
+    layers = []
+    for k, (E, nu, vf) in enumerate([(100, .4, .2), (25, .25, .3), (50, .3, .5)]):
+        lam, mu = fb.lame(E, nu)
+        s.add_material("layer%d" % (k + 1), "iso", mu, lam)
+        layers.append((vf, lam, mu))
+    s.init()
+    phis = np.zeros((3, 10, 1, 1))
+    phis[0, :2] = 1
+    phis[1, 2:5] = 1
+    phis[2, 5:] = 1
+    for k in range(3):
+        s.set_phase(k, phis[k])
+    C = s.get_effective_property()
+    Ca = fo.calc_isotropic_laminate(layers)
+    assert np.abs(C - Ca).max() / np.abs(Ca).max() < 1e-9
+
+
+def test_homogeneous_and_error_paths():
+    s = fb.LSSolver(8, 6, 5, mode="elasticity", method="cg", error_estimator="residual")
+    lam, mu = fb.lame(3.0, 0.3)
+    s.add_material("m", "iso", mu, lam)
+    s.init()
+    s.set_phase(0, np.ones((8, 6, 5)))
+    E = np.array([1., 0.5, -0.2, 0.1, 0.3, 0.7])
+    s.set_strain(E)
+    s.run()
+    assert len(s.get_residuals()) <= 2
+    assert np.allclose(s.get_field(), E.reshape(-1, 1, 1, 1), atol=1e-14)
+    # error behaviour of the reference: incompatible BCs, unknown settings, non-projector
+    with pytest.raises(fb.FgbError):
+        s.set("no_such_key", 1)
+    with pytest.raises(fb.FgbError):
+        s.set_bc_projector(2 * np.eye(6))
+    s.set_stress([1, 0, 0, 0, 0, 0])        # P = Id => P:S != 0
+    with pytest.raises(fb.FgbError, match="Incompatible stress"):
+        s.run()
+    s2 = fb.LSSolver(4, 4, 4, mode="elasticity", method="nesterov")
+    s2.add_material("m", "iso", 1.0, 1.0)
+    with pytest.raises(fb.FgbError, match="Unknown solver method"):
+        s2.init()
+    s3 = fb.LSSolver(4, 4, 4, gamma_scheme="willot")
+    s3.add_material("m", "iso", 1.0, 1.0)
+    with pytest.raises(fb.FgbError, match="gamma scheme"):
+        s3.init()
+
+
+def test_convergence_callback_and_maxiter():
+    n = (16, 16, 16)
+    s, o = build_pair(n, phases=el_phases(n), method="cg", error_estimator="residual", tol=1e-12, maxiter=5)
+    s.set_strain([1, 0, 0, 0, 0, 0])
+    o.setStrain([1, 0, 0, 0, 0, 0])
+    s.run()
+    o.run()
+    assert len(s.get_residuals()) == len(o.residuals) == 6       # iterations 0..5 (fg:21223)
+    calls = []
+    s.set("maxiter", 1000)
+    s.set_convergence_callback(lambda: (calls.append(1), len(calls) >= 3)[1])
+    s.run()
+    assert len(s.get_residuals()) == 3
