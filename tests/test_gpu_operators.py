@@ -88,6 +88,8 @@ def test_gamma_freq_hack():
     ctx = fb.Context(*n, *L, mode="elasticity", gamma_scheme="collocated")
     ctx.chk(ctx.lib.fgb_set_freq_hack(ctx.h, 1))
     o = fo.LSSolver(*n, *L, mode="elasticity", gamma_scheme="collocated", freq_hack=True)
+    o.set_reference(1.3, 0.4)
+    o.setBCProjector(fo.Id4(6))
     tau = np.random.default_rng(3).standard_normal((6,) + n)
     f = ctx.field(tau)
     ctx.gamma(f, np.zeros(6), 1.3, 0.4, -1.0, 0.0)
@@ -161,13 +163,17 @@ def test_constitutive_sweeps(mode, d, mixing):
         eps[:3] += 1.0
     W = rng.standard_normal((d,) + n)
     fe, fw, fo_ = ctx.field(eps), ctx.field(W), ctx.field()
+    # The hyperelastic laminate runs a backtracked Newton iteration per interface voxel whose stopping decisions
+    # (Armijo test on an energy difference at rounding level, fg:13378) flip with the last bit; the jump vector is
+    # then only converged to ~sqrt(eps_a) either way, so parity is bounded by the Newton tolerance, not by FP64.
+    tol = 1e-7 if (d == 9 and mixing == "laminate") else 1e-12
     for (mu0, lam0, alpha) in [(0.0, 0.0, 1.0), (2.5, 0.7, -1.0)]:
         ctx.chk(ctx.lib.fgb_calc_stress(ctx.h, fe, fo_, mu0, lam0, alpha))
-        assert relerr(ctx.download(fo_), o.calcStress(mu0, lam0, eps, alpha)) < 1e-12
+        assert relerr(ctx.download(fo_), o.calcStress(mu0, lam0, eps, alpha)) < tol
         ctx.chk(ctx.lib.fgb_calc_stress_deriv(ctx.h, fe, fw, fo_, mu0, lam0, alpha))
-        assert relerr(ctx.download(fo_), o.calcStressDeriv(mu0, lam0, eps, W, alpha)) < 1e-12
-    assert relerr(ctx.mean_pk1(fe), o.calcMeanStress(eps)) < 1e-12
-    assert abs(ctx.mean_energy(fe) - o.calcMeanEnergy(eps)) <= 1e-12 * abs(o.calcMeanEnergy(eps))
+        assert relerr(ctx.download(fo_), o.calcStressDeriv(mu0, lam0, eps, W, alpha)) < tol
+    assert relerr(ctx.mean_pk1(fe), o.calcMeanStress(eps)) < tol
+    assert abs(ctx.mean_energy(fe) - o.calcMeanEnergy(eps)) <= tol * abs(o.calcMeanEnergy(eps))
     lmin, lmax = ctx.ref_material(fe)
     _, olmin, olmax = o.getRefMaterial(eps, False, False)
     if olmin > 0:
