@@ -105,6 +105,8 @@ extern "C" int fgb_create(fgb_ctx** out, int nx, int ny, int nz, double Lx, doub
     c->g.lnx = nx / nranks;
     c->g.x0 = rank * c->g.lnx;
     c->g.plane = (size_t)c->g.lnx * ny * c->g.nzp;
+    c->g.unzcs = (c->g.nzc > 8) ? ((c->g.nzc + 7) / 8) * 8 : c->g.nzc;
+    c->g.uplane = (size_t)c->g.lnx * ny * 2 * c->g.unzcs;
     c->g.hx = nx / Lx; c->g.hy = ny / Ly; c->g.hz = nz / Lz;
     c->L[0] = Lx; c->L[1] = Ly; c->L[2] = Lz;
     c->mode = mode;
@@ -155,7 +157,7 @@ extern "C" int fgb_create(fgb_ctx** out, int nx, int ny, int nz, double Lx, doub
     CREATE_CUDA(cudaMalloc(&c->d_flag, sizeof(int)));
     CREATE_CUDA(cudaMemset(c->d_flag, 0, sizeof(int)));
     CREATE_CUDA(cudaMallocHost(&c->h_flag, sizeof(int)));
-    if (c->scheme == FGB_GAMMA_STAGGERED) CREATE_CUDA(cudaMalloc(&c->ubuf, sizeof(double) * c->g.plane * c->udim));
+    if (c->scheme == FGB_GAMMA_STAGGERED) CREATE_CUDA(cudaMalloc(&c->ubuf, sizeof(double) * c->g.uplane * c->udim));
     int rc = fgb_fft_init(c);
     if (rc) {
         g_create_error = c->err;
@@ -472,13 +474,14 @@ static int g0_staggered(fgb_ctx* c, double mu0, double lambda0, double alpha) {
     GreenArgs ga;
     green_args(c, ga, mu0, lambda0, alpha, 0.0);
     int rc;
-    if ((rc = fgb_fft_z_forward(c, c->ubuf, c->udim))) return rc;
-    if ((rc = fgb_fft_y(c, c->ubuf, c->udim, -1))) return rc;
-    if (c->nranks > 1) rc = fgb_comm_fft_x(c, c->ubuf, c->udim, &ga);
-    else rc = fgb_fft_x(c, c->ubuf, c->udim, 0, &ga);
+    const FftLayout lay = {c->g.unzcs};
+    if ((rc = fgb_fft_z_forward(c, c->ubuf, c->udim, lay))) return rc;
+    if ((rc = fgb_fft_y(c, c->ubuf, c->udim, lay, -1))) return rc;
+    if (c->nranks > 1) rc = fgb_comm_fft_x(c, c->ubuf, c->udim, lay, &ga);
+    else rc = fgb_fft_x(c, c->ubuf, c->udim, lay, 0, &ga);
     if (rc) return rc;
-    if ((rc = fgb_fft_y(c, c->ubuf, c->udim, +1))) return rc;
-    return fgb_fft_z_backward(c, c->ubuf, c->udim);
+    if ((rc = fgb_fft_y(c, c->ubuf, c->udim, lay, +1))) return rc;
+    return fgb_fft_z_backward(c, c->ubuf, c->udim, lay);
 }
 
 static int gamma_impl(fgb_ctx* c, double* field, const double* E, double mu0, double lambda0, double alpha, double beta) {
@@ -497,13 +500,14 @@ static int gamma_impl(fgb_ctx* c, double* field, const double* E, double mu0, do
     GreenArgs ga;                                                                   // GammaOperatorCollocated* fg:20302-20340
     green_args(c, ga, mu0, lambda0, alpha, beta);
     for (int i = 0; i < c->dim; i++) ga.dc[i] = Ec[i];
-    if ((rc = fgb_fft_z_forward(c, field, c->dim))) return rc;
-    if ((rc = fgb_fft_y(c, field, c->dim, -1))) return rc;
-    if (c->nranks > 1) rc = fgb_comm_fft_x(c, field, c->dim, &ga);
-    else rc = fgb_fft_x(c, field, c->dim, 0, &ga);
+    const FftLayout lay = {c->g.nzc};
+    if ((rc = fgb_fft_z_forward(c, field, c->dim, lay))) return rc;
+    if ((rc = fgb_fft_y(c, field, c->dim, lay, -1))) return rc;
+    if (c->nranks > 1) rc = fgb_comm_fft_x(c, field, c->dim, lay, &ga);
+    else rc = fgb_fft_x(c, field, c->dim, lay, 0, &ga);
     if (rc) return rc;
-    if ((rc = fgb_fft_y(c, field, c->dim, +1))) return rc;
-    return fgb_fft_z_backward(c, field, c->dim);
+    if ((rc = fgb_fft_y(c, field, c->dim, lay, +1))) return rc;
+    return fgb_fft_z_backward(c, field, c->dim, lay);
 }
 
 // DeltaOperatorStaggered (fg:20422-20460): viscosity dual formulation.  `copy` holds tau (input), field is overwritten.
@@ -547,7 +551,8 @@ extern "C" int fgb_u_upload(fgb_ctx* c, const double* const* comps, int n) {
     CHECK_CTX(c);
     if (!c->ubuf || n != c->udim) return fgb_fail(c, FGB_EINVAL, "u buffer has %d components", c->udim);
     for (int d = 0; d < n; d++)
-        FGB_CUDA(c, cudaMemcpyAsync(c->ubuf + (size_t)d * c->g.plane, comps[d], sizeof(double) * c->g.plane, cudaMemcpyHostToDevice, c->stream));
+        FGB_CUDA(c, cudaMemcpy2DAsync(c->ubuf + (size_t)d * c->g.uplane, sizeof(double) * 2 * c->g.unzcs, comps[d], sizeof(double) * c->g.nzp,
+                                      sizeof(double) * c->g.nzp, (size_t)c->g.lnx * c->g.ny, cudaMemcpyHostToDevice, c->stream));
     FGB_CUDA(c, cudaStreamSynchronize(c->stream));
     return FGB_OK;
 }
@@ -555,7 +560,8 @@ extern "C" int fgb_u_download(fgb_ctx* c, double* const* comps, int n) {
     CHECK_CTX(c);
     if (!c->ubuf || n != c->udim) return fgb_fail(c, FGB_EINVAL, "u buffer has %d components", c->udim);
     for (int d = 0; d < n; d++)
-        FGB_CUDA(c, cudaMemcpyAsync(comps[d], c->ubuf + (size_t)d * c->g.plane, sizeof(double) * c->g.plane, cudaMemcpyDeviceToHost, c->stream));
+        FGB_CUDA(c, cudaMemcpy2DAsync(comps[d], sizeof(double) * c->g.nzp, c->ubuf + (size_t)d * c->g.uplane, sizeof(double) * 2 * c->g.unzcs,
+                                      sizeof(double) * c->g.nzp, (size_t)c->g.lnx * c->g.ny, cudaMemcpyDeviceToHost, c->stream));
     FGB_CUDA(c, cudaStreamSynchronize(c->stream));
     return FGB_OK;
 }
@@ -563,18 +569,20 @@ extern "C" int fgb_u_download(fgb_ctx* c, double* const* comps, int n) {
 extern "C" int fgb_fft_forward(fgb_ctx* c, int f) {
     CHECK_CTX(c); CHECK_FIELD(c, f);
     int rc;
-    if ((rc = fgb_fft_z_forward(c, c->fields[f], c->dim))) return rc;
-    if ((rc = fgb_fft_y(c, c->fields[f], c->dim, -1))) return rc;
+    const FftLayout lay = {c->g.nzc};
+    if ((rc = fgb_fft_z_forward(c, c->fields[f], c->dim, lay))) return rc;
+    if ((rc = fgb_fft_y(c, c->fields[f], c->dim, lay, -1))) return rc;
     if (c->nranks > 1) return fgb_fail(c, FGB_EUNSUPPORTED, "plain 3-D transform is single-GPU only (the slab path always fuses the Green operator)");
-    return fgb_fft_x(c, c->fields[f], c->dim, -1, nullptr);
+    return fgb_fft_x(c, c->fields[f], c->dim, lay, -1, nullptr);
 }
 extern "C" int fgb_fft_backward(fgb_ctx* c, int f) {
     CHECK_CTX(c); CHECK_FIELD(c, f);
     int rc;
     if (c->nranks > 1) return fgb_fail(c, FGB_EUNSUPPORTED, "plain 3-D transform is single-GPU only (the slab path always fuses the Green operator)");
-    if ((rc = fgb_fft_x(c, c->fields[f], c->dim, +1, nullptr))) return rc;
-    if ((rc = fgb_fft_y(c, c->fields[f], c->dim, +1))) return rc;
-    return fgb_fft_z_backward(c, c->fields[f], c->dim);
+    const FftLayout lay = {c->g.nzc};
+    if ((rc = fgb_fft_x(c, c->fields[f], c->dim, lay, +1, nullptr))) return rc;
+    if ((rc = fgb_fft_y(c, c->fields[f], c->dim, lay, +1))) return rc;
+    return fgb_fft_z_backward(c, c->fields[f], c->dim, lay);
 }
 
 // ---- scheme-level ----------------------------------------------------------------------------------------------

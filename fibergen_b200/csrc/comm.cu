@@ -4,7 +4,7 @@
 
 int fgb_comm_free(fgb_ctx* ctx) { (void)ctx; return FGB_OK; }
 
-int fgb_comm_fft_x(fgb_ctx* ctx, double*, int, const GreenArgs*) {
+int fgb_comm_fft_x(fgb_ctx* ctx, double*, int, const FftLayout&, const GreenArgs*) {
     return fgb_fail(ctx, FGB_EUNSUPPORTED, "slab-partitioned x pass not built yet");
 }
 int fgb_comm_halo_tau(fgb_ctx* ctx, const double*) { return fgb_fail(ctx, FGB_EUNSUPPORTED, "halo exchange not built yet"); }

@@ -1,429 +1,262 @@
-// Hand-written batched multi-component 3-D real<->complex FFT for sm_100a, with the Green operator
-// fused between the forward and the inverse x pass.
-//
-// Replaces FFT3<double>::forward/backward (FFTW3 r2c/c2r, fg:7204-7245), the 1/nxyz scaling sweeps of
-// fftVector/fftTensor (fg:18501-18506, fg:18548-18553) and the Fourier-space operators
-// G0OperatorFourierStaggeredGeneral(Heat) (fg:19778-19927) and GammaOperatorFourierCollocated
-// (Heat/Hyper) (fg:19302-19745).  Conventions: forward = sign -1 and scaled by 1/nxyz, backward unscaled.
-//
-// Data movement per 3-D transform of one component (in place, reference layout):
-//   z pass : rows of nzp doubles are contiguous; two real rows are packed into one complex pencil
-//            (real/imag), transformed in shared memory and unpacked into two half spectra.
-//   y pass : pencils with element stride nzc; a CTA owns a tile of T consecutive k for all j so that
-//            global accesses are T*16-byte contiguous segments.
-//   x pass : as y with stride ny*nzc; the CTA holds all tensor components of its tile, applies the
-//            Green operator at every frequency and transforms back before anything returns to HBM.
-// The pencil transform is a Stockham autosort FFT in shared memory (radix 4/2 butterflies in registers,
-// generic O(p^2) stages for odd prime factors so that every n the reference accepts works).
-#include "fgb_internal.h"
+// 3-D real<->complex FFT passes and the fused x pass with the Green operator: plans, tables, launches.
+// Device code: fft_generic.cuh (any axis length: Stockham radix 4/2 + generic odd-prime stages in shared memory)
+// and the power-of-two fast path below (fft_pow2.cuh: register-resident radix-16/32 passes, warp shuffles).
+// Reference functions replaced: FFT3<double>::forward/backward fg:7204-7245, fftVector/fftTensor scaling
+// fg:18501-18506/18548-18553, G0OperatorFourierStaggered* fg:19749-19927, GammaOperatorFourierCollocated* fg:19302-19745.
+#include "fft_generic.cuh"
+#include "fft_pow2.cuh"
 #include <cmath>
 #include <complex>
 
-// ------------------------------------------------------------------------------------------------
-// device helpers
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
-    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
-__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ double2 cscale(double s, double2 a) { return make_double2(s * a.x, s * a.y); }
+using p2::Max;
 
-template <int DIR>
-__device__ __forceinline__ double2 twiddle(const double2* __restrict__ tw, int idx) {
-    double2 w = __ldg(tw + idx);
-    if (DIR > 0) w.y = -w.y;
-    return w;
-}
+// =================================================================================================
+// power-of-two kernels
+// =================================================================================================
 
-// Stockham FFT of T interleaved pencils: element e of lane t lives at buf[e*TS + t].
-// Returns the buffer holding the result (in or out).  All threads of the CTA must call it.
-template <int DIR>
-__device__ double2* fft_tile(double2* in, double2* out, const FftPlanDev& P, int T, int TS) {
-    const int n = P.n;
-    const int nthreads = blockDim.x;
+// z pass: two real rows -> one complex pencil of length N in registers; TPP threads per pencil pair,
+// exchange buffer of N(+pad) complex per pair, __syncwarp only (a pair never leaves its warp).
+#define FFTZ_THREADS 128
+template <int N, int R1, int R2, int FWD>
+__global__ void __launch_bounds__(FFTZ_THREADS) k_fftz_p2(double* __restrict__ base, long rows, long rowstride,
+                                                          const double2* __restrict__ tw, double scale) {
+    constexpr int TPP = Max<R1, R2>::v;
+    constexpr int PP = FFTZ_THREADS / TPP;         // pencil pairs per CTA
+    constexpr int XS = R2 + 1;                     // padded exchange stride
+    constexpr int NZC = N / 2 + 1;
+    extern __shared__ double2 smem_z[];
+    double2* tw_s = smem_z;                        // N
     const int tid = threadIdx.x;
-    int Ns = 1;
-    for (int s = 0; s < P.nstages; s++) {
-        const int r = P.radix[s];
-        const int m = n / r;
-        const int tws = n / (Ns * r);
-        if (r == 4) {
-            for (int idx = tid; idx < m * T; idx += nthreads) {
-                const int t = idx % T, j = idx / T;
-                const int k = j % Ns;
-                double2 v0 = in[(j)*TS + t];
-                double2 v1 = in[(j + m) * TS + t];
-                double2 v2 = in[(j + 2 * m) * TS + t];
-                double2 v3 = in[(j + 3 * m) * TS + t];
-                if (k) {
-                    v1 = cmul(v1, twiddle<DIR>(P.tw, k * tws));
-                    v2 = cmul(v2, twiddle<DIR>(P.tw, 2 * k * tws));
-                    v3 = cmul(v3, twiddle<DIR>(P.tw, 3 * k * tws));
-                }
-                const double2 a0 = cadd(v0, v2), a1 = csub(v0, v2), a2 = cadd(v1, v3);
-                double2 d = csub(v1, v3);
-                // multiply by -i (forward) or +i (inverse)
-                const double2 a3 = (DIR < 0) ? make_double2(d.y, -d.x) : make_double2(-d.y, d.x);
-                const int j0 = (j / Ns) * Ns * 4 + k;
-                out[(j0)*TS + t] = cadd(a0, a2);
-                out[(j0 + Ns) * TS + t] = cadd(a1, a3);
-                out[(j0 + 2 * Ns) * TS + t] = csub(a0, a2);
-                out[(j0 + 3 * Ns) * TS + t] = csub(a1, a3);
-            }
-        } else if (r == 2) {
-            for (int idx = tid; idx < m * T; idx += nthreads) {
-                const int t = idx % T, j = idx / T;
-                const int k = j % Ns;
-                double2 v0 = in[(j)*TS + t];
-                double2 v1 = in[(j + m) * TS + t];
-                if (k) v1 = cmul(v1, twiddle<DIR>(P.tw, k * tws));
-                const int j0 = (j / Ns) * Ns * 2 + k;
-                out[(j0)*TS + t] = cadd(v0, v1);
-                out[(j0 + Ns) * TS + t] = csub(v0, v1);
-            }
-        } else {
-            // generic radix-r stage: every output is an r-term sum (covers 3,5,7 and large primes)
-            for (int idx = tid; idx < n * T; idx += nthreads) {
-                const int t = idx % T, o = idx / T;
-                const int k = o % Ns;
-                const int qo = (o / Ns) % r;
-                const int j = (o / (Ns * r)) * Ns + k;
-                const int step = (k * tws + qo * m) % n;
-                double2 acc = in[j * TS + t];
-                int e = 0;
-                for (int q = 1; q < r; q++) {
-                    e += step;
-                    if (e >= n) e -= n;
-                    acc = cadd(acc, cmul(in[(j + q * m) * TS + t], twiddle<DIR>(P.tw, e)));
-                }
-                out[o * TS + t] = acc;
-            }
-        }
-        __syncthreads();
-        double2* tmp = in;
-        in = out;
-        out = tmp;
-        Ns *= r;
-    }
-    return in;
-}
-
-// ------------------------------------------------------------------------------------------------
-// z pass: in-place r2c / c2r of contiguous rows, two rows per complex pencil
-// ------------------------------------------------------------------------------------------------
-template <int FWD>
-__global__ void __launch_bounds__(256) k_fft_z(double* __restrict__ base, long rows, int nz, int nzc, int nzp,
-                                               FftPlanDev P, int T, int TS, double scale) {
-    extern __shared__ double2 smem[];
-    double2* a = smem;
-    double2* b = smem + (size_t)nz * TS;
-    const long pair0 = (long)blockIdx.x * T;
-    const int tid = threadIdx.x, nth = blockDim.x;
+    for (int i = tid; i < N; i += FFTZ_THREADS) tw_s[i] = tw[i];
+    __syncthreads();
+    const int s = tid % TPP, pp = tid / TPP;
+    const long pair = (long)blockIdx.x * PP + pp;
+    const long r0 = 2 * pair, r1 = r0 + 1;
+    const bool v0 = r0 < rows, v1 = r1 < rows;
+    double* rowA = base + r0 * rowstride;
+    double* rowB = base + r1 * rowstride;
+    double2* x = smem_z + N + (size_t)pp * (R1 * XS);
 
     if (FWD) {
-        for (int idx = tid; idx < T * nz; idx += nth) {
-            const int t = idx / nz, z = idx % nz;
-            const long r0 = 2 * (pair0 + t), r1 = r0 + 1;
-            double re = 0, im = 0;
-            if (r0 < rows) re = base[r0 * nzp + z];
-            if (r1 < rows) im = base[r1 * nzp + z];
-            a[z * TS + t] = make_double2(re, im);
+        if (s < R2) {
+            double2 v[R1];
+#pragma unroll
+            for (int n1 = 0; n1 < R1; n1++) {
+                const int z = R2 * n1 + s;
+                v[n1] = make_double2(v0 ? rowA[z] : 0.0, v1 ? rowB[z] : 0.0);
+            }
+            p2::pass1<R1, R2, -1>(v, s, tw_s);
+#pragma unroll
+            for (int k1 = 0; k1 < R1; k1++) x[k1 * XS + s] = v[k1];
         }
-        __syncthreads();
-        double2* res = fft_tile<-1>(a, b, P, T, TS);
-        for (int idx = tid; idx < T * nzc; idx += nth) {
-            const int t = idx / nzc, k = idx % nzc;
-            const long r0 = 2 * (pair0 + t), r1 = r0 + 1;
-            if (r0 >= rows) continue;
-            const double2 zk = res[k * TS + t];
-            const double2 zn = res[((nz - k) % nz) * TS + t];
-            const double h = 0.5 * scale;
-            // A = (Z[k] + conj(Z[n-k]))/2 ; B = (Z[k] - conj(Z[n-k]))/(2i)
-            const double2 A = make_double2(h * (zk.x + zn.x), h * (zk.y - zn.y));
-            const double2 B = make_double2(h * (zk.y + zn.y), -h * (zk.x - zn.x));
-            reinterpret_cast<double2*>(base + r0 * nzp)[k] = A;
-            if (r1 < rows) reinterpret_cast<double2*>(base + r1 * nzp)[k] = B;
+        __syncwarp();
+        double2 w[R2];
+        if (s < R1) {
+#pragma unroll
+            for (int n2 = 0; n2 < R2; n2++) w[n2] = x[s * XS + n2];
+            p2::RegFFT<R2, -1>::run(w);
+        } else {
+#pragma unroll
+            for (int n2 = 0; n2 < R2; n2++) w[n2] = make_double2(0, 0);
         }
-    } else {
-        // c2r: imaginary parts of the DC (and Nyquist) bins are ignored, like FFTW's c2r
-        for (int idx = tid; idx < T * nzc; idx += nth) {
-            const int t = idx / nzc, k = idx % nzc;
-            const long r0 = 2 * (pair0 + t), r1 = r0 + 1;
-            double2 A = make_double2(0, 0), B = make_double2(0, 0);
-            if (r0 < rows) A = reinterpret_cast<const double2*>(base + r0 * nzp)[k];
-            if (r1 < rows) B = reinterpret_cast<const double2*>(base + r1 * nzp)[k];
-            const bool selfconj = (k == 0) || (2 * k == nz);
-            if (selfconj) {
-                a[k * TS + t] = make_double2(A.x, B.x);
-            } else {
-                a[k * TS + t] = make_double2(A.x - B.y, A.y + B.x);
-                a[(nz - k) * TS + t] = make_double2(A.x + B.y, B.x - A.y);
+        // split: A[k] = (Z[k] + conj Z[N-k])/2, B[k] = (Z[k] - conj Z[N-k])/(2i); Z[N-k] lives in thread (R1-k1)%R1
+        const int lane = threadIdx.x & 31;
+        const int partner = (lane - s) + ((R1 - s) % R1);
+        const double h = 0.5 * scale;
+#pragma unroll
+        for (int k2 = 0; k2 < R2; k2++) {
+            double2 zn;
+            zn.x = __shfl_sync(0xffffffffu, w[R2 - 1 - k2].x, partner);
+            zn.y = __shfl_sync(0xffffffffu, w[R2 - 1 - k2].y, partner);
+            if (s == 0) zn = w[(R2 - k2) % R2];
+            const int k = s + R1 * k2;
+            if (s < R1 && k < NZC && v0) {
+                const double2 zk = w[k2];
+                reinterpret_cast<double2*>(rowA)[k] = make_double2(h * (zk.x + zn.x), h * (zk.y - zn.y));
+                if (v1) reinterpret_cast<double2*>(rowB)[k] = make_double2(h * (zk.y + zn.y), -h * (zk.x - zn.x));
             }
         }
-        __syncthreads();
-        double2* res = fft_tile<+1>(a, b, P, T, TS);
-        for (int idx = tid; idx < T * nz; idx += nth) {
-            const int t = idx / nz, z = idx % nz;
-            const long r0 = 2 * (pair0 + t), r1 = r0 + 1;
-            const double2 v = res[z * TS + t];
-            if (r0 < rows) base[r0 * nzp + z] = v.x;
-            if (r1 < rows) base[r1 * nzp + z] = v.y;
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// strided pass (y, and x without Green operator): one component per CTA
-// ------------------------------------------------------------------------------------------------
-template <int DIR>
-__global__ void __launch_bounds__(256) k_fft_strided(double2* __restrict__ base, FftPlanDev P, long estride, int ninner,
-                                                     long ostride, long cstride, int T) {
-    extern __shared__ double2 smem[];
-    const int n = P.n;
-    double2* a = smem;
-    double2* b = smem + (size_t)n * T;
-    const int tid = threadIdx.x, nth = blockDim.x;
-    const int inner0 = blockIdx.x * T;
-    double2* g = base + (long)blockIdx.z * cstride + (long)blockIdx.y * ostride + inner0;
-    const int tmax = min(T, ninner - inner0);
-    for (int idx = tid; idx < n * T; idx += nth) {
-        const int e = idx / T, t = idx % T;
-        a[idx] = (t < tmax) ? g[(long)e * estride + t] : make_double2(0, 0);
-    }
-    __syncthreads();
-    double2* res = fft_tile<DIR>(a, b, P, T, T);
-    for (int idx = tid; idx < n * T; idx += nth) {
-        const int e = idx / T, t = idx % T;
-        if (t < tmax) g[(long)e * estride + t] = res[idx];
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Green operators at one frequency
-// ------------------------------------------------------------------------------------------------
-struct GreenDev {
-    int kind;
-    double c10, c20, beta;
-    double dc[9];
-    int freq_hack;
-    int nx, ny, nz;
-    const double* kpm[3];
-    const double2* kp[3];
-    const double* xi[3];
-};
-
-// G0OperatorFourierStaggeredGeneral, fg:19834-19927
-__device__ __forceinline__ void green_staggered(const GreenDev& G, int ii, int jj, int kk, double2* f) {
-    const double s0 = __ldg(G.kpm[0] + ii), s1 = __ldg(G.kpm[1] + jj), s2 = __ldg(G.kpm[2] + kk);
-    const double norm = s0 * s0 + s1 * s1 + s2 * s2;
-    const double c1 = G.c10 / norm;
-    const double c2 = G.c20 / (norm * norm);
-    const double2 kp0 = __ldg(G.kp[0] + ii), kp1 = __ldg(G.kp[1] + jj), kp2 = __ldg(G.kp[2] + kk);
-    const double2 fkp = cadd(cadd(cmul(f[0], kp0), cmul(f[1], kp1)), cmul(f[2], kp2));
-    const double2 c2fkp = cscale(c2, fkp);
-    f[0] = cadd(cscale(c1, f[0]), cmul(c2fkp, make_double2(-kp0.x, kp0.y)));
-    f[1] = cadd(cscale(c1, f[1]), cmul(c2fkp, make_double2(-kp1.x, kp1.y)));
-    f[2] = cadd(cscale(c1, f[2]), cmul(c2fkp, make_double2(-kp2.x, kp2.y)));
-}
-
-// G0OperatorFourierStaggeredGeneralHeat, fg:19778-19830
-__device__ __forceinline__ void green_staggered_heat(const GreenDev& G, int ii, int jj, int kk, double2* f) {
-    const double s0 = __ldg(G.kpm[0] + ii), s1 = __ldg(G.kpm[1] + jj), s2 = __ldg(G.kpm[2] + kk);
-    const double norm = s0 * s0 + s1 * s1 + s2 * s2;
-    f[0] = cscale(G.c10 / norm, f[0]);
-}
-
-// the 21 coefficients of APPLY_GAMMA_CALC_G, fg:19435-19456
-__device__ __forceinline__ void gamma_el_coeffs(double* g, double c1, double c2, double xi0, double xi1, double xi2,
-                                                double S0, double S1, double S2, double s, bool accumulate) {
-    const double xi00 = xi0 * xi0, xi11 = xi1 * xi1, xi22 = xi2 * xi2;
-    const double xi01 = xi0 * xi1, xi02 = xi0 * xi2, xi12 = xi1 * xi2;
-    const double c12 = c1 * 2;
-    const double c3 = c12 + c2 * xi00, c4 = c12 + c2 * xi11, c5 = c12 + c2 * xi22;
-    double v[21];
-    v[0] = (c12 + c3) * xi00;                // 00
-    v[1] = c2 * xi00 * xi11;                 // 10
-    v[2] = c2 * xi00 * xi22;                 // 20
-    v[3] = c2 * xi00 * xi12 * S1 * S2;       // 30
-    v[4] = c3 * xi02 * S0 * S2;              // 40
-    v[5] = c3 * xi01 * S0 * S1;              // 50
-    v[6] = (c12 + c4) * xi11;                // 11
-    v[7] = c2 * xi11 * xi22;                 // 21
-    v[8] = c4 * xi12 * S1 * S2;              // 31
-    v[9] = c2 * xi11 * xi02 * S0 * S2;       // 41
-    v[10] = c4 * xi01 * S0 * S1;             // 51
-    v[11] = (c12 + c5) * xi22;               // 22
-    v[12] = c5 * xi12 * S1 * S2;             // 32
-    v[13] = c5 * xi02 * S0 * S2;             // 42
-    v[14] = c2 * xi22 * xi01 * S0 * S1;      // 52
-    v[15] = c1 * (xi11 + xi22) + c2 * xi11 * xi22;   // 33
-    v[16] = (c1 + c2 * xi22) * xi01 * S0 * S1;       // 43
-    v[17] = (c1 + c2 * xi11) * xi02 * S0 * S2;       // 53
-    v[18] = c1 * (xi00 + xi22) + c2 * xi00 * xi22;   // 44
-    v[19] = (c1 + c2 * xi00) * xi12 * S1 * S2;       // 54
-    v[20] = c1 * (xi00 + xi11) + c2 * xi00 * xi11;   // 55
-#pragma unroll
-    for (int i = 0; i < 21; i++) g[i] = accumulate ? g[i] + s * v[i] : v[i];
-}
-
-// index of symmetric entry (i>=j) in the 21-vector above (column-major lower triangle)
-__device__ __forceinline__ int sym21(int i, int j) {
-    if (i < j) { int t = i; i = j; j = t; }
-    // column j starts at offset j*6 - j*(j-1)/2
-    return j * 6 - (j * (j - 1)) / 2 + (i - j);
-}
-
-// GammaOperatorFourierCollocated, fg:19381-19608
-__device__ __forceinline__ void green_colloc_el(const GreenDev& G, int ii, int jj, int kk, double2* f) {
-    const double xi0 = __ldg(G.xi[0] + ii), xi1 = __ldg(G.xi[1] + jj), xi2 = __ldg(G.xi[2] + kk);
-    const double norm = xi0 * xi0 + xi1 * xi1 + xi2 * xi2;
-    const double c1 = G.c10 / norm;
-    const double c2 = G.c20 / (norm * norm);
-    double g[21];
-    const bool fi = G.freq_hack && (G.nx % 2 == 0) && ii == G.nx / 2;
-    const bool fj = G.freq_hack && (G.ny % 2 == 0) && jj == G.ny / 2;
-    const bool fk = G.freq_hack && (G.nz % 2 == 0) && kk == G.nz / 2;
-    if (fi || fj || fk) {
-#pragma unroll
-        for (int i = 0; i < 21; i++) g[i] = 0;
-        double s = 1;
-        if (fi) s *= 0.5;
-        if (fj) s *= 0.5;
-        if (fk) s *= 0.5;
-        for (int i = 1; i >= (fi ? -1 : 1); i -= 2)
-            for (int j = 1; j >= (fj ? -1 : 1); j -= 2)
-                for (int k2 = 1; k2 >= (fk ? -1 : 1); k2 -= 2)
-                    gamma_el_coeffs(g, c1, c2, xi0, xi1, xi2, (double)i, (double)j, (double)k2, s, true);
     } else {
-        gamma_el_coeffs(g, c1, c2, xi0, xi1, xi2, 1.0, 1.0, 1.0, 1.0, false);
-    }
-    double2 ey[6];
+        if (s < R2) {
+            double2 v[R1];
 #pragma unroll
-    for (int i = 0; i < 6; i++) {
-        double2 a = cadd(cadd(cscale(g[sym21(i, 0)], f[0]), cscale(g[sym21(i, 1)], f[1])), cscale(g[sym21(i, 2)], f[2]));
-        double2 b = cadd(cadd(cscale(g[sym21(i, 3)], f[3]), cscale(g[sym21(i, 4)], f[4])), cscale(g[sym21(i, 5)], f[5]));
-        ey[i] = cadd(a, cscale(2.0, b));
-    }
+            for (int n1 = 0; n1 < R1; n1++) {
+                const int idx = R2 * n1 + s;
+                const bool mirror = idx > N / 2;
+                const int k = mirror ? N - idx : idx;
+                double2 A = make_double2(0, 0), B = make_double2(0, 0);
+                if (v0) A = reinterpret_cast<const double2*>(rowA)[k];
+                if (v1) B = reinterpret_cast<const double2*>(rowB)[k];
+                if (k == 0 || 2 * k == N) v[n1] = make_double2(A.x, B.x);          // c2r ignores these imaginary parts
+                else if (!mirror) v[n1] = make_double2(A.x - B.y, A.y + B.x);        // A + iB
+                else v[n1] = make_double2(A.x + B.y, B.x - A.y);                     // conj(A) + i conj(B)
+            }
+            p2::pass1<R1, R2, +1>(v, s, tw_s);
 #pragma unroll
-    for (int i = 0; i < 6; i++) f[i] = cadd(ey[i], cscale(G.beta, f[i]));
-}
-
-// GammaOperatorFourierCollocatedHeat, fg:19302-19377
-__device__ __forceinline__ void green_colloc_heat(const GreenDev& G, int ii, int jj, int kk, double2* f) {
-    double xi[3] = {__ldg(G.xi[0] + ii), __ldg(G.xi[1] + jj), __ldg(G.xi[2] + kk)};
-    const double norm = xi[0] * xi[0] + xi[1] * xi[1] + xi[2] * xi[2];
-    const double c1 = G.c10 / norm;
-    double2 ey[3];
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-        double2 c = make_double2(0, 0);
-#pragma unroll
-        for (int j = 0; j < 3; j++) c = cadd(c, cscale(c1 * xi[i] * xi[j], f[j]));
-        ey[i] = c;
-    }
-#pragma unroll
-    for (int i = 0; i < 3; i++) f[i] = cadd(ey[i], cscale(G.beta, f[i]));
-}
-
-// GammaOperatorFourierCollocatedHyper, fg:19619-19745
-__device__ __forceinline__ void green_colloc_hyper(const GreenDev& G, int ii, int jj, int kk, double2* f) {
-    const int vi[9] = {0, 1, 2, 1, 0, 0, 2, 2, 1};
-    const int vj[9] = {0, 1, 2, 2, 2, 1, 1, 0, 0};
-    double xi[3] = {__ldg(G.xi[0] + ii), __ldg(G.xi[1] + jj), __ldg(G.xi[2] + kk)};
-    const double norm = xi[0] * xi[0] + xi[1] * xi[1] + xi[2] * xi[2];
-    const double c1 = G.c10 / norm;
-    const double c2 = G.c20 / (norm * norm);
-    double2 ey[9];
-#pragma unroll
-    for (int i = 0; i < 9; i++) {
-        double2 c = make_double2(0, 0);
-#pragma unroll
-        for (int j = 0; j < 9; j++) {
-            const double gij = c1 * ((vi[i] == vi[j]) ? xi[vj[i]] * xi[vj[j]] : 0.0) +
-                               c2 * (xi[vi[i]] * xi[vj[i]] * xi[vi[j]] * xi[vj[j]]);
-            c = cadd(c, cscale(gij, f[j]));
+            for (int k1 = 0; k1 < R1; k1++) x[k1 * XS + s] = v[k1];
         }
-        ey[i] = c;
-    }
+        __syncwarp();
+        if (s < R1) {
+            double2 w[R2];
 #pragma unroll
-    for (int i = 0; i < 9; i++) f[i] = cadd(ey[i], cscale(G.beta, f[i]));
+            for (int n2 = 0; n2 < R2; n2++) w[n2] = x[s * XS + n2];
+            p2::RegFFT<R2, +1>::run(w);
+#pragma unroll
+            for (int k2 = 0; k2 < R2; k2++) {
+                const int z = s + R1 * k2;
+                if (v0) rowA[z] = w[k2].x;
+                if (v1) rowB[z] = w[k2].y;
+            }
+        }
+    }
 }
 
-// ------------------------------------------------------------------------------------------------
-// x pass fused with the Green operator: forward x, operator, inverse x -- one HBM round trip
-// layout seen by this kernel: element (ii, inner) of component c at base[c*cstride + outer*ostride + ii*estride + inner]
-// (jj,kk) of an element: jj = jbase + outer*jouter + inner / nzc, kk = inner % nzc
-// ------------------------------------------------------------------------------------------------
-template <int NC, int KIND>
-__global__ void __launch_bounds__(256) k_fft_x_green(double2* __restrict__ base, FftPlanDev P, GreenDev G, long estride,
-                                                     int ninner, long ostride, long cstride, int T, int nzc, int jbase,
-                                                     int jouter) {
+// strided pass (y; x without Green): tile of T lanes, thread (t, s); exchange buffer X[(k1*R2+n2)*T + t]
+template <int N, int R1, int R2, int DIR, int T>
+__global__ void __launch_bounds__(Max<R1, R2>::v* T) k_ffts_p2(double2* __restrict__ base, const double2* __restrict__ tw, long estride,
+                                                               int ninner, long ostride, long cstride) {
+    constexpr int TPP = Max<R1, R2>::v;
+    __shared__ double2 tw_s[N];
+    __shared__ double2 X[N * T];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < N; i += TPP * T) tw_s[i] = tw[i];
+    const int t = tid % T, s = tid / T;
+    const int inner = blockIdx.x * T + t;
+    const bool valid = inner < ninner;
+    double2* g = base + (long)blockIdx.z * cstride + (long)blockIdx.y * ostride + inner;
+    double2 v[R1];
+    if (s < R2) {
+#pragma unroll
+        for (int n1 = 0; n1 < R1; n1++) v[n1] = valid ? g[(long)(R2 * n1 + s) * estride] : make_double2(0, 0);
+    }
+    __syncthreads();
+    if (s < R2) {
+        p2::pass1<R1, R2, DIR>(v, s, tw_s);
+#pragma unroll
+        for (int k1 = 0; k1 < R1; k1++) X[(k1 * R2 + s) * T + t] = v[k1];
+    }
+    __syncthreads();
+    if (s < R1) {
+        double2 w[R2];
+#pragma unroll
+        for (int n2 = 0; n2 < R2; n2++) w[n2] = X[(s * R2 + n2) * T + t];
+        p2::RegFFT<R2, DIR>::run(w);
+        if (valid) {
+#pragma unroll
+            for (int k2 = 0; k2 < R2; k2++) g[(long)(s + R1 * k2) * estride] = w[k2];
+        }
+    }
+}
+
+// x pass fused with the Green operator (power-of-two nx).  One shared-memory exchange per direction:
+//   forward : threads n2: R1-point FFT over n1, twiddle W_N^(n2 k1) | exchange | threads k1: R2-point FFT over n2 -> X[k1 + R1 k2]
+//   operator: every thread owns all NC components at its R2 frequencies (registers)
+//   inverse : threads k1: R2-point inverse FFT over k2, twiddle conj W_N^(k1 na) | exchange | threads na: R1-point inverse FFT over k1
+//             -> x[na + R2 nb], the same distribution the forward pass loaded, stored straight back to HBM.
+template <int N, int R1, int R2, int NC, int KIND, int T>
+__global__ void __launch_bounds__(Max<R1, R2>::v* T) k_fftx_green_p2(double2* __restrict__ base, const double2* __restrict__ tw, GreenDev G,
+                                                                     long estride, int ninner, long ostride, long cstride, int jbase) {
+    constexpr int TPP = Max<R1, R2>::v;
+    constexpr int NT = TPP * T;
     extern __shared__ double2 smem[];
-    const int n = P.n;
-    const int tid = threadIdx.x, nth = blockDim.x;
-    const size_t bufsz = (size_t)n * T;
-    double2* ptr[NC];
+    double2* tw_s = smem;                 // N
+    double2* S = smem + N;                // NC * N * T exchange space, component c at S + c*N*T
+    const int tid = threadIdx.x;
+    for (int i = tid; i < N; i += NT) tw_s[i] = tw[i];
+    const int t = tid % T, s = tid / T;
+    const int inner = blockIdx.x * T + t;
+    const bool valid = inner < ninner;
+    double2* g = base + (long)blockIdx.y * ostride + inner;
+    __syncthreads();
+
+    // ---- forward pass 1 (per component; one component in registers at a time)
+    if (s < R2) {
 #pragma unroll
-    for (int c = 0; c < NC; c++) ptr[c] = smem + c * bufsz;
-    double2* fr = smem + NC * bufsz;
-    const int inner0 = blockIdx.x * T;
-    double2* g = base + (long)blockIdx.y * ostride + inner0;
-    const int tmax = min(T, ninner - inner0);
+        for (int c = 0; c < NC; c++) {
+            double2* Sc = S + (size_t)c * N * T;
+            double2 v[R1];
 #pragma unroll
-    for (int c = 0; c < NC; c++) {
-        for (int idx = tid; idx < n * T; idx += nth) {
-            const int e = idx / T, t = idx % T;
-            ptr[c][idx] = (t < tmax) ? g[c * cstride + (long)e * estride + t] : make_double2(0, 0);
+            for (int n1 = 0; n1 < R1; n1++) v[n1] = valid ? g[c * cstride + (long)(R2 * n1 + s) * estride] : make_double2(0, 0);
+            p2::pass1<R1, R2, -1>(v, s, tw_s);
+#pragma unroll
+            for (int k1 = 0; k1 < R1; k1++) Sc[(k1 * R2 + s) * T + t] = v[k1];
         }
     }
     __syncthreads();
+    // ---- forward pass 2, Green operator and inverse pass 1 on registers
+    double2 w[NC][R2];
+    if (s < R1) {
 #pragma unroll
-    for (int c = 0; c < NC; c++) {
-        double2* res = fft_tile<-1>(ptr[c], fr, P, T, T);
-        if (res != ptr[c]) { fr = ptr[c]; ptr[c] = res; }
-    }
-    // Green operator
-    for (int idx = tid; idx < n * T; idx += nth) {
-        const int ii = idx / T, t = idx % T;
-        const int inner = inner0 + t;
-        if (t >= tmax) continue;
-        const int jj = jbase + blockIdx.y * jouter + inner / nzc;
-        const int kk = inner % nzc;
-        double2 f[NC];
+        for (int c = 0; c < NC; c++) {
+            const double2* Sc = S + (size_t)c * N * T;
 #pragma unroll
-        for (int c = 0; c < NC; c++) f[c] = ptr[c][idx];
-        if (ii == 0 && jj == 0 && kk == 0) {
+            for (int n2 = 0; n2 < R2; n2++) w[c][n2] = Sc[(s * R2 + n2) * T + t];
+            p2::RegFFT<R2, -1>::run(w[c]);
+        }
+        const int jj = jbase + blockIdx.y;
+        const int kk = inner;
+        if (valid) {
 #pragma unroll
-            for (int c = 0; c < NC; c++) f[c] = make_double2(G.dc[c], 0.0);
-        } else {
-            if (KIND == 1) green_staggered(G, ii, jj, kk, f);
-            if (KIND == 2) green_staggered_heat(G, ii, jj, kk, f);
-            if (KIND == 3) green_colloc_el(G, ii, jj, kk, f);
-            if (KIND == 4) green_colloc_heat(G, ii, jj, kk, f);
-            if (KIND == 5) green_colloc_hyper(G, ii, jj, kk, f);
+            for (int k2 = 0; k2 < R2; k2++) {
+                const int ii = s + R1 * k2;
+                double2 f[NC];
+#pragma unroll
+                for (int c = 0; c < NC; c++) f[c] = w[c][k2];
+                if (ii == 0 && jj == 0 && kk == 0) {
+#pragma unroll
+                    for (int c = 0; c < NC; c++) f[c] = make_double2(G.dc[c], 0.0);
+                } else {
+                    if (KIND == 1) green_staggered(G, ii, jj, kk, f);
+                    if (KIND == 2) green_staggered_heat(G, ii, jj, kk, f);
+                    if (KIND == 3) green_colloc_el(G, ii, jj, kk, f);
+                    if (KIND == 4) green_colloc_heat(G, ii, jj, kk, f);
+                    if (KIND == 5) green_colloc_hyper(G, ii, jj, kk, f);
+                }
+#pragma unroll
+                for (int c = 0; c < NC; c++) w[c][k2] = f[c];
+            }
         }
 #pragma unroll
-        for (int c = 0; c < NC; c++) ptr[c][idx] = f[c];
+        for (int c = 0; c < NC; c++) {
+            p2::RegFFT<R2, +1>::run(w[c]);          // inverse over k2 -> Y[k1][na], na = 0..R2-1
+#pragma unroll
+            for (int na = 1; na < R2; na++) {
+                double2 tws = tw_s[s * na];
+                tws.y = -tws.y;
+                w[c][na] = p2::pmul(w[c][na], tws);
+            }
+        }
+    }
+    __syncthreads();          // all exchange reads done before S is overwritten
+    if (s < R1) {
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            double2* Sc = S + (size_t)c * N * T;
+#pragma unroll
+            for (int na = 0; na < R2; na++) Sc[(na * R1 + s) * T + t] = w[c][na];
+        }
     }
     __syncthreads();
+    // ---- inverse pass 2: thread na gathers Y[k1][na] over k1, R1-point inverse FFT, output x[na + R2*nb]
+    if (s < R2) {
 #pragma unroll
-    for (int c = 0; c < NC; c++) {
-        double2* res = fft_tile<+1>(ptr[c], fr, P, T, T);
-        if (res != ptr[c]) { fr = ptr[c]; ptr[c] = res; }
-    }
+        for (int c = 0; c < NC; c++) {
+            const double2* Sc = S + (size_t)c * N * T;
+            double2 v[R1];
 #pragma unroll
-    for (int c = 0; c < NC; c++) {
-        for (int idx = tid; idx < n * T; idx += nth) {
-            const int e = idx / T, t = idx % T;
-            if (t < tmax) g[c * cstride + (long)e * estride + t] = ptr[c][idx];
+            for (int k1 = 0; k1 < R1; k1++) v[k1] = Sc[(s * R1 + k1) * T + t];
+            p2::RegFFT<R1, +1>::run(v);
+            if (valid) {
+#pragma unroll
+                for (int nb = 0; nb < R1; nb++) g[c * cstride + (long)(s + R2 * nb) * estride] = v[nb];
+            }
         }
     }
 }
 
-// ------------------------------------------------------------------------------------------------
+// =================================================================================================
 // host side: plans, tables, launches
-// ------------------------------------------------------------------------------------------------
+// =================================================================================================
 static void factorize(int n, FftPlanDev& P) {
     P.n = n;
     P.nstages = 0;
@@ -440,15 +273,26 @@ static double freq_index(int i, int n) {
     return (i <= half) ? (double)i : ((double)i - (double)n);
 }
 
+static bool is_fast_pow2(int n) { return n == 64 || n == 128 || n == 256 || n == 512 || n == 1024; }
+
 int fgb_fft_init(fgb_ctx* ctx) {
     const int dims[3] = {ctx->g.nx, ctx->g.ny, ctx->g.nz};
+    const long double PI = 3.14159265358979323846264338327950288L;
+    {
+        double2 w32[32];
+        for (int k = 0; k < 32; k++) {
+            const long double ang = -2.0L * PI * (long double)k / 32.0L;
+            w32[k] = make_double2((double)cosl(ang), (double)sinl(ang));
+        }
+        FGB_CUDA(ctx, cudaMemcpyToSymbol(c_w32, w32, sizeof(w32)));
+    }
     for (int a = 0; a < 3; a++) {
         const int n = dims[a];
         if (n > 16384) return fgb_fail(ctx, FGB_EUNSUPPORTED, "axis length %d too large for the shared-memory FFT", n);
         factorize(n, ctx->plan[a]);
         std::vector<double2> tw(n);
         for (int k = 0; k < n; k++) {
-            const long double ang = -2.0L * 3.14159265358979323846264338327950288L * (long double)k / (long double)n;
+            const long double ang = -2.0L * PI * (long double)k / (long double)n;
             tw[k] = make_double2((double)cosl(ang), (double)sinl(ang));
         }
         FGB_CUDA(ctx, cudaMalloc(&ctx->tw_dev[a], sizeof(double2) * n));
@@ -502,101 +346,149 @@ static cudaError_t set_smem(K kernel, size_t bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
-static int fft_z(fgb_ctx* ctx, double* base, int ncomp, bool fwd) {
-    const GridDev& g = ctx->g;
-    if (g.nz == 1) {
-        // length-1 axis: r2c/c2r are the identity on the real part; forward still scales by 1/nxyz
-        // handled by the generic kernel as well (nstages == 0)
+// ---- z ---------------------------------------------------------------------------------------------
+template <int N, int R1, int R2>
+static void launch_z_p2(fgb_ctx* ctx, double* base, long rows, long rowstride, bool fwd, double scale) {
+    constexpr int PP = FFTZ_THREADS / Max<R1, R2>::v;
+    const long pairs = (rows + 1) / 2;
+    const unsigned grid = (unsigned)((pairs + PP - 1) / PP);
+    const size_t smem = sizeof(double2) * (N + (size_t)PP * R1 * (R2 + 1));
+    if (fwd) {
+        set_smem(k_fftz_p2<N, R1, R2, 1>, smem);
+        k_fftz_p2<N, R1, R2, 1><<<grid, FFTZ_THREADS, smem, ctx->stream>>>(base, rows, rowstride, ctx->plan[2].tw, scale);
+    } else {
+        set_smem(k_fftz_p2<N, R1, R2, 0>, smem);
+        k_fftz_p2<N, R1, R2, 0><<<grid, FFTZ_THREADS, smem, ctx->stream>>>(base, rows, rowstride, ctx->plan[2].tw, 1.0);
     }
+}
+
+static int fft_z(fgb_ctx* ctx, double* base, int ncomp, const FftLayout& lay, bool fwd) {
+    const GridDev& g = ctx->g;
     const long rows = (long)ncomp * g.lnx * g.ny;
     if (rows == 0) return FGB_OK;
+    const long rowstride = 2L * lay.nzcs;
+    const double scale = 1.0 / ((double)g.nx * g.ny * g.nz);
+    ProfScope ps(ctx, fwd ? "fft_z_r2c" : "fft_z_c2r");
+    if (is_fast_pow2(g.nz)) {
+        switch (g.nz) {
+            case 64: launch_z_p2<64, 8, 8>(ctx, base, rows, rowstride, fwd, scale); break;
+            case 128: launch_z_p2<128, 16, 8>(ctx, base, rows, rowstride, fwd, scale); break;
+            case 256: launch_z_p2<256, 16, 16>(ctx, base, rows, rowstride, fwd, scale); break;
+            case 512: launch_z_p2<512, 32, 16>(ctx, base, rows, rowstride, fwd, scale); break;
+            case 1024: launch_z_p2<1024, 32, 32>(ctx, base, rows, rowstride, fwd, scale); break;
+        }
+        FGB_CHECK_LAUNCH(ctx, "k_fftz_p2");
+        return FGB_OK;
+    }
     int T = pick_T(ctx, g.nz, 2, 1, 8);
     if (!T) return fgb_fail(ctx, FGB_EUNSUPPORTED, "nz=%d does not fit shared memory", g.nz);
-    // keep enough CTAs in flight for small problems
     const int TS = T + 1;
     const size_t smem = (size_t)2 * g.nz * TS * sizeof(double2);
     const long pairs = (rows + 1) / 2;
     const unsigned grid = (unsigned)((pairs + T - 1) / T);
-    const double scale = 1.0 / ((double)g.nx * g.ny * g.nz);
     if (fwd) {
-        ProfScope ps(ctx, "fft_z_r2c");
         FGB_CUDA(ctx, set_smem(k_fft_z<1>, smem));
-        k_fft_z<1><<<grid, 256, smem, ctx->stream>>>(base, rows, g.nz, g.nzc, g.nzp, ctx->plan[2], T, TS, scale);
-        FGB_CHECK_LAUNCH(ctx, "k_fft_z<fwd>");
+        k_fft_z<1><<<grid, 256, smem, ctx->stream>>>(base, rows, g.nz, g.nzc, rowstride, ctx->plan[2], T, TS, scale);
     } else {
-        ProfScope ps(ctx, "fft_z_c2r");
         FGB_CUDA(ctx, set_smem(k_fft_z<0>, smem));
-        k_fft_z<0><<<grid, 256, smem, ctx->stream>>>(base, rows, g.nz, g.nzc, g.nzp, ctx->plan[2], T, TS, 1.0);
-        FGB_CHECK_LAUNCH(ctx, "k_fft_z<bwd>");
+        k_fft_z<0><<<grid, 256, smem, ctx->stream>>>(base, rows, g.nz, g.nzc, rowstride, ctx->plan[2], T, TS, 1.0);
     }
+    FGB_CHECK_LAUNCH(ctx, "k_fft_z");
     return FGB_OK;
 }
 
-int fgb_fft_z_forward(fgb_ctx* ctx, double* base, int ncomp) { return fft_z(ctx, base, ncomp, true); }
-int fgb_fft_z_backward(fgb_ctx* ctx, double* base, int ncomp) { return fft_z(ctx, base, ncomp, false); }
+int fgb_fft_z_forward(fgb_ctx* ctx, double* base, int ncomp, const FftLayout& lay) { return fft_z(ctx, base, ncomp, lay, true); }
+int fgb_fft_z_backward(fgb_ctx* ctx, double* base, int ncomp, const FftLayout& lay) { return fft_z(ctx, base, ncomp, lay, false); }
 
-int fgb_fft_y(fgb_ctx* ctx, double* base, int ncomp, int dir) {
-    const GridDev& g = ctx->g;
-    if (g.ny == 1 || g.lnx == 0) return FGB_OK;
-    int T = pick_T(ctx, g.ny, 2, 0, 8);
-    if (!T) return fgb_fail(ctx, FGB_EUNSUPPORTED, "ny=%d does not fit shared memory", g.ny);
-    const size_t smem = (size_t)2 * g.ny * T * sizeof(double2);
-    dim3 grid((g.nzc + T - 1) / T, g.lnx, ncomp);
-    ProfScope ps(ctx, dir < 0 ? "fft_y_fwd" : "fft_y_bwd");
+// ---- strided (y, plain x) -----------------------------------------------------------------------------
+template <int N, int R1, int R2, int T>
+static void launch_s_p2(fgb_ctx* ctx, double2* base, const double2* tw, long estride, int ninner, int nouter, long ostride, int ncomp,
+                        long cstride, int dir) {
+    dim3 grid((ninner + T - 1) / T, nouter, ncomp);
+    constexpr int NT = Max<R1, R2>::v * T;
+    if (dir < 0) k_ffts_p2<N, R1, R2, -1, T><<<grid, NT, 0, ctx->stream>>>(base, tw, estride, ninner, ostride, cstride);
+    else k_ffts_p2<N, R1, R2, +1, T><<<grid, NT, 0, ctx->stream>>>(base, tw, estride, ninner, ostride, cstride);
+}
+
+static int fft_strided(fgb_ctx* ctx, int axis, double2* base, long estride, int ninner, int nouter, long ostride, int ncomp, long cstride,
+                       int dir) {
+    const int n = ctx->plan[axis].n;
+    if (n == 1 || ninner == 0 || nouter == 0) return FGB_OK;
+    const double2* tw = ctx->plan[axis].tw;
+    if (is_fast_pow2(n)) {
+        switch (n) {
+            case 64: launch_s_p2<64, 8, 8, 8>(ctx, base, tw, estride, ninner, nouter, ostride, ncomp, cstride, dir); break;
+            case 128: launch_s_p2<128, 16, 8, 8>(ctx, base, tw, estride, ninner, nouter, ostride, ncomp, cstride, dir); break;
+            case 256: launch_s_p2<256, 16, 16, 8>(ctx, base, tw, estride, ninner, nouter, ostride, ncomp, cstride, dir); break;
+            case 512: launch_s_p2<512, 32, 16, 4>(ctx, base, tw, estride, ninner, nouter, ostride, ncomp, cstride, dir); break;
+            case 1024: launch_s_p2<1024, 32, 32, 2>(ctx, base, tw, estride, ninner, nouter, ostride, ncomp, cstride, dir); break;
+        }
+        FGB_CHECK_LAUNCH(ctx, "k_ffts_p2");
+        return FGB_OK;
+    }
+    int T = pick_T(ctx, n, 2, 0, 8);
+    if (!T) return fgb_fail(ctx, FGB_EUNSUPPORTED, "axis length %d does not fit shared memory", n);
+    const size_t smem = (size_t)2 * n * T * sizeof(double2);
+    dim3 grid((ninner + T - 1) / T, nouter, ncomp);
     if (dir < 0) {
         FGB_CUDA(ctx, set_smem(k_fft_strided<-1>, smem));
-        k_fft_strided<-1><<<grid, 256, smem, ctx->stream>>>((double2*)base, ctx->plan[1], g.nzc, g.nzc,
-                                                            (long)g.ny * g.nzc, (long)(g.plane / 2), T);
+        k_fft_strided<-1><<<grid, 256, smem, ctx->stream>>>(base, ctx->plan[axis], estride, ninner, ostride, cstride, T);
     } else {
         FGB_CUDA(ctx, set_smem(k_fft_strided<1>, smem));
-        k_fft_strided<1><<<grid, 256, smem, ctx->stream>>>((double2*)base, ctx->plan[1], g.nzc, g.nzc,
-                                                           (long)g.ny * g.nzc, (long)(g.plane / 2), T);
+        k_fft_strided<1><<<grid, 256, smem, ctx->stream>>>(base, ctx->plan[axis], estride, ninner, ostride, cstride, T);
     }
-    FGB_CHECK_LAUNCH(ctx, "k_fft_strided<y>");
+    FGB_CHECK_LAUNCH(ctx, "k_fft_strided");
+    return FGB_OK;
+}
+
+int fgb_fft_y(fgb_ctx* ctx, double* base, int ncomp, const FftLayout& lay, int dir) {
+    const GridDev& g = ctx->g;
+    ProfScope ps(ctx, dir < 0 ? "fft_y_fwd" : "fft_y_bwd");
+    return fft_strided(ctx, 1, (double2*)base, lay.nzcs, g.nzc, g.lnx, (long)g.ny * lay.nzcs, ncomp, (long)g.lnx * g.ny * lay.nzcs, dir);
+}
+
+// ---- x with Green operator ---------------------------------------------------------------------------------
+template <int N, int R1, int R2, int NC, int KIND, int T>
+static int launch_xg_p2(fgb_ctx* ctx, double2* base, const GreenDev& G, long estride, int ninner, int nouter, long ostride, long cstride,
+                        int jbase) {
+    constexpr int NT = Max<R1, R2>::v * T;
+    const size_t smem = (size_t)(N + (size_t)NC * N * T) * sizeof(double2);
+    if (smem > ctx->smem_optin) return -1;
+    dim3 grid((ninner + T - 1) / T, nouter, 1);
+    FGB_CUDA(ctx, set_smem(k_fftx_green_p2<N, R1, R2, NC, KIND, T>, smem));
+    k_fftx_green_p2<N, R1, R2, NC, KIND, T><<<grid, NT, smem, ctx->stream>>>(base, ctx->plan[0].tw, G, estride, ninner, ostride, cstride, jbase);
+    FGB_CHECK_LAUNCH(ctx, "k_fftx_green_p2");
     return FGB_OK;
 }
 
 template <int NC, int KIND>
-static int launch_x_green(fgb_ctx* ctx, double2* base, const GreenDev& G, long estride, int ninner, int nouter,
-                          long ostride, long cstride, int jbase, int jouter) {
-    const GridDev& g = ctx->g;
-    int T = pick_T(ctx, g.nx, NC + 1, 0, 8);
-    // prefer two resident CTAs per SM when the tile is large
-    if (!T) return fgb_fail(ctx, FGB_EUNSUPPORTED, "nx=%d with %d components does not fit shared memory", g.nx, NC);
-    const size_t smem = (size_t)(NC + 1) * g.nx * T * sizeof(double2);
+static int launch_x_green(fgb_ctx* ctx, double2* base, const GreenDev& G, long estride, int ninner, int nouter, long ostride, long cstride,
+                          int jbase) {
+    const int nx = ctx->g.nx;
+    int rc = -1;
+    // register budget: NC*R2 complex per thread -> the fast path covers NC <= 3 (staggered / heat); larger tensors use the generic kernel
+    if constexpr (NC <= 3) {
+        switch (nx) {
+            case 64: rc = launch_xg_p2<64, 8, 8, NC, KIND, 8>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase); break;
+            case 128: rc = launch_xg_p2<128, 16, 8, NC, KIND, 8>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase); break;
+            case 256: rc = launch_xg_p2<256, 16, 16, NC, KIND, 8>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase); break;
+            case 512: rc = launch_xg_p2<512, 32, 16, NC, KIND, 4>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase); break;
+            case 1024: if constexpr (NC == 1) rc = launch_xg_p2<1024, 32, 32, NC, KIND, 2>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase); break;
+        }
+        if (rc != -1) return rc;
+    }
+    int T = pick_T(ctx, nx, NC + 1, 0, 8);
+    if (!T) return fgb_fail(ctx, FGB_EUNSUPPORTED, "nx=%d with %d components does not fit shared memory", nx, NC);
+    const size_t smem = (size_t)(NC + 1) * nx * T * sizeof(double2);
     dim3 grid((ninner + T - 1) / T, nouter, 1);
-    ProfScope ps(ctx, "fft_x_green");
     FGB_CUDA(ctx, set_smem(k_fft_x_green<NC, KIND>, smem));
-    k_fft_x_green<NC, KIND><<<grid, 256, smem, ctx->stream>>>(base, ctx->plan[0], G, estride, ninner, ostride, cstride,
-                                                              T, g.nzc, jbase, jouter);
+    k_fft_x_green<NC, KIND><<<grid, 256, smem, ctx->stream>>>(base, ctx->plan[0], G, estride, ninner, ostride, cstride, T, jbase);
     FGB_CHECK_LAUNCH(ctx, "k_fft_x_green");
     return FGB_OK;
 }
 
-int fgb_fft_x(fgb_ctx* ctx, double* base, int ncomp, int dir, const GreenArgs* ga) {
+static void fill_green(const fgb_ctx* ctx, const GreenArgs* ga, GreenDev& G) {
     const GridDev& g = ctx->g;
-    if (ctx->nranks > 1) return fgb_fail(ctx, FGB_EUNSUPPORTED, "fgb_fft_x: slab-partitioned x pass goes through comm.cu");
-    const long estride = (long)g.ny * g.nzc;
-    const int ninner = g.ny * g.nzc;
-    const long cstride = (long)(g.plane / 2);
-    if (!ga || ga->kind == 0) {
-        if (g.nx == 1) return FGB_OK;
-        int T = pick_T(ctx, g.nx, 2, 0, 8);
-        if (!T) return fgb_fail(ctx, FGB_EUNSUPPORTED, "nx=%d does not fit shared memory", g.nx);
-        const size_t smem = (size_t)2 * g.nx * T * sizeof(double2);
-        dim3 grid((ninner + T - 1) / T, 1, ncomp);
-        ProfScope ps(ctx, dir < 0 ? "fft_x_fwd" : "fft_x_bwd");
-        if (dir < 0) {
-            FGB_CUDA(ctx, set_smem(k_fft_strided<-1>, smem));
-            k_fft_strided<-1><<<grid, 256, smem, ctx->stream>>>((double2*)base, ctx->plan[0], estride, ninner, 0, cstride, T);
-        } else {
-            FGB_CUDA(ctx, set_smem(k_fft_strided<1>, smem));
-            k_fft_strided<1><<<grid, 256, smem, ctx->stream>>>((double2*)base, ctx->plan[0], estride, ninner, 0, cstride, T);
-        }
-        FGB_CHECK_LAUNCH(ctx, "k_fft_strided<x>");
-        return FGB_OK;
-    }
-    GreenDev G;
     G.kind = ga->kind;
     G.c10 = ga->c10;
     G.c20 = ga->c20;
@@ -605,13 +497,33 @@ int fgb_fft_x(fgb_ctx* ctx, double* base, int ncomp, int dir, const GreenArgs* g
     G.freq_hack = ga->freq_hack;
     G.nx = g.nx; G.ny = g.ny; G.nz = g.nz;
     for (int a = 0; a < 3; a++) { G.kpm[a] = ctx->kpm_dev[a]; G.kp[a] = ctx->kp_dev[a]; G.xi[a] = ctx->xi_dev[a]; }
+}
+
+// x pass on a buffer whose x extent is complete: element (ii, jj, kk) at base[c*cstride + (jj-jbase)*ostride + ii*estride + kk]
+int fgb_fft_x_green_layout(fgb_ctx* ctx, double* base, const GreenArgs* ga, long estride, int nzc_valid, int nouter, long ostride,
+                           long cstride, int jbase) {
+    GreenDev G;
+    fill_green(ctx, ga, G);
     double2* b = (double2*)base;
+    ProfScope ps(ctx, "fft_x_green");
     switch (ga->kind) {
-        case 1: return launch_x_green<3, 1>(ctx, b, G, estride, ninner, 1, 0, cstride, 0, 0);
-        case 2: return launch_x_green<1, 2>(ctx, b, G, estride, ninner, 1, 0, cstride, 0, 0);
-        case 3: return launch_x_green<6, 3>(ctx, b, G, estride, ninner, 1, 0, cstride, 0, 0);
-        case 4: return launch_x_green<3, 4>(ctx, b, G, estride, ninner, 1, 0, cstride, 0, 0);
-        case 5: return launch_x_green<9, 5>(ctx, b, G, estride, ninner, 1, 0, cstride, 0, 0);
+        case 1: return launch_x_green<3, 1>(ctx, b, G, estride, nzc_valid, nouter, ostride, cstride, jbase);
+        case 2: return launch_x_green<1, 2>(ctx, b, G, estride, nzc_valid, nouter, ostride, cstride, jbase);
+        case 3: return launch_x_green<6, 3>(ctx, b, G, estride, nzc_valid, nouter, ostride, cstride, jbase);
+        case 4: return launch_x_green<3, 4>(ctx, b, G, estride, nzc_valid, nouter, ostride, cstride, jbase);
+        case 5: return launch_x_green<9, 5>(ctx, b, G, estride, nzc_valid, nouter, ostride, cstride, jbase);
     }
     return fgb_fail(ctx, FGB_EINVAL, "unknown Green operator kind %d", ga->kind);
+}
+
+int fgb_fft_x(fgb_ctx* ctx, double* base, int ncomp, const FftLayout& lay, int dir, const GreenArgs* ga) {
+    const GridDev& g = ctx->g;
+    if (ctx->nranks > 1) return fgb_fail(ctx, FGB_EUNSUPPORTED, "fgb_fft_x: slab-partitioned x pass goes through comm.cu");
+    const long estride = (long)g.ny * lay.nzcs;
+    const long cstride = (long)g.lnx * g.ny * lay.nzcs;
+    if (!ga || ga->kind == 0) {
+        ProfScope ps(ctx, dir < 0 ? "fft_x_fwd" : "fft_x_bwd");
+        return fft_strided(ctx, 0, (double2*)base, estride, g.nzc, g.ny, lay.nzcs, ncomp, cstride, dir);
+    }
+    return fgb_fft_x_green_layout(ctx, base, ga, estride, g.nzc, g.ny, lay.nzcs, cstride, 0);
 }

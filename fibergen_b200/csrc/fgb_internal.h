@@ -44,6 +44,8 @@ struct GridDev {
     int nx, ny, nz, nzc, nzp;   // global sizes
     int lnx, x0;                // local slab
     size_t plane;               // lnx*ny*nzp (doubles per component)
+    int unzcs;                  // complex row stride of the u buffer (nzc rounded up to a multiple of 8: 128-byte aligned rows)
+    size_t uplane;              // lnx*ny*2*unzcs (doubles per u component)
     double hx, hy, hz;          // nx/Lx ... (inverse voxel size, fg:18618-18620)
 };
 
@@ -136,10 +138,14 @@ struct ProfScope {
 // fft.cu -------------------------------------------------------------------------------------
 int fgb_fft_init(fgb_ctx* ctx);
 void fgb_fft_free(fgb_ctx* ctx);
-// in-place r2c/c2r along z of `ncomp` planes starting at base (plane stride ctx->g.plane)
-int fgb_fft_z_forward(fgb_ctx* ctx, double* base, int ncomp);
-int fgb_fft_z_backward(fgb_ctx* ctx, double* base, int ncomp);
-int fgb_fft_y(fgb_ctx* ctx, double* base, int ncomp, int dir);
+// row layout of a buffer being transformed: rows of nzcs complex (2*nzcs doubles), components lnx*ny rows apart
+struct FftLayout {
+    int nzcs;
+};
+// in-place r2c/c2r along z of `ncomp` components starting at base
+int fgb_fft_z_forward(fgb_ctx* ctx, double* base, int ncomp, const FftLayout& lay);
+int fgb_fft_z_backward(fgb_ctx* ctx, double* base, int ncomp, const FftLayout& lay);
+int fgb_fft_y(fgb_ctx* ctx, double* base, int ncomp, const FftLayout& lay, int dir);
 // x pass; green_kind: 0 none (plain forward or backward per dir), otherwise fused fwd-x, Green, inv-x
 struct GreenArgs {
     int kind;             // 0 none, 1 staggered elasticity/hyper (general), 2 staggered heat, 3 colloc elasticity, 4 colloc heat, 5 colloc hyper
@@ -148,7 +154,9 @@ struct GreenArgs {
     double dc[9];         // value of the zero frequency
     int freq_hack;
 };
-int fgb_fft_x(fgb_ctx* ctx, double* base, int ncomp, int dir, const GreenArgs* ga);
+int fgb_fft_x(fgb_ctx* ctx, double* base, int ncomp, const FftLayout& lay, int dir, const GreenArgs* ga);
+int fgb_fft_x_green_layout(fgb_ctx* ctx, double* base, const GreenArgs* ga, long estride, int nzc_valid, int nouter, long ostride,
+                           long cstride, int jbase);
 
 // stencil.cu ---------------------------------------------------------------------------------
 int fgb_k_div(fgb_ctx* ctx, const double* tau, double* u);
@@ -181,6 +189,6 @@ int fgb_allreduce_host(fgb_ctx* ctx, double* vals, int n, int op);
 // comm.cu ------------------------------------------------------------------------------------
 int fgb_comm_free(fgb_ctx* ctx);
 // slab-partitioned x pass: transpose -> fwd x, Green, inv x -> transpose back
-int fgb_comm_fft_x(fgb_ctx* ctx, double* base, int ncomp, const GreenArgs* ga);
+int fgb_comm_fft_x(fgb_ctx* ctx, double* base, int ncomp, const FftLayout& lay, const GreenArgs* ga);
 int fgb_comm_halo_tau(fgb_ctx* ctx, const double* tau);   // fills ctx->halo for k_div
 int fgb_comm_halo_u(fgb_ctx* ctx);                        // fills ctx->halo for k_eps

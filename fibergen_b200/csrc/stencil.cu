@@ -18,16 +18,16 @@ __device__ __forceinline__ const double* plane_ptr(const double* f, const GridDe
 
 // value of component plane `p` at (i+di, j, k) with periodic wrap in x or halo access
 __device__ __forceinline__ double at_x(const double* p, const GridDev& g, int i, int j, int k, int di, const double* halo_lo,
-                                       const double* halo_hi) {
+                                       const double* halo_hi, size_t rs) {
     int ii = i + di;
     if (halo_lo == nullptr) {
         if (ii < 0) ii += g.lnx;
         if (ii >= g.lnx) ii -= g.lnx;
-        return p[((size_t)ii * g.ny + j) * g.nzp + k];
+        return p[((size_t)ii * g.ny + j) * rs + k];
     }
     if (ii < 0) return halo_lo[(size_t)j * g.nzp + k];
     if (ii >= g.lnx) return halo_hi[(size_t)j * g.nzp + k];
-    return p[((size_t)ii * g.ny + j) * g.nzp + k];
+    return p[((size_t)ii * g.ny + j) * rs + k];
 }
 
 template <int D>
@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(256) k_div(const double* __restrict__ tau, dou
         const int j = (int)((v / g.nz) % g.ny);
         const int i = (int)(v / ((size_t)g.nz * g.ny));
         const size_t o = ((size_t)i * g.ny + j) * g.nzp + k;
+        const size_t uo = ((size_t)i * g.ny + j) * (2 * (size_t)g.unzcs) + k;
         const int jp = (j + 1 == g.ny) ? 0 : j + 1, jm = (j == 0) ? g.ny - 1 : j - 1;
         const int kp = (k + 1 == g.nz) ? 0 : k + 1, km = (k == 0) ? g.nz - 1 : k - 1;
         const size_t o_jp = ((size_t)i * g.ny + jp) * g.nzp + k, o_jm = ((size_t)i * g.ny + jm) * g.nzp + k;
@@ -47,23 +48,23 @@ __global__ void __launch_bounds__(256) k_div(const double* __restrict__ tau, dou
 #define T_(c) plane_ptr(tau, g, c)
         if (D == 3) {
             // halo_lo: [tau0 at i=-1]
-            double f = (T_(0)[o] - at_x(T_(0), g, i, j, k, -1, halo_lo, halo_hi)) * g.hx;
+            double f = (T_(0)[o] - at_x(T_(0), g, i, j, k, -1, halo_lo, halo_hi, (size_t)g.nzp)) * g.hx;
             f += (T_(1)[o] - T_(1)[o_jm]) * g.hy;
             f += (T_(2)[o] - T_(2)[o_km]) * g.hz;
-            u[o] = f;
+            u[uo] = f;
         } else {
             // shear operand indices: elasticity (5,4 | 5,3 | 4,3), hyper (5,4 | 8,3 | 7,6)
             const int c1x = (D == 6) ? 5 : 8, c2x = (D == 6) ? 4 : 7, c2y = (D == 6) ? 3 : 6;
             // halo_lo: [tau0 at -1]; halo_hi: [tau(c1x) at lnx, tau(c2x) at lnx]
-            const double f0 = (T_(0)[o] - at_x(T_(0), g, i, j, k, -1, halo_lo, halo_hi)) * g.hx + (T_(5)[o_jp] - T_(5)[o]) * g.hy +
+            const double f0 = (T_(0)[o] - at_x(T_(0), g, i, j, k, -1, halo_lo, halo_hi, (size_t)g.nzp)) * g.hx + (T_(5)[o_jp] - T_(5)[o]) * g.hy +
                               (T_(4)[o_kp] - T_(4)[o]) * g.hz;
-            const double f1 = (at_x(T_(c1x), g, i, j, k, +1, halo_lo, halo_hi) - T_(c1x)[o]) * g.hx + (T_(1)[o] - T_(1)[o_jm]) * g.hy +
+            const double f1 = (at_x(T_(c1x), g, i, j, k, +1, halo_lo, halo_hi, (size_t)g.nzp) - T_(c1x)[o]) * g.hx + (T_(1)[o] - T_(1)[o_jm]) * g.hy +
                               (T_(3)[o_kp] - T_(3)[o]) * g.hz;
-            const double f2 = (at_x(T_(c2x), g, i, j, k, +1, halo_lo, halo_hi ? halo_hi + hp : nullptr) - T_(c2x)[o]) * g.hx +
+            const double f2 = (at_x(T_(c2x), g, i, j, k, +1, halo_lo, halo_hi ? halo_hi + hp : nullptr, (size_t)g.nzp) - T_(c2x)[o]) * g.hx +
                               (T_(c2y)[o_jp] - T_(c2y)[o]) * g.hy + (T_(2)[o] - T_(2)[o_km]) * g.hz;
-            u[o] = f0;
-            u[g.plane + o] = f1;
-            u[2 * g.plane + o] = f2;
+            u[uo] = f0;
+            u[g.uplane + uo] = f1;
+            u[2 * g.uplane + uo] = f2;
         }
 #undef T_
     }
@@ -82,41 +83,43 @@ __global__ void __launch_bounds__(256) k_eps(const double* __restrict__ u, doubl
         const int k = (int)(v % g.nz);
         const int j = (int)((v / g.nz) % g.ny);
         const int i = (int)(v / ((size_t)g.nz * g.ny));
-        const size_t o = ((size_t)i * g.ny + j) * g.nzp + k;
+        const size_t eo = ((size_t)i * g.ny + j) * g.nzp + k;           // output (field layout)
+        const size_t us = 2 * (size_t)g.unzcs;                            // u row stride
         const int jp = (j + 1 == g.ny) ? 0 : j + 1, jm = (j == 0) ? g.ny - 1 : j - 1;
         const int kp = (k + 1 == g.nz) ? 0 : k + 1, km = (k == 0) ? g.nz - 1 : k - 1;
-        const size_t o_jp = ((size_t)i * g.ny + jp) * g.nzp + k, o_jm = ((size_t)i * g.ny + jm) * g.nzp + k;
-        const size_t o_kp = ((size_t)i * g.ny + j) * g.nzp + kp, o_km = ((size_t)i * g.ny + j) * g.nzp + km;
-#define U_(c) (u + (size_t)(c)*g.plane)
+        const size_t o = ((size_t)i * g.ny + j) * us + k;
+        const size_t o_jp = ((size_t)i * g.ny + jp) * us + k, o_jm = ((size_t)i * g.ny + jm) * us + k;
+        const size_t o_kp = ((size_t)i * g.ny + j) * us + kp, o_km = ((size_t)i * g.ny + j) * us + km;
+#define U_(c) (u + (size_t)(c)*g.uplane)
         // halo_lo: [u0,u1,u2 at i=-1], halo_hi: [u0 at i=lnx]
         if (D == 3) {
             const double u0 = U_(0)[o];
-            eta[o] = E.v[0] + (at_x(U_(0), g, i, j, k, +1, halo_lo, halo_hi) - u0) * g.hx;
-            eta[g.plane + o] = E.v[1] + (U_(0)[o_jp] - u0) * g.hy;
-            eta[2 * g.plane + o] = E.v[2] + (U_(0)[o_kp] - u0) * g.hz;
+            eta[eo] = E.v[0] + (at_x(U_(0), g, i, j, k, +1, halo_lo, halo_hi, us) - u0) * g.hx;
+            eta[g.plane + eo] = E.v[1] + (U_(0)[o_jp] - u0) * g.hy;
+            eta[2 * g.plane + eo] = E.v[2] + (U_(0)[o_kp] - u0) * g.hz;
         } else {
             const double u0 = U_(0)[o], u1 = U_(1)[o], u2 = U_(2)[o];
-            const double u0_xm = at_x(U_(0), g, i, j, k, -1, halo_lo, halo_hi);
-            const double u1_xm = at_x(U_(1), g, i, j, k, -1, halo_lo ? halo_lo + hp : nullptr, halo_hi);
-            const double u2_xm = at_x(U_(2), g, i, j, k, -1, halo_lo ? halo_lo + 2 * hp : nullptr, halo_hi);
+            const double u0_xm = at_x(U_(0), g, i, j, k, -1, halo_lo, halo_hi, us);
+            const double u1_xm = at_x(U_(1), g, i, j, k, -1, halo_lo ? halo_lo + hp : nullptr, halo_hi, us);
+            const double u2_xm = at_x(U_(2), g, i, j, k, -1, halo_lo ? halo_lo + 2 * hp : nullptr, halo_hi, us);
             (void)u0_xm;
-            const double e0 = E.v[0] + (at_x(U_(0), g, i, j, k, +1, halo_lo, halo_hi) - u0) * g.hx;
+            const double e0 = E.v[0] + (at_x(U_(0), g, i, j, k, +1, halo_lo, halo_hi, us) - u0) * g.hx;
             const double e1 = E.v[1] + (U_(1)[o_jp] - u1) * g.hy;
             const double e2 = E.v[2] + (U_(2)[o_kp] - u2) * g.hz;
-            eta[o] = e0;
-            eta[g.plane + o] = e1;
-            eta[2 * g.plane + o] = e2;
+            eta[eo] = e0;
+            eta[g.plane + eo] = e1;
+            eta[2 * g.plane + eo] = e2;
             if (D == 6) {
-                eta[3 * g.plane + o] = E.v[3] + 0.5 * ((u2 - U_(2)[o_jm]) * g.hy + (u1 - U_(1)[o_km]) * g.hz);
-                eta[4 * g.plane + o] = E.v[4] + 0.5 * ((u2 - u2_xm) * g.hx + (u0 - U_(0)[o_km]) * g.hz);
-                eta[5 * g.plane + o] = E.v[5] + 0.5 * ((u1 - u1_xm) * g.hx + (u0 - U_(0)[o_jm]) * g.hy);
+                eta[3 * g.plane + eo] = E.v[3] + 0.5 * ((u2 - U_(2)[o_jm]) * g.hy + (u1 - U_(1)[o_km]) * g.hz);
+                eta[4 * g.plane + eo] = E.v[4] + 0.5 * ((u2 - u2_xm) * g.hx + (u0 - U_(0)[o_km]) * g.hz);
+                eta[5 * g.plane + eo] = E.v[5] + 0.5 * ((u1 - u1_xm) * g.hx + (u0 - U_(0)[o_jm]) * g.hy);
             } else {
-                eta[3 * g.plane + o] = E.v[3] + (u1 - U_(1)[o_km]) * g.hz;
-                eta[4 * g.plane + o] = E.v[4] + (u0 - U_(0)[o_km]) * g.hz;
-                eta[5 * g.plane + o] = E.v[5] + (u0 - U_(0)[o_jm]) * g.hy;
-                eta[6 * g.plane + o] = E.v[6] + (u2 - U_(2)[o_jm]) * g.hy;
-                eta[7 * g.plane + o] = E.v[7] + (u2 - u2_xm) * g.hx;
-                eta[8 * g.plane + o] = E.v[8] + (u1 - u1_xm) * g.hx;
+                eta[3 * g.plane + eo] = E.v[3] + (u1 - U_(1)[o_km]) * g.hz;
+                eta[4 * g.plane + eo] = E.v[4] + (u0 - U_(0)[o_km]) * g.hz;
+                eta[5 * g.plane + eo] = E.v[5] + (u0 - U_(0)[o_jm]) * g.hy;
+                eta[6 * g.plane + eo] = E.v[6] + (u2 - U_(2)[o_jm]) * g.hy;
+                eta[7 * g.plane + eo] = E.v[7] + (u2 - u2_xm) * g.hx;
+                eta[8 * g.plane + eo] = E.v[8] + (u1 - u1_xm) * g.hx;
             }
         }
 #undef U_

@@ -236,3 +236,38 @@ def test_blas_and_reductions(n, mode, d):
     assert relerr(ctx.download(fb_), r1) < 1e-15
     assert abs(delta.value - o.innerProduct(r1, r1)) < 1e-12 * max(1.0, delta.value)
     ctx.close()
+
+
+@pytest.mark.parametrize("n", [(64, 64, 64), (128, 64, 256), (256, 128, 64), (64, 512, 128), (512, 64, 64), (64, 64, 1024), (1024, 64, 64)])
+def test_pow2_fast_paths(n):
+    """register-resident radix-8/16/32 passes (fft_pow2.cuh) on every supported axis length, forward/backward transform
+    and the fused x pass with the staggered / collocated Green operators"""
+    L = (1.0, 2.0, 1.5)
+    rng = np.random.default_rng(11)
+    # plain 3-D transform on a 3-component (heat) field
+    ctx = fb.Context(*n, *L, mode="heat", gamma_scheme="collocated")
+    o = fo.LSSolver(*n, *L, mode="heat", gamma_scheme="collocated")
+    x = rng.standard_normal((3,) + n)
+    f = ctx.field(x)
+    ctx.chk(ctx.lib.fgb_fft_forward(ctx.h, f))
+    got = ctx.download_padded(f).reshape(3, n[0], n[1], -1, 2)
+    assert relerr(got[..., 0] + 1j * got[..., 1], o.fft(x)) < 5e-14
+    ctx.chk(ctx.lib.fgb_fft_backward(ctx.h, f))
+    assert relerr(ctx.download(f), x) < 5e-14
+    o.set_reference(0.7, 0.0)
+    o.setBCProjector(fo.Id4(3))
+    E = rng.standard_normal(3)
+    ctx.gamma(f, E, 0.7, 0.0, -1.0, 0.5)
+    assert relerr(ctx.download(f), o.GammaOperator(E, 0.7, 0.0, x, -1.0, 0.5)) < 2e-12
+    ctx.close()
+    for mode, d in (("elasticity", 6), ("heat", 3)):
+        ctx = fb.Context(*n, *L, mode=mode, gamma_scheme="staggered")
+        o = fo.LSSolver(*n, *L, mode=mode, gamma_scheme="staggered")
+        o.set_reference(1.3, 0.4)
+        o.setBCProjector(fo.Id4(d))
+        tau = rng.standard_normal((d,) + n)
+        E = rng.standard_normal(d)
+        f = ctx.field(tau)
+        ctx.gamma(f, E, 1.3, 0.4, -1.0, 0.0)
+        assert relerr(ctx.download(f), o.GammaOperator(E, 1.3, 0.4, tau, -1.0, 0.0)) < 2e-12
+        ctx.close()
