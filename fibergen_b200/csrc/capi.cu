@@ -600,6 +600,12 @@ extern "C" int fgb_basic_step(fgb_ctx* c, int src, int dst, const double* E, dou
     CHECK_CTX(c); CHECK_FIELD(c, src); CHECK_FIELD(c, dst);
     int rc;
     if (c->bc_relax != 1.0 && (rc = fgb_k_component_dot(c, c->fields[src], nullptr, c->F00, 1))) return rc;   // fg:20563-20565
+    if (fgb_fused_iso_applicable(c) && !c->bc_active && c->bc_relax == 1.0) {
+        // fused: (C-C0):eps and div_h in one sweep, tau never written (calcStressDiff fg:18030 + divOperatorStaggered fg:18853)
+        if ((rc = fgb_k_dir_stress_div_iso(c, nullptr, 0.0, c->fields[src], nullptr, mu0, lambda0, 1.0))) return rc;
+        if ((rc = g0_staggered(c, mu0, lambda0, -1.0))) return rc;
+        return fgb_k_eps(c, c->ubuf, c->fields[dst], E);
+    }
     if ((rc = fgb_k_calc_stress(c, c->fields[src], c->fields[dst], mu0, lambda0, 1.0))) return rc;            // calcStressDiff fg:18030
     if (c->mode == FGB_MODE_VISCOSITY) {
         double* tmp;
@@ -644,6 +650,25 @@ extern "C" int fgb_cg_apply(fgb_ctx* c, int F, int p, int w, double mu0, double 
     }
     if (pAp) return fgb_k_inner(c, c->fields[p], c->fields[p], c->fields[w], pAp);
     return FGB_OK;
+}
+
+// One fused CG operator application: p_new = r + beta*p_old (skipped when r < 0, then p_new must equal p_old),
+// w = -Gamma0:(C-C0):p_new (or the tangent operator at F), pAp = <p_new, p_new - w>.
+extern "C" int fgb_cg_step(fgb_ctx* c, int F, int r, double beta, int p_old, int p_new, int w, double mu0, double lambda0, double* pAp) {
+    CHECK_CTX(c); CHECK_FIELD(c, p_old); CHECK_FIELD(c, p_new); CHECK_FIELD(c, w);
+    if (r >= 0) CHECK_FIELD(c, r);
+    if (r < 0 && p_old != p_new) return fgb_fail(c, FGB_EINVAL, "fgb_cg_step without a direction update needs p_new == p_old");
+    if (p_new == w) return fgb_fail(c, FGB_EINVAL, "krylovOperator cannot work in place (fg:20581)");
+    int rc;
+    if (F < 0 && fgb_fused_iso_applicable(c) && !c->bc_active && c->bc_relax == 1.0 && (r < 0 || p_old != p_new)) {
+        double zero[9] = {0};
+        if ((rc = fgb_k_dir_stress_div_iso(c, r >= 0 ? c->fields[r] : nullptr, beta, c->fields[p_old], c->fields[p_new], mu0, lambda0, 1.0))) return rc;
+        if ((rc = g0_staggered(c, mu0, lambda0, -1.0))) return rc;
+        if (pAp) return fgb_k_eps_dot(c, c->ubuf, c->fields[w], zero, c->fields[p_new], pAp);
+        return fgb_k_eps(c, c->ubuf, c->fields[w], zero);
+    }
+    if (r >= 0 && (rc = fgb_k_xpay(c, c->fields[p_new], c->fields[r], beta, c->fields[p_old]))) return rc;      // p = r + beta*p fg:23245
+    return fgb_cg_apply(c, F, p_new, w, mu0, lambda0, pAp);
 }
 
 extern "C" int fgb_cg_update(fgb_ctx* c, int x, int r, int p, int w, double a, double* delta) {

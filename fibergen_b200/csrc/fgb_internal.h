@@ -186,6 +186,14 @@ int fgb_k_cg_update(fgb_ctx* ctx, double* x, double* r, const double* p, const d
 int fgb_reduce_finish(fgb_ctx* ctx, int nblocks, int nvals, int op, double* host_out);
 int fgb_allreduce_host(fgb_ctx* ctx, double* vals, int n, int op);
 
+// fused.cu -----------------------------------------------------------------------------------
+int fgb_fused_iso_applicable(const fgb_ctx* ctx);
+// p_new = r + cgbeta*p_old (skipped when r == null), f = div (C-C0):p_new -> u buffer
+int fgb_k_dir_stress_div_iso(fgb_ctx* ctx, const double* r, double cgbeta, const double* p_old, double* p_new, double mu0, double lambda0,
+                             double alpha);
+// eta = E + sym-grad u and pAp = <p, p - eta>
+int fgb_k_eps_dot(fgb_ctx* ctx, const double* u, double* eta, const double* Econst, const double* p, double* pAp);
+
 // comm.cu ------------------------------------------------------------------------------------
 int fgb_comm_free(fgb_ctx* ctx);
 // slab-partitioned x pass: transpose -> fwd x, Green, inv x -> transpose back

@@ -1,0 +1,261 @@
+// Fused sweeps of the CG iteration for the staggered scheme (the bandwidth plan of DESIGN.md):
+//
+//   k_dir_stress_div_iso : p_new = r + beta*p_old                      (TensorField::xpay fg:9819, fg:23245)
+//                          tau   = (C - C0) : p_new                    (calcStress fg:18134, Voigt mixing fg:12752,
+//                                                                       LinearIsotropic fg:11375)
+//                          f     = div_h tau -> u buffer               (divOperatorStaggered fg:18853)
+//                          one pass: reads r, p_old, phi; writes p_new and the 3 rhs components.  tau never goes to HBM;
+//                          the stencil neighbours are re-evaluated from L1/L2-resident data (z neighbours by warp shuffle).
+//   k_eps_dot            : eta = E + sym-grad_h u                      (epsOperatorStaggered fg:18614, applyBCProjector fg:20263)
+//                          <p, p - eta>                                (innerProductL2 fg:20871) in the same pass.
+#include "fgb_internal.h"
+#include "reduce.cuh"
+
+struct IsoPhases {
+    int n;
+    const double* phi[FGB_MAX_PHASES];
+    double mu[FGB_MAX_PHASES], lam[FGB_MAX_PHASES];
+};
+
+struct Const9f {
+    double v[9];
+};
+
+#define FGB_VOIGT_THR (10 * 2.220446049250313e-16)
+
+// effective Voigt coefficients at a voxel, accumulated phase by phase like VoigtMixedMaterialLaw::PK1 does
+struct IsoCoef {
+    double two_mu[FGB_MAX_PHASES], lam[FGB_MAX_PHASES];
+    int n;
+};
+
+__device__ __forceinline__ void load_coef(const IsoPhases& M, size_t o, IsoCoef& c) {
+    c.n = 0;
+    c.two_mu[0] = 0;
+    c.lam[0] = 0;
+#pragma unroll 4
+    for (int p = 0; p < M.n; p++) {
+        const double phi = __ldg(M.phi[p] + o);
+        if (phi <= FGB_VOIGT_THR) continue;
+        c.two_mu[c.n] = 2 * phi * M.mu[p];      // two_mu = 2*alpha*mu with alpha = phi (fg:11381)
+        c.lam[c.n] = phi * M.lam[p];
+        c.n++;
+    }
+}
+
+// tau_c for a shear component (c >= 3): sum_p e*two_mu_p + beta*e
+__device__ __forceinline__ double tau_shear(const IsoCoef& c, double e, double beta) {
+    double s = e * c.two_mu[0];
+    for (int p = 1; p < c.n; p++) s += e * c.two_mu[p];
+    if (beta != 0) s += beta * e;
+    return s;
+}
+
+// tau_0..2 from the three diagonal strains
+__device__ __forceinline__ void tau_diag(const IsoCoef& c, double e0, double e1, double e2, double beta, double gamma, double& t0,
+                                         double& t1, double& t2) {
+    const double tr = e0 + e1 + e2;
+    double ltr = c.lam[0] * tr;
+    t0 = e0 * c.two_mu[0] + ltr;
+    t1 = e1 * c.two_mu[0] + ltr;
+    t2 = e2 * c.two_mu[0] + ltr;
+    for (int p = 1; p < c.n; p++) {
+        ltr = c.lam[p] * tr;
+        t0 += e0 * c.two_mu[p] + ltr;
+        t1 += e1 * c.two_mu[p] + ltr;
+        t2 += e2 * c.two_mu[p] + ltr;
+    }
+    if (beta != 0) { t0 += beta * e0; t1 += beta * e1; t2 += beta * e2; }
+    if (gamma != 0) { t0 += gamma * tr; t1 += gamma * tr; t2 += gamma * tr; }
+}
+
+template <int UPDATE>
+__device__ __forceinline__ double pval(const double* __restrict__ r, const double* __restrict__ p, size_t idx, double cgbeta) {
+    if (UPDATE) return __ldg(r + idx) + cgbeta * __ldg(p + idx);
+    return __ldg(p + idx);
+}
+
+// one CTA walks JB consecutive y rows of one x plane; a thread owns the voxels k = threadIdx.x + m*blockDim.x of each row
+template <int UPDATE>
+__global__ void __launch_bounds__(256) k_dir_stress_div_iso(const double* __restrict__ r, const double* __restrict__ p_old,
+                                                            double* __restrict__ p_new, double* __restrict__ u, GridDev g, IsoPhases M,
+                                                            double cgbeta, double beta, double gamma, int JB) {
+    const int jblocks = (g.ny + JB - 1) / JB;
+    const int i = blockIdx.x / jblocks;
+    const int j0 = (blockIdx.x - i * jblocks) * JB;
+    const int im = (i == 0) ? g.lnx - 1 : i - 1, ip = (i + 1 == g.lnx) ? 0 : i + 1;
+    const size_t P = g.plane;
+    const int lane = threadIdx.x & 31;
+    for (int jj = 0; jj < JB; jj++) {
+        const int j = j0 + jj;
+        if (j >= g.ny) break;
+        const int jm = (j == 0) ? g.ny - 1 : j - 1, jp = (j + 1 == g.ny) ? 0 : j + 1;
+        const size_t row = ((size_t)i * g.ny + j) * g.nzp;
+        const size_t row_im = ((size_t)im * g.ny + j) * g.nzp, row_ip = ((size_t)ip * g.ny + j) * g.nzp;
+        const size_t row_jm = ((size_t)i * g.ny + jm) * g.nzp, row_jp = ((size_t)i * g.ny + jp) * g.nzp;
+        const size_t urow = ((size_t)i * g.ny + j) * (2 * (size_t)g.unzcs);
+        for (int k0 = 0; k0 < g.nz; k0 += blockDim.x) {
+            const int k = k0 + threadIdx.x;
+            const bool active = k < g.nz;
+            double t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0;
+            IsoCoef c;
+            size_t o = row + k;
+            if (active) {
+                double e[6];
+#pragma unroll
+                for (int d = 0; d < 6; d++) e[d] = pval<UPDATE>(r, p_old, d * P + o, cgbeta);
+                if (UPDATE) {
+#pragma unroll
+                    for (int d = 0; d < 6; d++) p_new[d * P + o] = e[d];
+                }
+                load_coef(M, o, c);
+                tau_diag(c, e[0], e[1], e[2], beta, gamma, t0, t1, t2);
+                t3 = tau_shear(c, e[3], beta);
+                t4 = tau_shear(c, e[4], beta);
+                t5 = tau_shear(c, e[5], beta);
+            }
+            // z neighbours: tau4, tau3 at k+1 and tau2 at k-1 come from the adjacent lanes whenever they hold them
+            double t4_kp = __shfl_down_sync(0xffffffffu, t4, 1);
+            double t3_kp = __shfl_down_sync(0xffffffffu, t3, 1);
+            double t2_km = __shfl_up_sync(0xffffffffu, t2, 1);
+            if (!active) continue;
+            if (lane == 31 || k + 1 >= g.nz) {
+                const int kp = (k + 1 == g.nz) ? 0 : k + 1;
+                IsoCoef cn;
+                load_coef(M, row + kp, cn);
+                t4_kp = tau_shear(cn, pval<UPDATE>(r, p_old, 4 * P + row + kp, cgbeta), beta);
+                t3_kp = tau_shear(cn, pval<UPDATE>(r, p_old, 3 * P + row + kp, cgbeta), beta);
+            }
+            if (lane == 0 || k == 0) {
+                const int km = (k == 0) ? g.nz - 1 : k - 1;
+                IsoCoef cn;
+                load_coef(M, row + km, cn);
+                double a, b;
+                tau_diag(cn, pval<UPDATE>(r, p_old, row + km, cgbeta), pval<UPDATE>(r, p_old, P + row + km, cgbeta),
+                         pval<UPDATE>(r, p_old, 2 * P + row + km, cgbeta), beta, gamma, a, b, t2_km);
+            }
+            // x and y neighbours: re-evaluate the needed stress components from r, p_old, phi (L1/L2 hits)
+            double t0_im, t1_jm, dmy0, dmy1;
+            {
+                IsoCoef cn;
+                load_coef(M, row_im + k, cn);
+                tau_diag(cn, pval<UPDATE>(r, p_old, row_im + k, cgbeta), pval<UPDATE>(r, p_old, P + row_im + k, cgbeta),
+                         pval<UPDATE>(r, p_old, 2 * P + row_im + k, cgbeta), beta, gamma, t0_im, dmy0, dmy1);
+                load_coef(M, row_jm + k, cn);
+                tau_diag(cn, pval<UPDATE>(r, p_old, row_jm + k, cgbeta), pval<UPDATE>(r, p_old, P + row_jm + k, cgbeta),
+                         pval<UPDATE>(r, p_old, 2 * P + row_jm + k, cgbeta), beta, gamma, dmy0, t1_jm, dmy1);
+            }
+            double t5_ip, t4_ip, t5_jp, t3_jp;
+            {
+                IsoCoef cn;
+                load_coef(M, row_ip + k, cn);
+                t5_ip = tau_shear(cn, pval<UPDATE>(r, p_old, 5 * P + row_ip + k, cgbeta), beta);
+                t4_ip = tau_shear(cn, pval<UPDATE>(r, p_old, 4 * P + row_ip + k, cgbeta), beta);
+                load_coef(M, row_jp + k, cn);
+                t5_jp = tau_shear(cn, pval<UPDATE>(r, p_old, 5 * P + row_jp + k, cgbeta), beta);
+                t3_jp = tau_shear(cn, pval<UPDATE>(r, p_old, 3 * P + row_jp + k, cgbeta), beta);
+            }
+            // divOperatorStaggered fg:18863-18901
+            const double f0 = (t0 - t0_im) * g.hx + (t5_jp - t5) * g.hy + (t4_kp - t4) * g.hz;
+            const double f1 = (t5_ip - t5) * g.hx + (t1 - t1_jm) * g.hy + (t3_kp - t3) * g.hz;
+            const double f2 = (t4_ip - t4) * g.hx + (t3_jp - t3) * g.hy + (t2 - t2_km) * g.hz;
+            u[urow + k] = f0;
+            u[g.uplane + urow + k] = f1;
+            u[2 * g.uplane + urow + k] = f2;
+        }
+    }
+}
+
+// eta = E + sym-grad_h u (elasticity), and sum_voxels p:(p - eta) with Voigt weights
+__global__ void __launch_bounds__(256) k_eps_dot6(const double* __restrict__ u, double* __restrict__ eta, const double* __restrict__ p,
+                                                  GridDev g, Const9f E, double* __restrict__ partials) {
+    const unsigned nvox = (unsigned)g.lnx * (unsigned)g.ny * (unsigned)g.nz;
+    const size_t us = 2 * (size_t)g.unzcs;
+    double acc = 0;
+    for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += gridDim.x * blockDim.x) {
+        const unsigned row_ = v / (unsigned)g.nz;
+        const int k = (int)(v - row_ * (unsigned)g.nz);
+        const int i = (int)(row_ / (unsigned)g.ny);
+        const int j = (int)(row_ - (unsigned)i * (unsigned)g.ny);
+        const int im = (i == 0) ? g.lnx - 1 : i - 1, ip = (i + 1 == g.lnx) ? 0 : i + 1;
+        const int jm = (j == 0) ? g.ny - 1 : j - 1, jp = (j + 1 == g.ny) ? 0 : j + 1;
+        const int km = (k == 0) ? g.nz - 1 : k - 1, kp = (k + 1 == g.nz) ? 0 : k + 1;
+        const size_t o = (size_t)row_ * us + k;
+        const size_t o_im = ((size_t)im * g.ny + j) * us + k, o_ip = ((size_t)ip * g.ny + j) * us + k;
+        const size_t o_jm = ((size_t)i * g.ny + jm) * us + k, o_jp = ((size_t)i * g.ny + jp) * us + k;
+        const size_t o_km = (size_t)row_ * us + km, o_kp = (size_t)row_ * us + kp;
+        const double* u0p = u;
+        const double* u1p = u + g.uplane;
+        const double* u2p = u + 2 * g.uplane;
+        const double u0 = u0p[o], u1 = u1p[o], u2 = u2p[o];
+        double e[6];
+        e[0] = E.v[0] + (u0p[o_ip] - u0) * g.hx;
+        e[1] = E.v[1] + (u1p[o_jp] - u1) * g.hy;
+        e[2] = E.v[2] + (u2p[o_kp] - u2) * g.hz;
+        e[3] = E.v[3] + 0.5 * ((u2 - u2p[o_jm]) * g.hy + (u1 - u1p[o_km]) * g.hz);
+        e[4] = E.v[4] + 0.5 * ((u2 - u2p[o_im]) * g.hx + (u0 - u0p[o_km]) * g.hz);
+        e[5] = E.v[5] + 0.5 * ((u1 - u1p[o_im]) * g.hx + (u0 - u0p[o_jm]) * g.hy);
+        const size_t eo = (size_t)row_ * g.nzp + k;
+        double s = 0;
+#pragma unroll
+        for (int d = 0; d < 6; d++) {
+            eta[d * g.plane + eo] = e[d];
+            const double pv = __ldg(p + d * g.plane + eo);
+            s += ((d >= 3) ? 2.0 : 1.0) * pv * (pv - e[d]);
+        }
+        acc += s;
+    }
+    double vals[1] = {acc};
+    block_reduce_store<1, 0>(vals, partials);
+}
+
+// ------------------------------------------------------------------------------------------------
+// returns 1 if the fused path applies to this context (D = 6 elasticity, staggered, Voigt, all phases isotropic, one rank)
+int fgb_fused_iso_applicable(const fgb_ctx* ctx) {
+    if (ctx->dim != 6 || ctx->mode != FGB_MODE_ELASTICITY || ctx->scheme != FGB_GAMMA_STAGGERED) return 0;
+    if (ctx->mix != FGB_MIX_VOIGT || ctx->nranks != 1 || ctx->nphases < 1) return 0;
+    for (int p = 0; p < ctx->nphases; p++)
+        if (ctx->laws[p].id != FGB_LAW_ISO || !ctx->phi[p]) return 0;
+    return 1;
+}
+
+int fgb_k_dir_stress_div_iso(fgb_ctx* ctx, const double* r, double cgbeta, const double* p_old, double* p_new, double mu0, double lambda0,
+                             double alpha) {
+    IsoPhases M;
+    M.n = ctx->nphases;
+    for (int p = 0; p < ctx->nphases; p++) {
+        M.phi[p] = ctx->phi[p];
+        M.mu[p] = alpha * ctx->laws[p].p[0];
+        M.lam[p] = alpha * ctx->laws[p].p[1];
+    }
+    const double beta = -alpha * 2 * mu0, gamma = -alpha * lambda0;
+    const GridDev& g = ctx->g;
+    const int JB = 4;
+    const unsigned grid = (unsigned)(g.lnx * ((g.ny + JB - 1) / JB));
+    int threads = 256;
+    while (threads > 32 && threads / 2 >= g.nz) threads /= 2;
+    ProfScope ps(ctx, r ? "cg_direction_stress_div" : "stress_div");
+    if (r) k_dir_stress_div_iso<1><<<grid, threads, 0, ctx->stream>>>(r, p_old, p_new, ctx->ubuf, g, M, cgbeta, beta, gamma, JB);
+    else k_dir_stress_div_iso<0><<<grid, threads, 0, ctx->stream>>>(nullptr, p_old, nullptr, ctx->ubuf, g, M, 0.0, beta, gamma, JB);
+    FGB_CHECK_LAUNCH(ctx, "k_dir_stress_div_iso");
+    return FGB_OK;
+}
+
+int fgb_k_eps_dot(fgb_ctx* ctx, const double* u, double* eta, const double* Econst, const double* p, double* pAp) {
+    const GridDev& g = ctx->g;
+    Const9f E;
+    for (int i = 0; i < 9; i++) E.v[i] = i < 6 ? Econst[i] : 0.0;
+    const size_t nvox = (size_t)g.lnx * g.ny * g.nz;
+    size_t b = (nvox + 255) / 256;
+    if (b > (size_t)ctx->red_blocks) b = ctx->red_blocks;
+    const unsigned grid = (unsigned)b;
+    {
+        ProfScope ps(ctx, "eps_dot");
+        k_eps_dot6<<<grid, 256, 0, ctx->stream>>>(u, eta, p, g, E, ctx->d_partials);
+        FGB_CHECK_LAUNCH(ctx, "k_eps_dot6");
+    }
+    int rc = fgb_reduce_finish(ctx, grid, 1, 0, pAp);
+    if (rc) return rc;
+    pAp[0] /= (double)g.nx * g.ny * g.nz;
+    return FGB_OK;
+}

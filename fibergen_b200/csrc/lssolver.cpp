@@ -660,19 +660,24 @@ void LSSolver::runCGElasticity(const Vec& E0, const Vec& S0) {
     if (_update_ref != "never") calcRefMaterial();
     Vec E = calcBCMean(E0, S0);
     std::unique_ptr<ErrorEstimator> ee(create_error_estimator());
-    const int r = field(_f1), p = field(_f2), w = field(_f3);
+    const int r = field(_f1), w = field(_f3);
+    int p = field(_f2), p2 = field(_f4);                                                    // direction vector, ping-pong
     check(fgb_set_constant(_ctx, _epsilon, E.data()));
-    check(fgb_cg_apply(_ctx, -1, _epsilon, r, _mu_0, _lambda_0, nullptr));                 // krylovOperator(epsilon -> r)
+    check(fgb_cg_step(_ctx, -1, -1, 0.0, _epsilon, _epsilon, r, _mu_0, _lambda_0, nullptr)); // krylovOperator(epsilon -> r)
     check(fgb_adjust_residual(_ctx, r, E.data(), _epsilon));
     double gamma;
     check(fgb_inner(_ctx, r, r, -1, &gamma));
     gamma += SMALL;
     const double gamma0 = gamma;
-    check(fgb_copy(_ctx, r, p));
+    Vec zero(_dim, 0.0);
+    check(fgb_set_constant(_ctx, p, zero.data()));
+    double beta = 0.0;                                                                       // p = r  ==  r + 0*p
     size_t iter = 0;
     for (;;) {
         double alpha;
-        check(fgb_cg_apply(_ctx, -1, p, w, _mu_0, _lambda_0, &alpha));                     // w = MinusB(p); alpha = <p, p-w>
+        // p2 = r + beta*p ; w = MinusB(p2) ; alpha = <p2, p2 - w>   (fg:23245, fg:23209, fg:23211)
+        check(fgb_cg_step(_ctx, -1, r, beta, p, p2, w, _mu_0, _lambda_0, &alpha));
+        std::swap(p, p2);
         alpha += SMALL;
         alpha = gamma / alpha;
         if (_cg_reinit > 0) {
@@ -681,7 +686,7 @@ void LSSolver::runCGElasticity(const Vec& E0, const Vec& S0) {
             ee->update_cg(gamma, gamma0);
             if (converged(iter, ee->abs_error(), ee->rel_error())) break;
             if ((iter % _cg_reinit) == 0) {
-                check(fgb_cg_apply(_ctx, -1, _epsilon, r, _mu_0, _lambda_0, nullptr));
+                check(fgb_cg_step(_ctx, -1, -1, 0.0, _epsilon, _epsilon, r, _mu_0, _lambda_0, nullptr));
                 check(fgb_adjust_residual(_ctx, r, E.data(), _epsilon));
             } else {
                 check(fgb_xpaymz(_ctx, r, r, -alpha, p, w));
@@ -689,9 +694,8 @@ void LSSolver::runCGElasticity(const Vec& E0, const Vec& S0) {
             double delta;
             check(fgb_inner(_ctx, r, r, -1, &delta));
             delta += SMALL;
-            const double beta = delta / gamma;
+            beta = delta / gamma;
             gamma = delta;
-            check(fgb_cg_direction(_ctx, p, r, beta));
             continue;
         }
         // fused sweep: epsilon += alpha*p ; r -= alpha*(p - w) ; delta = <r,r>.  The residual update is independent of
@@ -701,9 +705,8 @@ void LSSolver::runCGElasticity(const Vec& E0, const Vec& S0) {
         ee->update_cg(gamma, gamma0);
         if (converged(iter, ee->abs_error(), ee->rel_error())) break;
         delta += SMALL;
-        const double beta = delta / gamma;
+        beta = delta / gamma;
         gamma = delta;
-        check(fgb_cg_direction(_ctx, p, r, beta));                                          // p = r + beta*p
     }
 }
 

@@ -32,10 +32,13 @@ MaterialDev fgb_material_dev(fgb_ctx* ctx) {
     return M;
 }
 
+// 32-bit voxel index arithmetic (a slab never exceeds 2^32 voxels); 64-bit divisions were the bottleneck of v1
 #define VOXEL_LOOP(g)                                                                                              \
-    const size_t nvox = (size_t)g.lnx * g.ny * g.nz;                                                               \
-    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (size_t)gridDim.x * blockDim.x)
-#define VOXEL_OFFSET(g) const size_t o = (v / g.nz) * g.nzp + (v % g.nz);
+    const unsigned nvox = (unsigned)g.lnx * (unsigned)g.ny * (unsigned)g.nz;                                       \
+    for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += gridDim.x * blockDim.x)
+#define VOXEL_OFFSET(g)                         \
+    const unsigned row_ = v / (unsigned)g.nz;   \
+    const size_t o = (size_t)row_ * g.nzp + (v - row_ * (unsigned)g.nz);
 
 // sigma = alpha*P_mix(eps) + beta*eps + gamma*tr(eps)*I ; DERIV: with dP_mix/dF(F):W and W in the correction terms
 template <int D, int DERIV>

@@ -33,12 +33,13 @@ __device__ __forceinline__ double at_x(const double* p, const GridDev& g, int i,
 template <int D>
 __global__ void __launch_bounds__(256) k_div(const double* __restrict__ tau, double* __restrict__ u, GridDev g,
                                              const double* __restrict__ halo_lo, const double* __restrict__ halo_hi) {
-    const size_t nvox = (size_t)g.lnx * g.ny * g.nz;
+    const unsigned nvox = (unsigned)g.lnx * (unsigned)g.ny * (unsigned)g.nz;
     const size_t hp = (size_t)g.ny * g.nzp;   // halo plane size
-    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (size_t)gridDim.x * blockDim.x) {
-        const int k = (int)(v % g.nz);
-        const int j = (int)((v / g.nz) % g.ny);
-        const int i = (int)(v / ((size_t)g.nz * g.ny));
+    for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += gridDim.x * blockDim.x) {
+        const unsigned row_ = v / (unsigned)g.nz;
+        const int k = (int)(v - row_ * (unsigned)g.nz);
+        const int i = (int)(row_ / (unsigned)g.ny);
+        const int j = (int)(row_ - (unsigned)i * (unsigned)g.ny);
         const size_t o = ((size_t)i * g.ny + j) * g.nzp + k;
         const size_t uo = ((size_t)i * g.ny + j) * (2 * (size_t)g.unzcs) + k;
         const int jp = (j + 1 == g.ny) ? 0 : j + 1, jm = (j == 0) ? g.ny - 1 : j - 1;
@@ -77,12 +78,13 @@ struct Const9 {
 template <int D>
 __global__ void __launch_bounds__(256) k_eps(const double* __restrict__ u, double* __restrict__ eta, GridDev g, Const9 E,
                                              const double* __restrict__ halo_lo, const double* __restrict__ halo_hi) {
-    const size_t nvox = (size_t)g.lnx * g.ny * g.nz;
+    const unsigned nvox = (unsigned)g.lnx * (unsigned)g.ny * (unsigned)g.nz;
     const size_t hp = (size_t)g.ny * g.nzp;
-    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (size_t)gridDim.x * blockDim.x) {
-        const int k = (int)(v % g.nz);
-        const int j = (int)((v / g.nz) % g.ny);
-        const int i = (int)(v / ((size_t)g.nz * g.ny));
+    for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += gridDim.x * blockDim.x) {
+        const unsigned row_ = v / (unsigned)g.nz;
+        const int k = (int)(v - row_ * (unsigned)g.nz);
+        const int i = (int)(row_ / (unsigned)g.ny);
+        const int j = (int)(row_ - (unsigned)i * (unsigned)g.ny);
         const size_t eo = ((size_t)i * g.ny + j) * g.nzp + k;           // output (field layout)
         const size_t us = 2 * (size_t)g.unzcs;                            // u row stride
         const int jp = (j + 1 == g.ny) ? 0 : j + 1, jm = (j == 0) ? g.ny - 1 : j - 1;

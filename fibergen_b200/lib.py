@@ -79,6 +79,7 @@ PROTOTYPES = {
     "fgb_basic_step": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_dp, C.c_double, C.c_double]),
     "fgb_polarization_step": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_dp, C.c_double, C.c_double]),
     "fgb_cg_apply": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, c_dp]),
+    "fgb_cg_step": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, c_dp]),
     "fgb_cg_update": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, c_dp]),
     "fgb_cg_direction": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double]),
     "fgb_check_numeric": (C.c_int, [C.c_void_p]),

@@ -182,6 +182,10 @@ int  fgb_polarization_step(fgb_ctx* ctx, int src, int dst, const double* P0, dou
  * fgb_cg_update: x += a*p ; r -= a*(p - w) ; returns delta = <r, r>          (fg:23221, fg:23237-23240)
  * fgb_cg_direction: p = r + beta*p                                          (fg:23245)            */
 int  fgb_cg_apply(fgb_ctx* ctx, int F_or_neg, int p, int w, double mu0, double lambda0, double* pAp);
+/* fused form of "fgb_cg_direction then fgb_cg_apply": p_new = r + beta*p_old (r < 0: no update, p_new == p_old), then the
+ * operator on p_new.  With p_new != p_old the direction update, the constitutive law and div_h run as ONE sweep and
+ * sym-grad_h + <p, p - w> as another (staggered scheme, isotropic phases, Voigt mixing); otherwise it composes the calls above. */
+int  fgb_cg_step(fgb_ctx* ctx, int F_or_neg, int r_or_neg, double beta, int p_old, int p_new, int w, double mu0, double lambda0, double* pAp);
 int  fgb_cg_update(fgb_ctx* ctx, int x, int r, int p, int w, double a, double* delta);
 int  fgb_cg_direction(fgb_ctx* ctx, int p, int r, double beta);
 /* returns FGB_ENUMERIC if a material law flagged a domain error since the last call (fg:10293, fg:21202) */
