@@ -37,7 +37,7 @@ KERNEL_BYTES_PER_VOXEL = {
     "calc_stress": (6 + 1 + 6) * 8, "div_staggered": (6 + 3) * 8, "fft_z_r2c": 2 * 3 * 8, "fft_y_fwd": 2 * 3 * 8,
     "fft_x_green": 2 * 3 * 8, "fft_y_bwd": 2 * 3 * 8, "fft_z_c2r": 2 * 3 * 8, "eps_staggered": (3 + 6) * 8,
     "inner_product": 2 * 6 * 8 + 6 * 8, "cg_update": 6 * 6 * 8, "xpay": 3 * 6 * 8,
-    "stress_div_fftz": (6 + 1 + 3) * 8, "fftz_eps_dot": (3 + 6 + 6) * 8, "cg_direction_stress_div_fftz": (12 + 1 + 6 + 3) * 8,
+    "cg_direction_stress_div": (12 + 1 + 6 + 3) * 8, "stress_div": (6 + 1 + 3) * 8, "eps_dot": (3 + 6 + 6) * 8,
 }
 
 
@@ -216,6 +216,7 @@ def run_cuda(args):
     ctxobj = fb.Context.__new__(fb.Context)
     ctxobj.lib, ctxobj.h = s.lib, ctxp
     prof = fb.Context.profile_results(ctxobj)
+    ctxobj.h = None          # borrowed handle: the solver owns the context
     s.lib.fgb_profile_enable(ctxp, 0)
     peak, peak_src = peaks()
     nloc = nxyz // world

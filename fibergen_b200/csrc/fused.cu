@@ -23,50 +23,64 @@ struct Const9f {
 
 #define FGB_VOIGT_THR (10 * 2.220446049250313e-16)
 
-// effective Voigt coefficients at a voxel, accumulated phase by phase like VoigtMixedMaterialLaw::PK1 does
-struct IsoCoef {
-    double two_mu[FGB_MAX_PHASES], lam[FGB_MAX_PHASES];
-    int n;
-};
+// Voigt-mixed isotropic stress, accumulated phase by phase like VoigtMixedMaterialLaw::PK1 (fg:12752) with
+// LinearIsotropicMaterialLaw::PK1 (fg:11375): S += E*two_mu_p + lambda_p*tr, two_mu_p = 2*phi_p*mu_p.  No per-voxel
+// arrays (they would live in local memory): every helper walks the phases once and keeps its sums in registers.
 
-__device__ __forceinline__ void load_coef(const IsoPhases& M, size_t o, IsoCoef& c) {
-    c.n = 0;
-    c.two_mu[0] = 0;
-    c.lam[0] = 0;
-#pragma unroll 4
+// tau_a, tau_b for two shear components at voxel o
+__device__ __forceinline__ void tau_shear2(const IsoPhases& M, size_t o, double ea, double eb, double beta, double& ta, double& tb) {
+    ta = 0;
+    tb = 0;
     for (int p = 0; p < M.n; p++) {
         const double phi = __ldg(M.phi[p] + o);
         if (phi <= FGB_VOIGT_THR) continue;
-        c.two_mu[c.n] = 2 * phi * M.mu[p];      // two_mu = 2*alpha*mu with alpha = phi (fg:11381)
-        c.lam[c.n] = phi * M.lam[p];
-        c.n++;
+        const double two_mu = 2 * phi * M.mu[p];
+        ta += ea * two_mu;
+        tb += eb * two_mu;
     }
+    if (beta != 0) { ta += beta * ea; tb += beta * eb; }
 }
 
-// tau_c for a shear component (c >= 3): sum_p e*two_mu_p + beta*e
-__device__ __forceinline__ double tau_shear(const IsoCoef& c, double e, double beta) {
-    double s = e * c.two_mu[0];
-    for (int p = 1; p < c.n; p++) s += e * c.two_mu[p];
-    if (beta != 0) s += beta * e;
-    return s;
-}
-
-// tau_0..2 from the three diagonal strains
-__device__ __forceinline__ void tau_diag(const IsoCoef& c, double e0, double e1, double e2, double beta, double gamma, double& t0,
-                                         double& t1, double& t2) {
+// tau_0..2 from the three diagonal strains at voxel o
+__device__ __forceinline__ void tau_diag(const IsoPhases& M, size_t o, double e0, double e1, double e2, double beta, double gamma,
+                                         double& t0, double& t1, double& t2) {
     const double tr = e0 + e1 + e2;
-    double ltr = c.lam[0] * tr;
-    t0 = e0 * c.two_mu[0] + ltr;
-    t1 = e1 * c.two_mu[0] + ltr;
-    t2 = e2 * c.two_mu[0] + ltr;
-    for (int p = 1; p < c.n; p++) {
-        ltr = c.lam[p] * tr;
-        t0 += e0 * c.two_mu[p] + ltr;
-        t1 += e1 * c.two_mu[p] + ltr;
-        t2 += e2 * c.two_mu[p] + ltr;
+    t0 = t1 = t2 = 0;
+    for (int p = 0; p < M.n; p++) {
+        const double phi = __ldg(M.phi[p] + o);
+        if (phi <= FGB_VOIGT_THR) continue;
+        const double two_mu = 2 * phi * M.mu[p];
+        const double ltr = (phi * M.lam[p]) * tr;
+        t0 += e0 * two_mu + ltr;
+        t1 += e1 * two_mu + ltr;
+        t2 += e2 * two_mu + ltr;
     }
     if (beta != 0) { t0 += beta * e0; t1 += beta * e1; t2 += beta * e2; }
     if (gamma != 0) { t0 += gamma * tr; t1 += gamma * tr; t2 += gamma * tr; }
+}
+
+// all six components at voxel o
+__device__ __forceinline__ void tau_all(const IsoPhases& M, size_t o, const double* e, double beta, double gamma, double* t) {
+    const double tr = e[0] + e[1] + e[2];
+#pragma unroll
+    for (int d = 0; d < 6; d++) t[d] = 0;
+    for (int p = 0; p < M.n; p++) {
+        const double phi = __ldg(M.phi[p] + o);
+        if (phi <= FGB_VOIGT_THR) continue;
+        const double two_mu = 2 * phi * M.mu[p];
+        const double ltr = (phi * M.lam[p]) * tr;
+        t[0] += e[0] * two_mu + ltr;
+        t[1] += e[1] * two_mu + ltr;
+        t[2] += e[2] * two_mu + ltr;
+        t[3] += e[3] * two_mu;
+        t[4] += e[4] * two_mu;
+        t[5] += e[5] * two_mu;
+    }
+    if (beta != 0) {
+#pragma unroll
+        for (int d = 0; d < 6; d++) t[d] += beta * e[d];
+    }
+    if (gamma != 0) { t[0] += gamma * tr; t[1] += gamma * tr; t[2] += gamma * tr; }
 }
 
 template <int UPDATE>
@@ -97,9 +111,8 @@ __global__ void __launch_bounds__(256) k_dir_stress_div_iso(const double* __rest
         for (int k0 = 0; k0 < g.nz; k0 += blockDim.x) {
             const int k = k0 + threadIdx.x;
             const bool active = k < g.nz;
-            double t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0;
-            IsoCoef c;
-            size_t o = row + k;
+            double t[6] = {0, 0, 0, 0, 0, 0};
+            const size_t o = row + k;
             if (active) {
                 double e[6];
 #pragma unroll
@@ -108,52 +121,37 @@ __global__ void __launch_bounds__(256) k_dir_stress_div_iso(const double* __rest
 #pragma unroll
                     for (int d = 0; d < 6; d++) p_new[d * P + o] = e[d];
                 }
-                load_coef(M, o, c);
-                tau_diag(c, e[0], e[1], e[2], beta, gamma, t0, t1, t2);
-                t3 = tau_shear(c, e[3], beta);
-                t4 = tau_shear(c, e[4], beta);
-                t5 = tau_shear(c, e[5], beta);
+                tau_all(M, o, e, beta, gamma, t);
             }
+            const double t0 = t[0], t1 = t[1], t2 = t[2], t3 = t[3], t4 = t[4], t5 = t[5];
             // z neighbours: tau4, tau3 at k+1 and tau2 at k-1 come from the adjacent lanes whenever they hold them
             double t4_kp = __shfl_down_sync(0xffffffffu, t4, 1);
             double t3_kp = __shfl_down_sync(0xffffffffu, t3, 1);
             double t2_km = __shfl_up_sync(0xffffffffu, t2, 1);
             if (!active) continue;
+            double dmy0, dmy1;
             if (lane == 31 || k + 1 >= g.nz) {
-                const int kp = (k + 1 == g.nz) ? 0 : k + 1;
-                IsoCoef cn;
-                load_coef(M, row + kp, cn);
-                t4_kp = tau_shear(cn, pval<UPDATE>(r, p_old, 4 * P + row + kp, cgbeta), beta);
-                t3_kp = tau_shear(cn, pval<UPDATE>(r, p_old, 3 * P + row + kp, cgbeta), beta);
+                const size_t on = row + ((k + 1 == g.nz) ? 0 : k + 1);
+                tau_shear2(M, on, pval<UPDATE>(r, p_old, 4 * P + on, cgbeta), pval<UPDATE>(r, p_old, 3 * P + on, cgbeta), beta, t4_kp, t3_kp);
             }
             if (lane == 0 || k == 0) {
-                const int km = (k == 0) ? g.nz - 1 : k - 1;
-                IsoCoef cn;
-                load_coef(M, row + km, cn);
-                double a, b;
-                tau_diag(cn, pval<UPDATE>(r, p_old, row + km, cgbeta), pval<UPDATE>(r, p_old, P + row + km, cgbeta),
-                         pval<UPDATE>(r, p_old, 2 * P + row + km, cgbeta), beta, gamma, a, b, t2_km);
+                const size_t on = row + ((k == 0) ? g.nz - 1 : k - 1);
+                tau_diag(M, on, pval<UPDATE>(r, p_old, on, cgbeta), pval<UPDATE>(r, p_old, P + on, cgbeta),
+                         pval<UPDATE>(r, p_old, 2 * P + on, cgbeta), beta, gamma, dmy0, dmy1, t2_km);
             }
             // x and y neighbours: re-evaluate the needed stress components from r, p_old, phi (L1/L2 hits)
-            double t0_im, t1_jm, dmy0, dmy1;
+            double t0_im, t1_jm, t5_ip, t4_ip, t5_jp, t3_jp;
             {
-                IsoCoef cn;
-                load_coef(M, row_im + k, cn);
-                tau_diag(cn, pval<UPDATE>(r, p_old, row_im + k, cgbeta), pval<UPDATE>(r, p_old, P + row_im + k, cgbeta),
-                         pval<UPDATE>(r, p_old, 2 * P + row_im + k, cgbeta), beta, gamma, t0_im, dmy0, dmy1);
-                load_coef(M, row_jm + k, cn);
-                tau_diag(cn, pval<UPDATE>(r, p_old, row_jm + k, cgbeta), pval<UPDATE>(r, p_old, P + row_jm + k, cgbeta),
-                         pval<UPDATE>(r, p_old, 2 * P + row_jm + k, cgbeta), beta, gamma, dmy0, t1_jm, dmy1);
-            }
-            double t5_ip, t4_ip, t5_jp, t3_jp;
-            {
-                IsoCoef cn;
-                load_coef(M, row_ip + k, cn);
-                t5_ip = tau_shear(cn, pval<UPDATE>(r, p_old, 5 * P + row_ip + k, cgbeta), beta);
-                t4_ip = tau_shear(cn, pval<UPDATE>(r, p_old, 4 * P + row_ip + k, cgbeta), beta);
-                load_coef(M, row_jp + k, cn);
-                t5_jp = tau_shear(cn, pval<UPDATE>(r, p_old, 5 * P + row_jp + k, cgbeta), beta);
-                t3_jp = tau_shear(cn, pval<UPDATE>(r, p_old, 3 * P + row_jp + k, cgbeta), beta);
+                size_t on = row_im + k;
+                tau_diag(M, on, pval<UPDATE>(r, p_old, on, cgbeta), pval<UPDATE>(r, p_old, P + on, cgbeta),
+                         pval<UPDATE>(r, p_old, 2 * P + on, cgbeta), beta, gamma, t0_im, dmy0, dmy1);
+                on = row_jm + k;
+                tau_diag(M, on, pval<UPDATE>(r, p_old, on, cgbeta), pval<UPDATE>(r, p_old, P + on, cgbeta),
+                         pval<UPDATE>(r, p_old, 2 * P + on, cgbeta), beta, gamma, dmy0, t1_jm, dmy1);
+                on = row_ip + k;
+                tau_shear2(M, on, pval<UPDATE>(r, p_old, 5 * P + on, cgbeta), pval<UPDATE>(r, p_old, 4 * P + on, cgbeta), beta, t5_ip, t4_ip);
+                on = row_jp + k;
+                tau_shear2(M, on, pval<UPDATE>(r, p_old, 5 * P + on, cgbeta), pval<UPDATE>(r, p_old, 3 * P + on, cgbeta), beta, t5_jp, t3_jp);
             }
             // divOperatorStaggered fg:18863-18901
             const double f0 = (t0 - t0_im) * g.hx + (t5_jp - t5) * g.hy + (t4_kp - t4) * g.hz;
