@@ -20,7 +20,7 @@ $(OBJ)/%.cpp.o: $(SRC)/%.cpp $(wildcard $(SRC)/*.h) $(wildcard include/*.h)
 	$(NVCC) $(NVFLAGS) -x cu -c $< -o $@
 
 $(LIB): $(OBJS)
-	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart $(LDLIBS)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart -ldl $(LDLIBS)
 
 clean:
 	rm -rf build $(LIB)

@@ -1,15 +1,243 @@
-// Multi-GPU plumbing: x-slab partition, all-to-all transposes around the fused x pass, halo planes for the
-// staggered stencils and rank-ordered reductions.  One process per GPU; NCCL over NVLink.
+// Multi-GPU plumbing: one process per GPU, x-slab partition, NCCL over NVLink 5 / NVSwitch.
+//
+// The reference has no distributed code at all; this is the new exchange step of the path:
+//   * 3-D FFT of a slab-partitioned buffer: z and y passes are local; the y pass writes its output straight into the
+//     all-to-all staging layout S[c][q][il][jl][k] (PencilMap), one grouped ncclSend/ncclRecv per (component, peer)
+//     moves it to the y-slab layout R[c][ii][jl][k] on which the fused x pass (forward x, Green operator, inverse x)
+//     runs in place; the way back is symmetric and the inverse y pass reads the staging layout directly.  No separate
+//     pack / unpack sweeps touch HBM.
+//   * staggered stencils: one x plane of the needed components from each slab neighbour (periodic).
+//   * reductions: per-rank partial results are all-gathered and summed in rank order (deterministic).
+// NCCL is resolved at run time (dlopen "libnccl.so.2": torch's bundled copy if the host process already loaded it, the
+// system one otherwise), so libfgb200 has no link-time dependency on it.
 #include "fgb_internal.h"
+#include <dlfcn.h>
+#include <nccl.h>
 
-int fgb_comm_free(fgb_ctx* ctx) { (void)ctx; return FGB_OK; }
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
 
-int fgb_comm_fft_x(fgb_ctx* ctx, double*, int, const FftLayout&, const GreenArgs*) {
-    return fgb_fail(ctx, FGB_EUNSUPPORTED, "slab-partitioned x pass not built yet");
+static int load_nccl(fgb_ctx* ctx) {
+    if (g_nccl.lib) return FGB_OK;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* lib = nullptr;
+    for (const char* n : names) {
+        lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (lib) break;
+    }
+    if (!lib) return fgb_fail(ctx, FGB_ECOMM, "cannot load libnccl.so.2: %s", dlerror());
+#define SYM(field, name)                                                                     \
+    g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(lib, name));               \
+    if (!g_nccl.field) return fgb_fail(ctx, FGB_ECOMM, "libnccl lacks %s", name);
+    SYM(GetUniqueId, "ncclGetUniqueId")
+    SYM(CommInitRank, "ncclCommInitRank")
+    SYM(CommDestroy, "ncclCommDestroy")
+    SYM(Send, "ncclSend")
+    SYM(Recv, "ncclRecv")
+    SYM(GroupStart, "ncclGroupStart")
+    SYM(GroupEnd, "ncclGroupEnd")
+    SYM(AllGather, "ncclAllGather")
+    SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    g_nccl.lib = lib;
+    return FGB_OK;
 }
-int fgb_comm_halo_tau(fgb_ctx* ctx, const double*) { return fgb_fail(ctx, FGB_EUNSUPPORTED, "halo exchange not built yet"); }
-int fgb_comm_halo_u(fgb_ctx* ctx) { return fgb_fail(ctx, FGB_EUNSUPPORTED, "halo exchange not built yet"); }
-int fgb_allreduce_host(fgb_ctx* ctx, double*, int, int) { return fgb_fail(ctx, FGB_EUNSUPPORTED, "multi-rank reductions not built yet"); }
 
-extern "C" int fgb_comm_unique_id(void*) { return FGB_EUNSUPPORTED; }
-extern "C" int fgb_comm_init(fgb_ctx* ctx, const void*) { return fgb_fail(ctx, FGB_EUNSUPPORTED, "multi-GPU communicator not built yet"); }
+#define FGB_NCCL(ctx, call)                                                                       \
+    do {                                                                                          \
+        ncclResult_t r__ = (call);                                                                \
+        if (r__ != ncclSuccess)                                                                   \
+            return fgb_fail(ctx, FGB_ECOMM, "%s failed: %s", #call, g_nccl.GetErrorString(r__));  \
+    } while (0)
+
+extern "C" int fgb_comm_unique_id(void* id128) {
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
+    int rc = load_nccl(nullptr);
+    if (rc) return rc;
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) return fgb_fail(nullptr, FGB_ECOMM, "ncclGetUniqueId failed");
+    memcpy(id128, &id, 128);
+    return FGB_OK;
+}
+
+extern "C" int fgb_comm_init(fgb_ctx* ctx, const void* id128) {
+    if (!ctx) return FGB_EINVAL;
+    cudaSetDevice(ctx->device);
+    if (ctx->nranks == 1) return FGB_OK;
+    int rc = load_nccl(ctx);
+    if (rc) return rc;
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    ncclComm_t comm;
+    FGB_NCCL(ctx, g_nccl.CommInitRank(&comm, ctx->nranks, id, ctx->rank));
+    ctx->nccl_comm = comm;
+    const GridDev& g = ctx->g;
+    // halo slots: a full x plane of one component in either layout
+    size_t a = (size_t)g.ny * g.nzp, b = (size_t)g.ny * 2 * g.unzcs;
+    ctx->halo_slot = a > b ? a : b;
+    FGB_CUDA(ctx, cudaMalloc(&ctx->halo, sizeof(double) * 6 * ctx->halo_slot));
+    FGB_CUDA(ctx, cudaMalloc(&ctx->d_gather, sizeof(double) * 64 * ctx->nranks));
+    return FGB_OK;
+}
+
+int fgb_comm_free(fgb_ctx* ctx) {
+    if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)ctx->nccl_comm);
+    ctx->nccl_comm = nullptr;
+    if (ctx->sbuf) cudaFree(ctx->sbuf);
+    if (ctx->xbuf) cudaFree(ctx->xbuf);
+    if (ctx->halo) cudaFree(ctx->halo);
+    if (ctx->d_gather) cudaFree(ctx->d_gather);
+    ctx->sbuf = ctx->xbuf = ctx->halo = ctx->d_gather = nullptr;
+    return FGB_OK;
+}
+
+static int need_comm(fgb_ctx* ctx) {
+    if (!ctx->nccl_comm) return fgb_fail(ctx, FGB_ECOMM, "context has %d ranks but fgb_comm_init was not called", ctx->nranks);
+    return FGB_OK;
+}
+
+static int ensure_xbuf(fgb_ctx* ctx, int ncomp, int nzcs) {
+    if (ctx->xbuf && ctx->xbuf_comps >= ncomp && ctx->xbuf_nzcs >= nzcs) return FGB_OK;
+    if (ctx->sbuf) cudaFree(ctx->sbuf);
+    if (ctx->xbuf) cudaFree(ctx->xbuf);
+    ctx->sbuf = ctx->xbuf = nullptr;
+    const GridDev& g = ctx->g;
+    const size_t bytes = sizeof(double) * 2 * (size_t)ncomp * g.lnx * g.ny * nzcs;
+    cudaError_t e = cudaMalloc(&ctx->sbuf, bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->xbuf, bytes);
+    if (e != cudaSuccess) return fgb_fail(ctx, FGB_ENOMEM, "cannot allocate the transpose buffers (%zu bytes each): %s", bytes, cudaGetErrorString(e));
+    ctx->xbuf_comps = ncomp;
+    ctx->xbuf_nzcs = nzcs;
+    return FGB_OK;
+}
+
+// all-to-all of `ncomp` components: chunk (c, q) of `chunk` complex numbers at src + (c*P + q)*chunk goes to rank q and lands
+// at dst + (c*P + me)*chunk there
+static int alltoall(fgb_ctx* ctx, const double* src, double* dst, int ncomp, size_t chunk_complex) {
+    ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+    const int P = ctx->nranks, me = ctx->rank;
+    const size_t cnt = 2 * chunk_complex;          // doubles
+    FGB_NCCL(ctx, g_nccl.GroupStart());
+    for (int c = 0; c < ncomp; c++) {
+        for (int dq = 1; dq < P; dq++) {
+            const int to = (me + dq) % P, from = (me - dq + P) % P;
+            FGB_NCCL(ctx, g_nccl.Send(src + ((size_t)c * P + to) * cnt, cnt, ncclDouble, to, comm, ctx->stream));
+            FGB_NCCL(ctx, g_nccl.Recv(dst + ((size_t)c * P + from) * cnt, cnt, ncclDouble, from, comm, ctx->stream));
+        }
+    }
+    FGB_NCCL(ctx, g_nccl.GroupEnd());
+    for (int c = 0; c < ncomp; c++)
+        FGB_CUDA(ctx, cudaMemcpyAsync(dst + ((size_t)c * P + me) * cnt, src + ((size_t)c * P + me) * cnt, sizeof(double) * cnt,
+                                      cudaMemcpyDeviceToDevice, ctx->stream));
+    return FGB_OK;
+}
+
+// forward y -> transpose -> fused x pass -> transpose -> inverse y; `base` holds the z-transformed slab (rows of lay.nzcs complex)
+int fgb_comm_fft_x(fgb_ctx* ctx, double* base, int ncomp, const FftLayout& lay, const GreenArgs* ga) {
+    int rc = need_comm(ctx);
+    if (rc) return rc;
+    const GridDev& g = ctx->g;
+    const int P = ctx->nranks, lny = g.ny / P, nzcs = lay.nzcs;
+    if ((rc = ensure_xbuf(ctx, ncomp, nzcs))) return rc;
+    const size_t chunk = (size_t)g.lnx * lny * nzcs;                 // complex numbers per (component, peer)
+    const PencilMap nat = {nzcs, g.ny, 0, (long)g.ny * nzcs, (long)g.lnx * g.ny * nzcs};
+    const PencilMap stg = {nzcs, lny, (long)chunk, (long)lny * nzcs, (long)P * (long)chunk};
+    {
+        ProfScope ps(ctx, "fft_y_fwd");
+        if ((rc = fgb_fft_strided(ctx, 1, base, ctx->sbuf, nat, stg, g.nzc, g.lnx, ncomp, -1))) return rc;
+    }
+    {
+        ProfScope ps(ctx, "alltoall_fwd");
+        if ((rc = alltoall(ctx, ctx->sbuf, ctx->xbuf, ncomp, chunk))) return rc;
+    }
+    // y-slab layout R[c][ii][jl][k]: x pencils have stride lny*nzcs, the outer index is jl, jj = rank*lny + jl
+    if ((rc = fgb_fft_x_green_layout(ctx, ctx->xbuf, ga, (long)lny * nzcs, g.nzc, lny, nzcs, (long)g.nx * lny * nzcs, ctx->rank * lny))) return rc;
+    {
+        ProfScope ps(ctx, "alltoall_bwd");
+        if ((rc = alltoall(ctx, ctx->xbuf, ctx->sbuf, ncomp, chunk))) return rc;
+    }
+    {
+        ProfScope ps(ctx, "fft_y_bwd");
+        if ((rc = fgb_fft_strided(ctx, 1, ctx->sbuf, base, stg, nat, g.nzc, g.lnx, ncomp, +1))) return rc;
+    }
+    return FGB_OK;
+}
+
+// neighbour planes: lo slot s <- plane lnx-1 of lo_src[s] on the left rank, hi slot s <- plane 0 of hi_src[s] on the right rank
+static int halo_exchange(fgb_ctx* ctx, const double* const* lo_src, int nlo, const double* const* hi_src, int nhi, size_t plane_elems,
+                         size_t comp_stride_unused) {
+    (void)comp_stride_unused;
+    int rc = need_comm(ctx);
+    if (rc) return rc;
+    ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+    const int P = ctx->nranks, me = ctx->rank;
+    const int left = (me - 1 + P) % P, right = (me + 1) % P;
+    const GridDev& g = ctx->g;
+    double* lo = ctx->halo;
+    double* hi = ctx->halo + 3 * ctx->halo_slot;
+    ProfScope ps(ctx, "halo_exchange");
+    FGB_NCCL(ctx, g_nccl.GroupStart());
+    // my first planes go to the left rank (its hi halo); my last planes go to the right rank (its lo halo)
+    for (int s = 0; s < nhi; s++) FGB_NCCL(ctx, g_nccl.Send(hi_src[s], plane_elems, ncclDouble, left, comm, ctx->stream));
+    for (int s = 0; s < nlo; s++)
+        FGB_NCCL(ctx, g_nccl.Send(lo_src[s] + (size_t)(g.lnx - 1) * plane_elems, plane_elems, ncclDouble, right, comm, ctx->stream));
+    for (int s = 0; s < nhi; s++) FGB_NCCL(ctx, g_nccl.Recv(hi + s * ctx->halo_slot, plane_elems, ncclDouble, right, comm, ctx->stream));
+    for (int s = 0; s < nlo; s++) FGB_NCCL(ctx, g_nccl.Recv(lo + s * ctx->halo_slot, plane_elems, ncclDouble, left, comm, ctx->stream));
+    FGB_NCCL(ctx, g_nccl.GroupEnd());
+    return FGB_OK;
+}
+
+// k_div needs tau_0 at i-1 and the two shear components at i+1 (fg:18868-18901, hyper fg:19026-19064)
+int fgb_comm_halo_tau(fgb_ctx* ctx, const double* tau) {
+    const GridDev& g = ctx->g;
+    const size_t pe = (size_t)g.ny * g.nzp;
+    const double* lo[1] = {tau};
+    if (ctx->dim == 3) return halo_exchange(ctx, lo, 1, nullptr, 0, pe, 0);
+    const int c1x = (ctx->dim == 6) ? 5 : 8, c2x = (ctx->dim == 6) ? 4 : 7;
+    const double* hi[2] = {tau + (size_t)c1x * g.plane, tau + (size_t)c2x * g.plane};
+    return halo_exchange(ctx, lo, 1, hi, 2, pe, 0);
+}
+
+// k_eps needs u_0 at i+1 and u_0..2 at i-1 (fg:18632-18654)
+int fgb_comm_halo_u(fgb_ctx* ctx) {
+    const GridDev& g = ctx->g;
+    const size_t pe = (size_t)g.ny * 2 * g.unzcs;
+    const double* u = ctx->ubuf;
+    const double* hi[1] = {u};
+    if (ctx->dim == 3) return halo_exchange(ctx, nullptr, 0, hi, 1, pe, 0);
+    const double* lo[3] = {u, u + g.uplane, u + 2 * g.uplane};
+    return halo_exchange(ctx, lo, 3, hi, 1, pe, 0);
+}
+
+// combine per-rank partial results in rank order (op 0 sum, 1 min, 2 max); vals holds this rank's values on entry
+int fgb_allreduce_host(fgb_ctx* ctx, double* vals, int n, int op) {
+    int rc = need_comm(ctx);
+    if (rc) return rc;
+    if (n > 64) return fgb_fail(ctx, FGB_EINVAL, "too many reduction values");
+    ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+    // d_result still holds this rank's n values (fgb_reduce_finish wrote them); gather all ranks' vectors
+    FGB_NCCL(ctx, g_nccl.AllGather(ctx->d_result, ctx->d_gather, (size_t)n, ncclDouble, comm, ctx->stream));
+    std::vector<double> all((size_t)n * ctx->nranks);
+    FGB_CUDA(ctx, cudaMemcpyAsync(all.data(), ctx->d_gather, sizeof(double) * all.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    FGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < n; i++) {
+        double acc = all[i];
+        for (int r = 1; r < ctx->nranks; r++) {
+            const double x = all[(size_t)r * n + i];
+            acc = (op == 0) ? acc + x : (op == 1 ? (x < acc ? x : acc) : (x > acc ? x : acc));
+        }
+        vals[i] = acc;
+    }
+    return FGB_OK;
+}

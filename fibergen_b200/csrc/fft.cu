@@ -111,10 +111,12 @@ __global__ void __launch_bounds__(FFTZ_THREADS) k_fftz_p2(double* __restrict__ b
     }
 }
 
-// strided pass (y; x without Green): tile of T lanes, thread (t, s); exchange buffer X[(k1*R2+n2)*T + t]
+// strided pass (y; x without Green): tile of T lanes, thread (t, s); exchange buffer X[(k1*R2+n2)*T + t].
+// Source and destination may differ and are addressed through PencilMaps, so the y pass of a slab-partitioned run
+// writes straight into (reads straight from) the all-to-all staging layout.
 template <int N, int R1, int R2, int DIR, int T>
-__global__ void __launch_bounds__(Max<R1, R2>::v* T) k_ffts_p2(double2* __restrict__ base, const double2* __restrict__ tw, long estride,
-                                                               int ninner, long ostride, long cstride) {
+__global__ void __launch_bounds__(Max<R1, R2>::v* T) k_ffts_p2(const double2* __restrict__ src, double2* __restrict__ dst,
+                                                               const double2* __restrict__ tw, PencilMap mi, PencilMap mo, int ninner) {
     constexpr int TPP = Max<R1, R2>::v;
     __shared__ double2 tw_s[N];
     __shared__ double2 X[N * T];
@@ -123,11 +125,12 @@ __global__ void __launch_bounds__(Max<R1, R2>::v* T) k_ffts_p2(double2* __restri
     const int t = tid % T, s = tid / T;
     const int inner = blockIdx.x * T + t;
     const bool valid = inner < ninner;
-    double2* g = base + (long)blockIdx.z * cstride + (long)blockIdx.y * ostride + inner;
+    const double2* gi = src + (long)blockIdx.z * mi.cstride + (long)blockIdx.y * mi.ostride + inner;
+    double2* go = dst + (long)blockIdx.z * mo.cstride + (long)blockIdx.y * mo.ostride + inner;
     double2 v[R1];
     if (s < R2) {
 #pragma unroll
-        for (int n1 = 0; n1 < R1; n1++) v[n1] = valid ? g[(long)(R2 * n1 + s) * estride] : make_double2(0, 0);
+        for (int n1 = 0; n1 < R1; n1++) v[n1] = valid ? gi[mi.at(R2 * n1 + s)] : make_double2(0, 0);
     }
     __syncthreads();
     if (s < R2) {
@@ -143,7 +146,7 @@ __global__ void __launch_bounds__(Max<R1, R2>::v* T) k_ffts_p2(double2* __restri
         p2::RegFFT<R2, DIR>::run(w);
         if (valid) {
 #pragma unroll
-            for (int k2 = 0; k2 < R2; k2++) g[(long)(s + R1 * k2) * estride] = w[k2];
+            for (int k2 = 0; k2 < R2; k2++) go[mo.at(s + R1 * k2)] = w[k2];
         }
     }
 }
@@ -402,26 +405,29 @@ int fgb_fft_z_backward(fgb_ctx* ctx, double* base, int ncomp, const FftLayout& l
 
 // ---- strided (y, plain x) -----------------------------------------------------------------------------
 template <int N, int R1, int R2, int T>
-static void launch_s_p2(fgb_ctx* ctx, double2* base, const double2* tw, long estride, int ninner, int nouter, long ostride, int ncomp,
-                        long cstride, int dir) {
+static void launch_s_p2(fgb_ctx* ctx, const double2* src, double2* dst, const double2* tw, const PencilMap& mi, const PencilMap& mo,
+                        int ninner, int nouter, int ncomp, int dir) {
     dim3 grid((ninner + T - 1) / T, nouter, ncomp);
     constexpr int NT = Max<R1, R2>::v * T;
-    if (dir < 0) k_ffts_p2<N, R1, R2, -1, T><<<grid, NT, 0, ctx->stream>>>(base, tw, estride, ninner, ostride, cstride);
-    else k_ffts_p2<N, R1, R2, +1, T><<<grid, NT, 0, ctx->stream>>>(base, tw, estride, ninner, ostride, cstride);
+    if (dir < 0) k_ffts_p2<N, R1, R2, -1, T><<<grid, NT, 0, ctx->stream>>>(src, dst, tw, mi, mo, ninner);
+    else k_ffts_p2<N, R1, R2, +1, T><<<grid, NT, 0, ctx->stream>>>(src, dst, tw, mi, mo, ninner);
 }
 
-static int fft_strided(fgb_ctx* ctx, int axis, double2* base, long estride, int ninner, int nouter, long ostride, int ncomp, long cstride,
-                       int dir) {
+int fgb_fft_strided(fgb_ctx* ctx, int axis, const double* src_, double* dst_, const PencilMap& mi, const PencilMap& mo, int ninner,
+                    int nouter, int ncomp, int dir) {
     const int n = ctx->plan[axis].n;
-    if (n == 1 || ninner == 0 || nouter == 0) return FGB_OK;
+    const double2* src = (const double2*)src_;
+    double2* dst = (double2*)dst_;
+    if (ninner == 0 || nouter == 0) return FGB_OK;
+    if (n == 1 && src == dst) return FGB_OK;
     const double2* tw = ctx->plan[axis].tw;
     if (is_fast_pow2(n)) {
         switch (n) {
-            case 64: launch_s_p2<64, 8, 8, 8>(ctx, base, tw, estride, ninner, nouter, ostride, ncomp, cstride, dir); break;
-            case 128: launch_s_p2<128, 16, 8, 8>(ctx, base, tw, estride, ninner, nouter, ostride, ncomp, cstride, dir); break;
-            case 256: launch_s_p2<256, 16, 16, 8>(ctx, base, tw, estride, ninner, nouter, ostride, ncomp, cstride, dir); break;
-            case 512: launch_s_p2<512, 32, 16, 4>(ctx, base, tw, estride, ninner, nouter, ostride, ncomp, cstride, dir); break;
-            case 1024: launch_s_p2<1024, 32, 32, 2>(ctx, base, tw, estride, ninner, nouter, ostride, ncomp, cstride, dir); break;
+            case 64: launch_s_p2<64, 8, 8, 8>(ctx, src, dst, tw, mi, mo, ninner, nouter, ncomp, dir); break;
+            case 128: launch_s_p2<128, 16, 8, 8>(ctx, src, dst, tw, mi, mo, ninner, nouter, ncomp, dir); break;
+            case 256: launch_s_p2<256, 16, 16, 8>(ctx, src, dst, tw, mi, mo, ninner, nouter, ncomp, dir); break;
+            case 512: launch_s_p2<512, 32, 16, 4>(ctx, src, dst, tw, mi, mo, ninner, nouter, ncomp, dir); break;
+            case 1024: launch_s_p2<1024, 32, 32, 2>(ctx, src, dst, tw, mi, mo, ninner, nouter, ncomp, dir); break;
         }
         FGB_CHECK_LAUNCH(ctx, "k_ffts_p2");
         return FGB_OK;
@@ -432,10 +438,10 @@ static int fft_strided(fgb_ctx* ctx, int axis, double2* base, long estride, int 
     dim3 grid((ninner + T - 1) / T, nouter, ncomp);
     if (dir < 0) {
         FGB_CUDA(ctx, set_smem(k_fft_strided<-1>, smem));
-        k_fft_strided<-1><<<grid, 256, smem, ctx->stream>>>(base, ctx->plan[axis], estride, ninner, ostride, cstride, T);
+        k_fft_strided<-1><<<grid, 256, smem, ctx->stream>>>(src, dst, ctx->plan[axis], mi, mo, ninner, T);
     } else {
         FGB_CUDA(ctx, set_smem(k_fft_strided<1>, smem));
-        k_fft_strided<1><<<grid, 256, smem, ctx->stream>>>(base, ctx->plan[axis], estride, ninner, ostride, cstride, T);
+        k_fft_strided<1><<<grid, 256, smem, ctx->stream>>>(src, dst, ctx->plan[axis], mi, mo, ninner, T);
     }
     FGB_CHECK_LAUNCH(ctx, "k_fft_strided");
     return FGB_OK;
@@ -444,7 +450,8 @@ static int fft_strided(fgb_ctx* ctx, int axis, double2* base, long estride, int 
 int fgb_fft_y(fgb_ctx* ctx, double* base, int ncomp, const FftLayout& lay, int dir) {
     const GridDev& g = ctx->g;
     ProfScope ps(ctx, dir < 0 ? "fft_y_fwd" : "fft_y_bwd");
-    return fft_strided(ctx, 1, (double2*)base, lay.nzcs, g.nzc, g.lnx, (long)g.ny * lay.nzcs, ncomp, (long)g.lnx * g.ny * lay.nzcs, dir);
+    const PencilMap m = {lay.nzcs, g.ny, 0, (long)g.ny * lay.nzcs, (long)g.lnx * g.ny * lay.nzcs};
+    return fgb_fft_strided(ctx, 1, base, base, m, m, g.nzc, g.lnx, ncomp, dir);
 }
 
 // ---- x with Green operator ---------------------------------------------------------------------------------
@@ -523,7 +530,8 @@ int fgb_fft_x(fgb_ctx* ctx, double* base, int ncomp, const FftLayout& lay, int d
     const long cstride = (long)g.lnx * g.ny * lay.nzcs;
     if (!ga || ga->kind == 0) {
         ProfScope ps(ctx, dir < 0 ? "fft_x_fwd" : "fft_x_bwd");
-        return fft_strided(ctx, 0, (double2*)base, estride, g.nzc, g.ny, lay.nzcs, ncomp, cstride, dir);
+        const PencilMap m = {estride, g.nx, 0, (long)lay.nzcs, cstride};
+        return fgb_fft_strided(ctx, 0, base, base, m, m, g.nzc, g.ny, ncomp, dir);
     }
     return fgb_fft_x_green_layout(ctx, base, ga, estride, g.nzc, g.ny, lay.nzcs, cstride, 0);
 }

@@ -176,25 +176,26 @@ __global__ void __launch_bounds__(256) k_fft_z(double* __restrict__ base, long r
 // strided pass (y, and x without Green operator): one component per CTA
 // ------------------------------------------------------------------------------------------------
 template <int DIR>
-__global__ void __launch_bounds__(256) k_fft_strided(double2* __restrict__ base, FftPlanDev P, long estride, int ninner,
-                                                     long ostride, long cstride, int T) {
+__global__ void __launch_bounds__(256) k_fft_strided(const double2* __restrict__ src, double2* __restrict__ dst, FftPlanDev P,
+                                                     PencilMap mi, PencilMap mo, int ninner, int T) {
     extern __shared__ double2 smem[];
     const int n = P.n;
     double2* a = smem;
     double2* b = smem + (size_t)n * T;
     const int tid = threadIdx.x, nth = blockDim.x;
     const int inner0 = blockIdx.x * T;
-    double2* g = base + (long)blockIdx.z * cstride + (long)blockIdx.y * ostride + inner0;
+    const double2* gi = src + (long)blockIdx.z * mi.cstride + (long)blockIdx.y * mi.ostride + inner0;
+    double2* go = dst + (long)blockIdx.z * mo.cstride + (long)blockIdx.y * mo.ostride + inner0;
     const int tmax = min(T, ninner - inner0);
     for (int idx = tid; idx < n * T; idx += nth) {
         const int e = idx / T, t = idx % T;
-        a[idx] = (t < tmax) ? g[(long)e * estride + t] : make_double2(0, 0);
+        a[idx] = (t < tmax) ? gi[mi.at(e) + t] : make_double2(0, 0);
     }
     __syncthreads();
     double2* res = fft_tile<DIR>(a, b, P, T, T);
     for (int idx = tid; idx < n * T; idx += nth) {
         const int e = idx / T, t = idx % T;
-        if (t < tmax) g[(long)e * estride + t] = res[idx];
+        if (t < tmax) go[mo.at(e) + t] = res[idx];
     }
 }
 

@@ -94,8 +94,14 @@ struct fgb_ctx {
 
     // multi-GPU
     void* nccl_comm;            // ncclComm_t
-    double* xbuf;               // transposed complex buffer (y-slab layout)
-    double* halo;               // halo planes
+    void* nccl_lib;             // dlopen handle of libnccl.so.2
+    double* sbuf;               // all-to-all staging, [c][q][il][jl][k] complex (same size as the transformed buffer)
+    double* xbuf;               // y-slab layout [c][ii][jl][k] complex: the fused x pass runs in place on it
+    int xbuf_comps;             // components sbuf/xbuf are sized for
+    int xbuf_nzcs;
+    double* halo;               // [3 lo slots][3 hi slots] of halo_slot doubles (neighbour x planes for the stencils)
+    size_t halo_slot;
+    double* d_gather;           // rank-ordered reduction staging
 
     // mixed boundary conditions (fgb_set_bc): row-major dim x dim matrices MQ and M:(QC0)
     bool bc_active;
@@ -142,10 +148,27 @@ void fgb_fft_free(fgb_ctx* ctx);
 struct FftLayout {
     int nzcs;
 };
+// where element e of a strided pencil lives: segments of `seglen` elements `segstride` apart, `estride` inside a segment.
+// seglen == n is the plain strided layout; seglen = ny/nranks addresses the all-to-all send/receive staging layout.
+struct PencilMap {
+    long estride;
+    int seglen;
+    long segstride;
+    long ostride;      // per blockIdx.y
+    long cstride;      // per component
+#ifdef __CUDACC__
+    __host__ __device__ __forceinline__ long at(int e) const {
+        const int q = e / seglen;
+        return (long)q * segstride + (long)(e - q * seglen) * estride;
+    }
+#endif
+};
 // in-place r2c/c2r along z of `ncomp` components starting at base
 int fgb_fft_z_forward(fgb_ctx* ctx, double* base, int ncomp, const FftLayout& lay);
 int fgb_fft_z_backward(fgb_ctx* ctx, double* base, int ncomp, const FftLayout& lay);
 int fgb_fft_y(fgb_ctx* ctx, double* base, int ncomp, const FftLayout& lay, int dir);
+int fgb_fft_strided(fgb_ctx* ctx, int axis, const double* src, double* dst, const PencilMap& mi, const PencilMap& mo, int ninner,
+                    int nouter, int ncomp, int dir);
 // x pass; green_kind: 0 none (plain forward or backward per dir), otherwise fused fwd-x, Green, inv-x
 struct GreenArgs {
     int kind;             // 0 none, 1 staggered elasticity/hyper (general), 2 staggered heat, 3 colloc elasticity, 4 colloc heat, 5 colloc hyper

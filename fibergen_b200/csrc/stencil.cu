@@ -25,16 +25,15 @@ __device__ __forceinline__ double at_x(const double* p, const GridDev& g, int i,
         if (ii >= g.lnx) ii -= g.lnx;
         return p[((size_t)ii * g.ny + j) * rs + k];
     }
-    if (ii < 0) return halo_lo[(size_t)j * g.nzp + k];
-    if (ii >= g.lnx) return halo_hi[(size_t)j * g.nzp + k];
+    if (ii < 0) return halo_lo[(size_t)j * rs + k];
+    if (ii >= g.lnx) return halo_hi[(size_t)j * rs + k];
     return p[((size_t)ii * g.ny + j) * rs + k];
 }
 
 template <int D>
 __global__ void __launch_bounds__(256) k_div(const double* __restrict__ tau, double* __restrict__ u, GridDev g,
-                                             const double* __restrict__ halo_lo, const double* __restrict__ halo_hi) {
+                                             const double* __restrict__ halo_lo, const double* __restrict__ halo_hi, size_t hp) {
     const unsigned nvox = (unsigned)g.lnx * (unsigned)g.ny * (unsigned)g.nz;
-    const size_t hp = (size_t)g.ny * g.nzp;   // halo plane size
     for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += gridDim.x * blockDim.x) {
         const unsigned row_ = v / (unsigned)g.nz;
         const int k = (int)(v - row_ * (unsigned)g.nz);
@@ -77,9 +76,8 @@ struct Const9 {
 
 template <int D>
 __global__ void __launch_bounds__(256) k_eps(const double* __restrict__ u, double* __restrict__ eta, GridDev g, Const9 E,
-                                             const double* __restrict__ halo_lo, const double* __restrict__ halo_hi) {
+                                             const double* __restrict__ halo_lo, const double* __restrict__ halo_hi, size_t hp) {
     const unsigned nvox = (unsigned)g.lnx * (unsigned)g.ny * (unsigned)g.nz;
-    const size_t hp = (size_t)g.ny * g.nzp;
     for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += gridDim.x * blockDim.x) {
         const unsigned row_ = v / (unsigned)g.nz;
         const int k = (int)(v - row_ * (unsigned)g.nz);
@@ -136,12 +134,11 @@ static unsigned grid_for(const fgb_ctx* ctx, size_t n, int block) {
     return (unsigned)b;
 }
 
-// halo layout is owned by comm.cu: ctx->halo = [lo planes (3)] [hi planes (3)]
+// halo layout is owned by comm.cu: ctx->halo = [3 lo slots][3 hi slots], each slot ctx->halo_slot doubles
 static void halo_ptrs(fgb_ctx* ctx, const double** lo, const double** hi) {
     if (ctx->nranks > 1 && ctx->halo) {
-        const size_t hp = (size_t)ctx->g.ny * ctx->g.nzp;
         *lo = ctx->halo;
-        *hi = ctx->halo + 3 * hp;
+        *hi = ctx->halo + 3 * ctx->halo_slot;
     } else {
         *lo = nullptr;
         *hi = nullptr;
@@ -155,9 +152,9 @@ int fgb_k_div(fgb_ctx* ctx, const double* tau, double* u) {
     halo_ptrs(ctx, &lo, &hi);
     ProfScope ps(ctx, "div_staggered");
     const unsigned grid = grid_for(ctx, nvox, 256);
-    if (ctx->dim == 3) k_div<3><<<grid, 256, 0, ctx->stream>>>(tau, u, g, lo, hi);
-    else if (ctx->dim == 6) k_div<6><<<grid, 256, 0, ctx->stream>>>(tau, u, g, lo, hi);
-    else k_div<9><<<grid, 256, 0, ctx->stream>>>(tau, u, g, lo, hi);
+    if (ctx->dim == 3) k_div<3><<<grid, 256, 0, ctx->stream>>>(tau, u, g, lo, hi, ctx->halo_slot);
+    else if (ctx->dim == 6) k_div<6><<<grid, 256, 0, ctx->stream>>>(tau, u, g, lo, hi, ctx->halo_slot);
+    else k_div<9><<<grid, 256, 0, ctx->stream>>>(tau, u, g, lo, hi, ctx->halo_slot);
     FGB_CHECK_LAUNCH(ctx, "k_div");
     return FGB_OK;
 }
@@ -171,9 +168,9 @@ int fgb_k_eps(fgb_ctx* ctx, const double* u, double* eta, const double* Econst) 
     halo_ptrs(ctx, &lo, &hi);
     ProfScope ps(ctx, "eps_staggered");
     const unsigned grid = grid_for(ctx, nvox, 256);
-    if (ctx->dim == 3) k_eps<3><<<grid, 256, 0, ctx->stream>>>(u, eta, g, E, lo, hi);
-    else if (ctx->dim == 6) k_eps<6><<<grid, 256, 0, ctx->stream>>>(u, eta, g, E, lo, hi);
-    else k_eps<9><<<grid, 256, 0, ctx->stream>>>(u, eta, g, E, lo, hi);
+    if (ctx->dim == 3) k_eps<3><<<grid, 256, 0, ctx->stream>>>(u, eta, g, E, lo, hi, ctx->halo_slot);
+    else if (ctx->dim == 6) k_eps<6><<<grid, 256, 0, ctx->stream>>>(u, eta, g, E, lo, hi, ctx->halo_slot);
+    else k_eps<9><<<grid, 256, 0, ctx->stream>>>(u, eta, g, E, lo, hi, ctx->halo_slot);
     FGB_CHECK_LAUNCH(ctx, "k_eps");
     return FGB_OK;
 }
