@@ -477,11 +477,14 @@ static int g0_staggered(fgb_ctx* c, double mu0, double lambda0, double alpha) {
     int rc;
     const FftLayout lay = {c->g.unzcs};
     if ((rc = fgb_fft_z_forward(c, c->ubuf, c->udim, lay))) return rc;
-    if ((rc = fgb_fft_y(c, c->ubuf, c->udim, lay, -1))) return rc;
-    if (c->nranks > 1) rc = fgb_comm_fft_x(c, c->ubuf, c->udim, lay, &ga);
-    else rc = fgb_fft_x(c, c->ubuf, c->udim, lay, 0, &ga);
-    if (rc) return rc;
-    if ((rc = fgb_fft_y(c, c->ubuf, c->udim, lay, +1))) return rc;
+    if (c->nranks > 1) {
+        // slab partition: the y passes are part of the transposed x pass (they read/write the all-to-all staging layout)
+        if ((rc = fgb_comm_fft_x(c, c->ubuf, c->udim, lay, &ga))) return rc;
+    } else {
+        if ((rc = fgb_fft_y(c, c->ubuf, c->udim, lay, -1))) return rc;
+        if ((rc = fgb_fft_x(c, c->ubuf, c->udim, lay, 0, &ga))) return rc;
+        if ((rc = fgb_fft_y(c, c->ubuf, c->udim, lay, +1))) return rc;
+    }
     return fgb_fft_z_backward(c, c->ubuf, c->udim, lay);
 }
 
@@ -503,11 +506,13 @@ static int gamma_impl(fgb_ctx* c, double* field, const double* E, double mu0, do
     for (int i = 0; i < c->dim; i++) ga.dc[i] = Ec[i];
     const FftLayout lay = {c->g.nzc};
     if ((rc = fgb_fft_z_forward(c, field, c->dim, lay))) return rc;
-    if ((rc = fgb_fft_y(c, field, c->dim, lay, -1))) return rc;
-    if (c->nranks > 1) rc = fgb_comm_fft_x(c, field, c->dim, lay, &ga);
-    else rc = fgb_fft_x(c, field, c->dim, lay, 0, &ga);
-    if (rc) return rc;
-    if ((rc = fgb_fft_y(c, field, c->dim, lay, +1))) return rc;
+    if (c->nranks > 1) {
+        if ((rc = fgb_comm_fft_x(c, field, c->dim, lay, &ga))) return rc;
+    } else {
+        if ((rc = fgb_fft_y(c, field, c->dim, lay, -1))) return rc;
+        if ((rc = fgb_fft_x(c, field, c->dim, lay, 0, &ga))) return rc;
+        if ((rc = fgb_fft_y(c, field, c->dim, lay, +1))) return rc;
+    }
     return fgb_fft_z_backward(c, field, c->dim, lay);
 }
 
