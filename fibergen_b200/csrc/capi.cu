@@ -133,7 +133,7 @@ extern "C" int fgb_create(fgb_ctx** out, int nx, int ny, int nz, double Lx, doub
     for (int a = 0; a < 3; a++) { c->tw_dev[a] = nullptr; c->kpm_dev[a] = nullptr; c->kp_dev[a] = nullptr; c->xi_dev[a] = nullptr; }
     c->d_partials = nullptr; c->d_result = nullptr; c->h_result = nullptr; c->d_scalars = nullptr; c->d_flag = nullptr; c->h_flag = nullptr;
     c->nccl_comm = nullptr; c->nccl_lib = nullptr; c->sbuf = nullptr; c->xbuf = nullptr; c->xbuf_comps = 0; c->xbuf_nzcs = 0;
-    c->halo = nullptr; c->halo_slot = 0; c->d_gather = nullptr; c->visc_tmp = nullptr;
+    c->halo = nullptr; c->halo_slot = 0; c->d_gather = nullptr; c->visc_tmp = nullptr; c->p2p = false;
     c->launches = 0; c->profiling = false;
     c->bc_active = false; c->bc_relax = 1.0;
     for (int i = 0; i < 81; i++) c->bc_MQ[i] = c->bc_MQC0[i] = 0;

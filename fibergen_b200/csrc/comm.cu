@@ -61,6 +61,84 @@ static int load_nccl(fgb_ctx* ctx) {
             return fgb_fail(ctx, FGB_ECOMM, "%s failed: %s", #call, g_nccl.GetErrorString(r__));  \
     } while (0)
 
+static int need_comm(fgb_ctx* ctx) {
+    if (!ctx->nccl_comm) return fgb_fail(ctx, FGB_ECOMM, "context has %d ranks but fgb_comm_init was not called", ctx->nranks);
+    return FGB_OK;
+}
+
+static int ensure_xbuf(fgb_ctx* ctx, int ncomp, int nzcs) {
+    if (ctx->xbuf && ctx->xbuf_comps >= ncomp && ctx->xbuf_nzcs >= nzcs) return FGB_OK;
+    if (ctx->p2p) return fgb_fail(ctx, FGB_EINVAL, "transposition buffers are mapped by the peers and cannot grow");
+    if (ctx->sbuf) cudaFree(ctx->sbuf);
+    if (ctx->xbuf) cudaFree(ctx->xbuf);
+    ctx->sbuf = ctx->xbuf = nullptr;
+    const GridDev& g = ctx->g;
+    const size_t bytes = sizeof(double) * 2 * (size_t)ncomp * g.lnx * g.ny * nzcs;
+    cudaError_t e = cudaMalloc(&ctx->sbuf, bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->xbuf, bytes);
+    if (e != cudaSuccess) return fgb_fail(ctx, FGB_ENOMEM, "cannot allocate the transpose buffers (%zu bytes each): %s", bytes, cudaGetErrorString(e));
+    ctx->xbuf_comps = ncomp;
+    ctx->xbuf_nzcs = nzcs;
+    return FGB_OK;
+}
+
+
+// stream-ordered barrier over all ranks (tiny all-gather): everything the peers enqueued before it has completed when it completes
+static int comm_barrier(fgb_ctx* ctx) {
+    FGB_NCCL(ctx, g_nccl.AllGather(ctx->d_result + 60, ctx->d_gather, 1, ncclDouble, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+    return FGB_OK;
+}
+
+// Map the transposition buffers of every peer (CUDA IPC over NVLink/NVSwitch) so that the FFT kernels can write the
+// transposed data straight into the destination GPU: compute and transfer become one kernel (no staging, no NCCL copy).
+// Falls back to the grouped ncclSend/ncclRecv all-to-all if any rank cannot map its peers (or FGB_NO_P2P is set).
+static int map_peers(fgb_ctx* ctx) {
+    ctx->p2p = false;
+    const int P = ctx->nranks, me = ctx->rank;
+    for (int q = 0; q < 8; q++) ctx->peer_xbuf[q] = ctx->peer_sbuf[q] = nullptr;
+    if (P > 8) return FGB_OK;
+    struct Handles { cudaIpcMemHandle_t x, s; double ok; };
+    static_assert(sizeof(Handles) % 8 == 0, "handle record must be a multiple of 8 bytes");
+    Handles mine;
+    memset(&mine, 0, sizeof(mine));
+    bool ok = getenv("FGB_NO_P2P") == nullptr;
+    if (ok) ok = cudaIpcGetMemHandle(&mine.x, ctx->xbuf) == cudaSuccess && cudaIpcGetMemHandle(&mine.s, ctx->sbuf) == cudaSuccess;
+    cudaGetLastError();
+    mine.ok = ok ? 1.0 : 0.0;
+    Handles* d_all = nullptr;
+    Handles* d_mine = nullptr;
+    FGB_CUDA(ctx, cudaMalloc(&d_all, sizeof(Handles) * P));
+    FGB_CUDA(ctx, cudaMalloc(&d_mine, sizeof(Handles)));
+    std::vector<Handles> all(P);
+    FGB_CUDA(ctx, cudaMemcpyAsync(d_mine, &mine, sizeof(Handles), cudaMemcpyHostToDevice, ctx->stream));
+    FGB_NCCL(ctx, g_nccl.AllGather(d_mine, d_all, sizeof(Handles), ncclChar, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+    FGB_CUDA(ctx, cudaMemcpyAsync(all.data(), d_all, sizeof(Handles) * P, cudaMemcpyDeviceToHost, ctx->stream));
+    FGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int q = 0; q < P; q++) ok = ok && all[q].ok == 1.0;
+    if (ok) {
+        for (int q = 0; q < P && ok; q++) {
+            if (q == me) { ctx->peer_xbuf[q] = ctx->xbuf; ctx->peer_sbuf[q] = ctx->sbuf; continue; }
+            void *px = nullptr, *psb = nullptr;
+            ok = cudaIpcOpenMemHandle(&px, all[q].x, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess &&
+                 cudaIpcOpenMemHandle(&psb, all[q].s, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+            ctx->peer_xbuf[q] = (double*)px;
+            ctx->peer_sbuf[q] = (double*)psb;
+        }
+        cudaGetLastError();
+    }
+    // consensus: every rank must have mapped every peer
+    mine.ok = ok ? 1.0 : 0.0;
+    FGB_CUDA(ctx, cudaMemcpyAsync(d_mine, &mine, sizeof(Handles), cudaMemcpyHostToDevice, ctx->stream));
+    FGB_NCCL(ctx, g_nccl.AllGather(d_mine, d_all, sizeof(Handles), ncclChar, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+    FGB_CUDA(ctx, cudaMemcpyAsync(all.data(), d_all, sizeof(Handles) * P, cudaMemcpyDeviceToHost, ctx->stream));
+    FGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int q = 0; q < P; q++) ok = ok && all[q].ok == 1.0;
+    cudaFree(d_all);
+    cudaFree(d_mine);
+    ctx->p2p = ok;
+    return FGB_OK;
+}
+
 extern "C" int fgb_comm_unique_id(void* id128) {
     static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
     int rc = load_nccl(nullptr);
@@ -88,37 +166,27 @@ extern "C" int fgb_comm_init(fgb_ctx* ctx, const void* id128) {
     ctx->halo_slot = a > b ? a : b;
     FGB_CUDA(ctx, cudaMalloc(&ctx->halo, sizeof(double) * 6 * ctx->halo_slot));
     FGB_CUDA(ctx, cudaMalloc(&ctx->d_gather, sizeof(double) * 64 * ctx->nranks));
-    return FGB_OK;
+    // transposition buffers are allocated once (their addresses are exported to the peers)
+    const bool stag = ctx->scheme == FGB_GAMMA_STAGGERED;
+    if ((rc = ensure_xbuf(ctx, stag ? ctx->udim : ctx->dim, stag ? g.unzcs : g.nzc))) return rc;
+    return map_peers(ctx);
 }
 
 int fgb_comm_free(fgb_ctx* ctx) {
     if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)ctx->nccl_comm);
     ctx->nccl_comm = nullptr;
+    if (ctx->p2p)
+        for (int q = 0; q < ctx->nranks && q < 8; q++)
+            if (q != ctx->rank) {
+                if (ctx->peer_xbuf[q]) cudaIpcCloseMemHandle(ctx->peer_xbuf[q]);
+                if (ctx->peer_sbuf[q]) cudaIpcCloseMemHandle(ctx->peer_sbuf[q]);
+            }
+    ctx->p2p = false;
     if (ctx->sbuf) cudaFree(ctx->sbuf);
     if (ctx->xbuf) cudaFree(ctx->xbuf);
     if (ctx->halo) cudaFree(ctx->halo);
     if (ctx->d_gather) cudaFree(ctx->d_gather);
     ctx->sbuf = ctx->xbuf = ctx->halo = ctx->d_gather = nullptr;
-    return FGB_OK;
-}
-
-static int need_comm(fgb_ctx* ctx) {
-    if (!ctx->nccl_comm) return fgb_fail(ctx, FGB_ECOMM, "context has %d ranks but fgb_comm_init was not called", ctx->nranks);
-    return FGB_OK;
-}
-
-static int ensure_xbuf(fgb_ctx* ctx, int ncomp, int nzcs) {
-    if (ctx->xbuf && ctx->xbuf_comps >= ncomp && ctx->xbuf_nzcs >= nzcs) return FGB_OK;
-    if (ctx->sbuf) cudaFree(ctx->sbuf);
-    if (ctx->xbuf) cudaFree(ctx->xbuf);
-    ctx->sbuf = ctx->xbuf = nullptr;
-    const GridDev& g = ctx->g;
-    const size_t bytes = sizeof(double) * 2 * (size_t)ncomp * g.lnx * g.ny * nzcs;
-    cudaError_t e = cudaMalloc(&ctx->sbuf, bytes);
-    if (e == cudaSuccess) e = cudaMalloc(&ctx->xbuf, bytes);
-    if (e != cudaSuccess) return fgb_fail(ctx, FGB_ENOMEM, "cannot allocate the transpose buffers (%zu bytes each): %s", bytes, cudaGetErrorString(e));
-    ctx->xbuf_comps = ncomp;
-    ctx->xbuf_nzcs = nzcs;
     return FGB_OK;
 }
 
@@ -153,6 +221,29 @@ int fgb_comm_fft_x(fgb_ctx* ctx, double* base, int ncomp, const FftLayout& lay, 
     const size_t chunk = (size_t)g.lnx * lny * nzcs;                 // complex numbers per (component, peer)
     const PencilMap nat = {nzcs, g.ny, 0, (long)g.ny * nzcs, (long)g.lnx * g.ny * nzcs};
     const PencilMap stg = {nzcs, lny, (long)chunk, (long)lny * nzcs, (long)P * (long)chunk};
+    if (ctx->p2p && nzcs == ctx->xbuf_nzcs) {
+        // fused compute + transfer: the forward y pass stores segment q of every pencil into R of rank q over NVLink,
+        // the fused x pass stores segment q of its output into the staging buffer of rank q; two stream-ordered barriers.
+        const int me = ctx->rank;
+        PeerTable pr, psb;
+        pr.n = psb.n = P;
+        for (int q = 0; q < P; q++) {
+            pr.p[q] = (double2*)ctx->peer_xbuf[q] + (long)me * g.lnx * lny * nzcs;     // R_q[c][me*lnx + il][jl][k]
+            psb.p[q] = (double2*)ctx->peer_sbuf[q] + (long)me * (long)chunk;            // S_q[c][me][il][jl][k]
+        }
+        const PencilMap rmap = {nzcs, lny, 0, (long)lny * nzcs, (long)g.nx * lny * nzcs};
+        const PencilMap smap = {(long)lny * nzcs, g.lnx, 0, (long)nzcs, (long)P * (long)chunk};
+        {
+            ProfScope ps(ctx, "fft_y_fwd_p2p");
+            if ((rc = fgb_fft_strided(ctx, 1, base, ctx->xbuf, nat, rmap, g.nzc, g.lnx, ncomp, -1, &pr))) return rc;
+        }
+        if ((rc = comm_barrier(ctx))) return rc;
+        if ((rc = fgb_fft_x_green_layout(ctx, ctx->xbuf, ga, (long)lny * nzcs, g.nzc, lny, nzcs, (long)g.nx * lny * nzcs, me * lny, &smap, &psb)))
+            return rc;
+        if ((rc = comm_barrier(ctx))) return rc;
+        ProfScope ps(ctx, "fft_y_bwd");
+        return fgb_fft_strided(ctx, 1, ctx->sbuf, base, stg, nat, g.nzc, g.lnx, ncomp, +1);
+    }
     {
         ProfScope ps(ctx, "fft_y_fwd");
         if ((rc = fgb_fft_strided(ctx, 1, base, ctx->sbuf, nat, stg, g.nzc, g.lnx, ncomp, -1))) return rc;

@@ -116,7 +116,8 @@ __global__ void __launch_bounds__(FFTZ_THREADS) k_fftz_p2(double* __restrict__ b
 // writes straight into (reads straight from) the all-to-all staging layout.
 template <int N, int R1, int R2, int DIR, int T>
 __global__ void __launch_bounds__(Max<R1, R2>::v* T) k_ffts_p2(const double2* __restrict__ src, double2* __restrict__ dst,
-                                                               const double2* __restrict__ tw, PencilMap mi, PencilMap mo, int ninner) {
+                                                               const double2* __restrict__ tw, PencilMap mi, PencilMap mo, int ninner,
+                                                               PeerTable pt) {
     constexpr int TPP = Max<R1, R2>::v;
     __shared__ double2 tw_s[N];
     __shared__ double2 X[N * T];
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(Max<R1, R2>::v* T) k_ffts_p2(const double2* __
     const int inner = blockIdx.x * T + t;
     const bool valid = inner < ninner;
     const double2* gi = src + (long)blockIdx.z * mi.cstride + (long)blockIdx.y * mi.ostride + inner;
-    double2* go = dst + (long)blockIdx.z * mo.cstride + (long)blockIdx.y * mo.ostride + inner;
+    const long coff = (long)blockIdx.z * mo.cstride + (long)blockIdx.y * mo.ostride + inner;
     double2 v[R1];
     if (s < R2) {
 #pragma unroll
@@ -146,7 +147,11 @@ __global__ void __launch_bounds__(Max<R1, R2>::v* T) k_ffts_p2(const double2* __
         p2::RegFFT<R2, DIR>::run(w);
         if (valid) {
 #pragma unroll
-            for (int k2 = 0; k2 < R2; k2++) go[mo.at(s + R1 * k2)] = w[k2];
+            for (int k2 = 0; k2 < R2; k2++) {
+                const int e = s + R1 * k2;
+                double2* b = pt.n ? pt.p[e / mo.seglen] : dst;
+                b[coff + mo.at(e)] = w[k2];
+            }
         }
     }
 }
@@ -158,7 +163,8 @@ __global__ void __launch_bounds__(Max<R1, R2>::v* T) k_ffts_p2(const double2* __
 //             -> x[na + R2 nb], the same distribution the forward pass loaded, stored straight back to HBM.
 template <int N, int R1, int R2, int NC, int KIND, int T>
 __global__ void __launch_bounds__(Max<R1, R2>::v* T) k_fftx_green_p2(double2* __restrict__ base, const double2* __restrict__ tw, GreenDev G,
-                                                                     long estride, int ninner, long ostride, long cstride, int jbase) {
+                                                                     long estride, int ninner, long ostride, long cstride, int jbase,
+                                                                     PencilMap xo, PeerTable pt) {
     constexpr int TPP = Max<R1, R2>::v;
     constexpr int NT = TPP * T;
     extern __shared__ double2 smem[];
@@ -251,7 +257,11 @@ __global__ void __launch_bounds__(Max<R1, R2>::v* T) k_fftx_green_p2(double2* __
             p2::RegFFT<R1, +1>::run(v);
             if (valid) {
 #pragma unroll
-                for (int nb = 0; nb < R1; nb++) g[c * cstride + (long)(s + R2 * nb) * estride] = v[nb];
+                for (int nb = 0; nb < R1; nb++) {
+                    const int e = s + R2 * nb;
+                    double2* b = pt.n ? pt.p[e / xo.seglen] : base;
+                    b[c * xo.cstride + (long)blockIdx.y * xo.ostride + inner + xo.at(e)] = v[nb];
+                }
             }
         }
     }
@@ -406,16 +416,19 @@ int fgb_fft_z_backward(fgb_ctx* ctx, double* base, int ncomp, const FftLayout& l
 // ---- strided (y, plain x) -----------------------------------------------------------------------------
 template <int N, int R1, int R2, int T>
 static void launch_s_p2(fgb_ctx* ctx, const double2* src, double2* dst, const double2* tw, const PencilMap& mi, const PencilMap& mo,
-                        int ninner, int nouter, int ncomp, int dir) {
+                        int ninner, int nouter, int ncomp, int dir, const PeerTable& pt) {
     dim3 grid((ninner + T - 1) / T, nouter, ncomp);
     constexpr int NT = Max<R1, R2>::v * T;
-    if (dir < 0) k_ffts_p2<N, R1, R2, -1, T><<<grid, NT, 0, ctx->stream>>>(src, dst, tw, mi, mo, ninner);
-    else k_ffts_p2<N, R1, R2, +1, T><<<grid, NT, 0, ctx->stream>>>(src, dst, tw, mi, mo, ninner);
+    if (dir < 0) k_ffts_p2<N, R1, R2, -1, T><<<grid, NT, 0, ctx->stream>>>(src, dst, tw, mi, mo, ninner, pt);
+    else k_ffts_p2<N, R1, R2, +1, T><<<grid, NT, 0, ctx->stream>>>(src, dst, tw, mi, mo, ninner, pt);
 }
 
 int fgb_fft_strided(fgb_ctx* ctx, int axis, const double* src_, double* dst_, const PencilMap& mi, const PencilMap& mo, int ninner,
-                    int nouter, int ncomp, int dir) {
+                    int nouter, int ncomp, int dir, const PeerTable* peers) {
     const int n = ctx->plan[axis].n;
+    PeerTable pt;
+    pt.n = 0;
+    if (peers) pt = *peers;
     const double2* src = (const double2*)src_;
     double2* dst = (double2*)dst_;
     if (ninner == 0 || nouter == 0) return FGB_OK;
@@ -423,11 +436,11 @@ int fgb_fft_strided(fgb_ctx* ctx, int axis, const double* src_, double* dst_, co
     const double2* tw = ctx->plan[axis].tw;
     if (is_fast_pow2(n)) {
         switch (n) {
-            case 64: launch_s_p2<64, 8, 8, 8>(ctx, src, dst, tw, mi, mo, ninner, nouter, ncomp, dir); break;
-            case 128: launch_s_p2<128, 16, 8, 8>(ctx, src, dst, tw, mi, mo, ninner, nouter, ncomp, dir); break;
-            case 256: launch_s_p2<256, 16, 16, 8>(ctx, src, dst, tw, mi, mo, ninner, nouter, ncomp, dir); break;
-            case 512: launch_s_p2<512, 32, 16, 4>(ctx, src, dst, tw, mi, mo, ninner, nouter, ncomp, dir); break;
-            case 1024: launch_s_p2<1024, 32, 32, 2>(ctx, src, dst, tw, mi, mo, ninner, nouter, ncomp, dir); break;
+            case 64: launch_s_p2<64, 8, 8, 8>(ctx, src, dst, tw, mi, mo, ninner, nouter, ncomp, dir, pt); break;
+            case 128: launch_s_p2<128, 16, 8, 8>(ctx, src, dst, tw, mi, mo, ninner, nouter, ncomp, dir, pt); break;
+            case 256: launch_s_p2<256, 16, 16, 8>(ctx, src, dst, tw, mi, mo, ninner, nouter, ncomp, dir, pt); break;
+            case 512: launch_s_p2<512, 32, 16, 4>(ctx, src, dst, tw, mi, mo, ninner, nouter, ncomp, dir, pt); break;
+            case 1024: launch_s_p2<1024, 32, 32, 2>(ctx, src, dst, tw, mi, mo, ninner, nouter, ncomp, dir, pt); break;
         }
         FGB_CHECK_LAUNCH(ctx, "k_ffts_p2");
         return FGB_OK;
@@ -438,10 +451,10 @@ int fgb_fft_strided(fgb_ctx* ctx, int axis, const double* src_, double* dst_, co
     dim3 grid((ninner + T - 1) / T, nouter, ncomp);
     if (dir < 0) {
         FGB_CUDA(ctx, set_smem(k_fft_strided<-1>, smem));
-        k_fft_strided<-1><<<grid, 256, smem, ctx->stream>>>(src, dst, ctx->plan[axis], mi, mo, ninner, T);
+        k_fft_strided<-1><<<grid, 256, smem, ctx->stream>>>(src, dst, ctx->plan[axis], mi, mo, ninner, T, pt);
     } else {
         FGB_CUDA(ctx, set_smem(k_fft_strided<1>, smem));
-        k_fft_strided<1><<<grid, 256, smem, ctx->stream>>>(src, dst, ctx->plan[axis], mi, mo, ninner, T);
+        k_fft_strided<1><<<grid, 256, smem, ctx->stream>>>(src, dst, ctx->plan[axis], mi, mo, ninner, T, pt);
     }
     FGB_CHECK_LAUNCH(ctx, "k_fft_strided");
     return FGB_OK;
@@ -457,30 +470,30 @@ int fgb_fft_y(fgb_ctx* ctx, double* base, int ncomp, const FftLayout& lay, int d
 // ---- x with Green operator ---------------------------------------------------------------------------------
 template <int N, int R1, int R2, int NC, int KIND, int T>
 static int launch_xg_p2(fgb_ctx* ctx, double2* base, const GreenDev& G, long estride, int ninner, int nouter, long ostride, long cstride,
-                        int jbase) {
+                        int jbase, const PencilMap& xo, const PeerTable& pt) {
     constexpr int NT = Max<R1, R2>::v * T;
     const size_t smem = (size_t)(N + (size_t)NC * N * T) * sizeof(double2);
     if (smem > ctx->smem_optin) return -1;
     dim3 grid((ninner + T - 1) / T, nouter, 1);
     FGB_CUDA(ctx, set_smem(k_fftx_green_p2<N, R1, R2, NC, KIND, T>, smem));
-    k_fftx_green_p2<N, R1, R2, NC, KIND, T><<<grid, NT, smem, ctx->stream>>>(base, ctx->plan[0].tw, G, estride, ninner, ostride, cstride, jbase);
+    k_fftx_green_p2<N, R1, R2, NC, KIND, T><<<grid, NT, smem, ctx->stream>>>(base, ctx->plan[0].tw, G, estride, ninner, ostride, cstride, jbase, xo, pt);
     FGB_CHECK_LAUNCH(ctx, "k_fftx_green_p2");
     return FGB_OK;
 }
 
 template <int NC, int KIND>
 static int launch_x_green(fgb_ctx* ctx, double2* base, const GreenDev& G, long estride, int ninner, int nouter, long ostride, long cstride,
-                          int jbase) {
+                          int jbase, const PencilMap& xo, const PeerTable& pt) {
     const int nx = ctx->g.nx;
     int rc = -1;
     // register budget: NC*R2 complex per thread -> the fast path covers NC <= 3 (staggered / heat); larger tensors use the generic kernel
     if constexpr (NC <= 3) {
         switch (nx) {
-            case 64: rc = launch_xg_p2<64, 8, 8, NC, KIND, 8>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase); break;
-            case 128: rc = launch_xg_p2<128, 16, 8, NC, KIND, 8>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase); break;
-            case 256: rc = launch_xg_p2<256, 16, 16, NC, KIND, 8>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase); break;
-            case 512: rc = launch_xg_p2<512, 32, 16, NC, KIND, 4>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase); break;
-            case 1024: if constexpr (NC == 1) rc = launch_xg_p2<1024, 32, 32, NC, KIND, 2>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase); break;
+            case 64: rc = launch_xg_p2<64, 8, 8, NC, KIND, 8>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt); break;
+            case 128: rc = launch_xg_p2<128, 16, 8, NC, KIND, 8>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt); break;
+            case 256: rc = launch_xg_p2<256, 16, 16, NC, KIND, 8>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt); break;
+            case 512: rc = launch_xg_p2<512, 32, 16, NC, KIND, 4>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt); break;
+            case 1024: if constexpr (NC == 1) rc = launch_xg_p2<1024, 32, 32, NC, KIND, 2>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt); break;
         }
         if (rc != -1) return rc;
     }
@@ -489,7 +502,7 @@ static int launch_x_green(fgb_ctx* ctx, double2* base, const GreenDev& G, long e
     const size_t smem = (size_t)(NC + 1) * nx * T * sizeof(double2);
     dim3 grid((ninner + T - 1) / T, nouter, 1);
     FGB_CUDA(ctx, set_smem(k_fft_x_green<NC, KIND>, smem));
-    k_fft_x_green<NC, KIND><<<grid, 256, smem, ctx->stream>>>(base, ctx->plan[0], G, estride, ninner, ostride, cstride, T, jbase);
+    k_fft_x_green<NC, KIND><<<grid, 256, smem, ctx->stream>>>(base, ctx->plan[0], G, estride, ninner, ostride, cstride, T, jbase, xo, pt);
     FGB_CHECK_LAUNCH(ctx, "k_fft_x_green");
     return FGB_OK;
 }
@@ -508,17 +521,22 @@ static void fill_green(const fgb_ctx* ctx, const GreenArgs* ga, GreenDev& G) {
 
 // x pass on a buffer whose x extent is complete: element (ii, jj, kk) at base[c*cstride + (jj-jbase)*ostride + ii*estride + kk]
 int fgb_fft_x_green_layout(fgb_ctx* ctx, double* base, const GreenArgs* ga, long estride, int nzc_valid, int nouter, long ostride,
-                           long cstride, int jbase) {
+                           long cstride, int jbase, const PencilMap* out_map, const PeerTable* peers) {
     GreenDev G;
     fill_green(ctx, ga, G);
+    PencilMap xo = {estride, ctx->g.nx, 0, ostride, cstride};       // default: store back in place
+    if (out_map) xo = *out_map;
+    PeerTable pt;
+    pt.n = 0;
+    if (peers) pt = *peers;
     double2* b = (double2*)base;
     ProfScope ps(ctx, "fft_x_green");
     switch (ga->kind) {
-        case 1: return launch_x_green<3, 1>(ctx, b, G, estride, nzc_valid, nouter, ostride, cstride, jbase);
-        case 2: return launch_x_green<1, 2>(ctx, b, G, estride, nzc_valid, nouter, ostride, cstride, jbase);
-        case 3: return launch_x_green<6, 3>(ctx, b, G, estride, nzc_valid, nouter, ostride, cstride, jbase);
-        case 4: return launch_x_green<3, 4>(ctx, b, G, estride, nzc_valid, nouter, ostride, cstride, jbase);
-        case 5: return launch_x_green<9, 5>(ctx, b, G, estride, nzc_valid, nouter, ostride, cstride, jbase);
+        case 1: return launch_x_green<3, 1>(ctx, b, G, estride, nzc_valid, nouter, ostride, cstride, jbase, xo, pt);
+        case 2: return launch_x_green<1, 2>(ctx, b, G, estride, nzc_valid, nouter, ostride, cstride, jbase, xo, pt);
+        case 3: return launch_x_green<6, 3>(ctx, b, G, estride, nzc_valid, nouter, ostride, cstride, jbase, xo, pt);
+        case 4: return launch_x_green<3, 4>(ctx, b, G, estride, nzc_valid, nouter, ostride, cstride, jbase, xo, pt);
+        case 5: return launch_x_green<9, 5>(ctx, b, G, estride, nzc_valid, nouter, ostride, cstride, jbase, xo, pt);
     }
     return fgb_fail(ctx, FGB_EINVAL, "unknown Green operator kind %d", ga->kind);
 }

@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(256) k_fft_z(double* __restrict__ base, long r
 // ------------------------------------------------------------------------------------------------
 template <int DIR>
 __global__ void __launch_bounds__(256) k_fft_strided(const double2* __restrict__ src, double2* __restrict__ dst, FftPlanDev P,
-                                                     PencilMap mi, PencilMap mo, int ninner, int T) {
+                                                     PencilMap mi, PencilMap mo, int ninner, int T, PeerTable pt) {
     extern __shared__ double2 smem[];
     const int n = P.n;
     double2* a = smem;
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(256) k_fft_strided(const double2* __restrict__
     const int tid = threadIdx.x, nth = blockDim.x;
     const int inner0 = blockIdx.x * T;
     const double2* gi = src + (long)blockIdx.z * mi.cstride + (long)blockIdx.y * mi.ostride + inner0;
-    double2* go = dst + (long)blockIdx.z * mo.cstride + (long)blockIdx.y * mo.ostride + inner0;
+    const long coff = (long)blockIdx.z * mo.cstride + (long)blockIdx.y * mo.ostride + inner0;
     const int tmax = min(T, ninner - inner0);
     for (int idx = tid; idx < n * T; idx += nth) {
         const int e = idx / T, t = idx % T;
@@ -195,7 +195,10 @@ __global__ void __launch_bounds__(256) k_fft_strided(const double2* __restrict__
     double2* res = fft_tile<DIR>(a, b, P, T, T);
     for (int idx = tid; idx < n * T; idx += nth) {
         const int e = idx / T, t = idx % T;
-        if (t < tmax) go[mo.at(e) + t] = res[idx];
+        if (t < tmax) {
+            double2* b = pt.n ? pt.p[e / mo.seglen] : dst;
+            b[coff + mo.at(e) + t] = res[idx];
+        }
     }
 }
 
@@ -357,7 +360,7 @@ __device__ __forceinline__ void green_colloc_hyper(const GreenDev& G, int ii, in
 // ------------------------------------------------------------------------------------------------
 template <int NC, int KIND>
 __global__ void __launch_bounds__(256) k_fft_x_green(double2* __restrict__ base, FftPlanDev P, GreenDev G, long estride,
-                                                     int ninner, long ostride, long cstride, int T, int jbase) {
+                                                     int ninner, long ostride, long cstride, int T, int jbase, PencilMap xo, PeerTable pt) {
     extern __shared__ double2 smem[];
     const int n = P.n;
     const int tid = threadIdx.x, nth = blockDim.x;
@@ -415,7 +418,10 @@ __global__ void __launch_bounds__(256) k_fft_x_green(double2* __restrict__ base,
     for (int c = 0; c < NC; c++) {
         for (int idx = tid; idx < n * T; idx += nth) {
             const int e = idx / T, t = idx % T;
-            if (t < tmax) g[c * cstride + (long)e * estride + t] = ptr[c][idx];
+            if (t < tmax) {
+                double2* b = pt.n ? pt.p[e / xo.seglen] : base;
+                b[c * xo.cstride + (long)blockIdx.y * xo.ostride + inner0 + xo.at(e) + t] = ptr[c][idx];
+            }
         }
     }
 }

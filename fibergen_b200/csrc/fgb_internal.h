@@ -102,6 +102,9 @@ struct fgb_ctx {
     double* halo;               // [3 lo slots][3 hi slots] of halo_slot doubles (neighbour x planes for the stencils)
     size_t halo_slot;
     double* d_gather;           // rank-ordered reduction staging
+    bool p2p;                   // peer buffers mapped: transposes are written by the FFT kernels straight into peer memory
+    double* peer_xbuf[8];       // xbuf of every rank (own pointer at [rank])
+    double* peer_sbuf[8];
 
     // mixed boundary conditions (fgb_set_bc): row-major dim x dim matrices MQ and M:(QC0)
     bool bc_active;
@@ -163,12 +166,18 @@ struct PencilMap {
     }
 #endif
 };
+// destination bases of a store that targets peer GPUs: segment q of a pencil (PencilMap::seglen elements) goes to p[q]
+// (mapped peer memory over NVLink, cudaIpcOpenMemHandle); n == 0 means "store locally"
+struct PeerTable {
+    int n;
+    double2* p[8];
+};
 // in-place r2c/c2r along z of `ncomp` components starting at base
 int fgb_fft_z_forward(fgb_ctx* ctx, double* base, int ncomp, const FftLayout& lay);
 int fgb_fft_z_backward(fgb_ctx* ctx, double* base, int ncomp, const FftLayout& lay);
 int fgb_fft_y(fgb_ctx* ctx, double* base, int ncomp, const FftLayout& lay, int dir);
 int fgb_fft_strided(fgb_ctx* ctx, int axis, const double* src, double* dst, const PencilMap& mi, const PencilMap& mo, int ninner,
-                    int nouter, int ncomp, int dir);
+                    int nouter, int ncomp, int dir, const PeerTable* peers = nullptr);
 // x pass; green_kind: 0 none (plain forward or backward per dir), otherwise fused fwd-x, Green, inv-x
 struct GreenArgs {
     int kind;             // 0 none, 1 staggered elasticity/hyper (general), 2 staggered heat, 3 colloc elasticity, 4 colloc heat, 5 colloc hyper
@@ -179,7 +188,7 @@ struct GreenArgs {
 };
 int fgb_fft_x(fgb_ctx* ctx, double* base, int ncomp, const FftLayout& lay, int dir, const GreenArgs* ga);
 int fgb_fft_x_green_layout(fgb_ctx* ctx, double* base, const GreenArgs* ga, long estride, int nzc_valid, int nouter, long ostride,
-                           long cstride, int jbase);
+                           long cstride, int jbase, const PencilMap* out_map = nullptr, const PeerTable* peers = nullptr);
 
 // stencil.cu ---------------------------------------------------------------------------------
 int fgb_k_div(fgb_ctx* ctx, const double* tau, double* u);
