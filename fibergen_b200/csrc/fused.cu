@@ -10,6 +10,7 @@
 //                          <p, p - eta>                                (innerProductL2 fg:20871) in the same pass.
 #include "fgb_internal.h"
 #include "reduce.cuh"
+#include <cstdlib>
 
 struct IsoPhases {
     int n;
@@ -164,6 +165,185 @@ __global__ void __launch_bounds__(256) k_dir_stress_div_iso(const double* __rest
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// x-marching version of the fused sweep.  A thread owns one k column of BJ consecutive y rows and walks along x:
+//   * y neighbours (tau_1 at j-1, tau_5 / tau_3 at j+1) are its own registers (plus one halo row on either side),
+//   * the previous x plane's tau_0 and the next x plane's tau_5 / tau_4 (with its phi) are carried in registers,
+//   * z neighbours come from the adjacent lanes by warp shuffle (direct evaluation at warp / chunk edges),
+// so every r, p_old and phi value of the CTA's own rows is loaded exactly once; no shared memory, no barriers.
+template <int NP>
+__device__ __forceinline__ void phi_load(const IsoPhases& M, size_t o, double* phi) {
+#pragma unroll
+    for (int p = 0; p < NP; p++) phi[p] = __ldg(M.phi[p] + o);
+}
+template <int NP>
+__device__ __forceinline__ double shear_from(const IsoPhases& M, const double* phi, double e, double beta) {
+    double t = 0;
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+        const double two_mu = (phi[p] > FGB_VOIGT_THR) ? 2 * phi[p] * M.mu[p] : 0.0;
+        t += e * two_mu;
+    }
+    if (beta != 0) t += beta * e;
+    return t;
+}
+template <int NP>
+__device__ __forceinline__ void diag_from(const IsoPhases& M, const double* phi, double e0, double e1, double e2, double beta, double gamma,
+                                          double& t0, double& t1, double& t2) {
+    const double tr = e0 + e1 + e2;
+    t0 = t1 = t2 = 0;
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+        const bool on = phi[p] > FGB_VOIGT_THR;
+        const double two_mu = on ? 2 * phi[p] * M.mu[p] : 0.0;
+        const double ltr = on ? (phi[p] * M.lam[p]) * tr : 0.0;
+        t0 += e0 * two_mu + ltr;
+        t1 += e1 * two_mu + ltr;
+        t2 += e2 * two_mu + ltr;
+    }
+    if (beta != 0) { t0 += beta * e0; t1 += beta * e1; t2 += beta * e2; }
+    if (gamma != 0) { t0 += gamma * tr; t1 += gamma * tr; t2 += gamma * tr; }
+}
+
+template <int UPDATE, int NP, int BJ>
+__global__ void __launch_bounds__(256) k_dsd_march(const double* __restrict__ r, const double* __restrict__ p_old, double* __restrict__ p_new,
+                                                   double* __restrict__ u, GridDev g, IsoPhases M, double cgbeta, double beta, double gamma,
+                                                   int SEG) {
+    const int j0 = blockIdx.x * BJ;
+    const int i0 = blockIdx.y * SEG;
+    const int i1 = min(i0 + SEG, g.lnx);
+    const int k = blockIdx.z * blockDim.x + threadIdx.x;
+    const bool active = k < g.nz;
+    const int kc = active ? k : 0;                      // inactive lanes shadow k = 0 (no stores) so that shuffles stay uniform
+    const int lane = threadIdx.x & 31;
+    const size_t P = g.plane;
+    const int jm0 = (j0 == 0) ? g.ny - 1 : j0 - 1;
+    const int jpB = (j0 + BJ == g.ny) ? 0 : j0 + BJ;
+    const int kp = (kc + 1 == g.nz) ? 0 : kc + 1, km = (kc == 0) ? g.nz - 1 : kc - 1;
+    const bool edge_hi = (lane == 31) || (threadIdx.x == blockDim.x - 1) || (kc + 1 >= g.nz);
+    const bool edge_lo = (lane == 0) || (kc == 0);
+#define ROW(i, j) (((size_t)(i) * g.ny + (j)) * g.nzp)
+
+    double t0_prev[BJ], t5n[BJ], t4n[BJ], phin[BJ][NP];
+    // warm-up: tau_0 of plane i0-1, and tau_5 / tau_4 / phi of plane i0
+    {
+        const int im = (i0 == 0) ? g.lnx - 1 : i0 - 1;
+#pragma unroll
+        for (int jr = 0; jr < BJ; jr++) {
+            double ph[NP], d1, d2;
+            size_t o = ROW(im, j0 + jr) + kc;
+            phi_load<NP>(M, o, ph);
+            diag_from<NP>(M, ph, pval<UPDATE>(r, p_old, o, cgbeta), pval<UPDATE>(r, p_old, P + o, cgbeta),
+                          pval<UPDATE>(r, p_old, 2 * P + o, cgbeta), beta, gamma, t0_prev[jr], d1, d2);
+            o = ROW(i0, j0 + jr) + kc;
+            phi_load<NP>(M, o, phin[jr]);
+            const double e5 = pval<UPDATE>(r, p_old, 5 * P + o, cgbeta), e4 = pval<UPDATE>(r, p_old, 4 * P + o, cgbeta);
+            if (UPDATE && active) { p_new[5 * P + o] = e5; p_new[4 * P + o] = e4; }
+            t5n[jr] = shear_from<NP>(M, phin[jr], e5, beta);
+            t4n[jr] = shear_from<NP>(M, phin[jr], e4, beta);
+        }
+    }
+    for (int i = i0; i < i1; i++) {
+        const int ip = (i + 1 == g.lnx) ? 0 : i + 1;
+        // halo rows of plane i
+        double t1_m, t5_p, t3_p;
+        {
+            double ph[NP], d0, d2;
+            size_t o = ROW(i, jm0) + kc;
+            phi_load<NP>(M, o, ph);
+            diag_from<NP>(M, ph, pval<UPDATE>(r, p_old, o, cgbeta), pval<UPDATE>(r, p_old, P + o, cgbeta),
+                          pval<UPDATE>(r, p_old, 2 * P + o, cgbeta), beta, gamma, d0, t1_m, d2);
+            o = ROW(i, jpB) + kc;
+            phi_load<NP>(M, o, ph);
+            t5_p = shear_from<NP>(M, ph, pval<UPDATE>(r, p_old, 5 * P + o, cgbeta), beta);
+            t3_p = shear_from<NP>(M, ph, pval<UPDATE>(r, p_old, 3 * P + o, cgbeta), beta);
+        }
+        // own rows of plane i: components 0..3 from memory, 4 and 5 carried from the previous step
+        double tc[BJ][6];
+#pragma unroll
+        for (int jr = 0; jr < BJ; jr++) {
+            const size_t o = ROW(i, j0 + jr) + kc;
+            const double e0 = pval<UPDATE>(r, p_old, o, cgbeta), e1 = pval<UPDATE>(r, p_old, P + o, cgbeta);
+            const double e2 = pval<UPDATE>(r, p_old, 2 * P + o, cgbeta), e3 = pval<UPDATE>(r, p_old, 3 * P + o, cgbeta);
+            if (UPDATE && active) { p_new[o] = e0; p_new[P + o] = e1; p_new[2 * P + o] = e2; p_new[3 * P + o] = e3; }
+            diag_from<NP>(M, phin[jr], e0, e1, e2, beta, gamma, tc[jr][0], tc[jr][1], tc[jr][2]);
+            tc[jr][3] = shear_from<NP>(M, phin[jr], e3, beta);
+            tc[jr][4] = t4n[jr];
+            tc[jr][5] = t5n[jr];
+        }
+        // next plane: phi, tau_5, tau_4 (and the p_new values of those two components)
+#pragma unroll
+        for (int jr = 0; jr < BJ; jr++) {
+            const size_t o = ROW(ip, j0 + jr) + kc;
+            phi_load<NP>(M, o, phin[jr]);
+            const double e5 = pval<UPDATE>(r, p_old, 5 * P + o, cgbeta), e4 = pval<UPDATE>(r, p_old, 4 * P + o, cgbeta);
+            if (UPDATE && active && (i + 1 < i1)) { p_new[5 * P + o] = e5; p_new[4 * P + o] = e4; }
+            t5n[jr] = shear_from<NP>(M, phin[jr], e5, beta);
+            t4n[jr] = shear_from<NP>(M, phin[jr], e4, beta);
+        }
+#pragma unroll
+        for (int jr = 0; jr < BJ; jr++) {
+            // z neighbours
+            double t4_kp = __shfl_down_sync(0xffffffffu, tc[jr][4], 1);
+            double t3_kp = __shfl_down_sync(0xffffffffu, tc[jr][3], 1);
+            double t2_km = __shfl_up_sync(0xffffffffu, tc[jr][2], 1);
+            if (edge_hi) {
+                double ph[NP];
+                const size_t o = ROW(i, j0 + jr) + kp;
+                phi_load<NP>(M, o, ph);
+                t4_kp = shear_from<NP>(M, ph, pval<UPDATE>(r, p_old, 4 * P + o, cgbeta), beta);
+                t3_kp = shear_from<NP>(M, ph, pval<UPDATE>(r, p_old, 3 * P + o, cgbeta), beta);
+            }
+            if (edge_lo) {
+                double ph[NP], d0, d1;
+                const size_t o = ROW(i, j0 + jr) + km;
+                phi_load<NP>(M, o, ph);
+                diag_from<NP>(M, ph, pval<UPDATE>(r, p_old, o, cgbeta), pval<UPDATE>(r, p_old, P + o, cgbeta),
+                              pval<UPDATE>(r, p_old, 2 * P + o, cgbeta), beta, gamma, d0, d1, t2_km);
+            }
+            const double t1_jm = (jr == 0) ? t1_m : tc[jr > 0 ? jr - 1 : 0][1];
+            const double t5_jp = (jr == BJ - 1) ? t5_p : tc[jr < BJ - 1 ? jr + 1 : jr][5];
+            const double t3_jp = (jr == BJ - 1) ? t3_p : tc[jr < BJ - 1 ? jr + 1 : jr][3];
+            // divOperatorStaggered fg:18863-18901
+            const double f0 = (tc[jr][0] - t0_prev[jr]) * g.hx + (t5_jp - tc[jr][5]) * g.hy + (t4_kp - tc[jr][4]) * g.hz;
+            const double f1 = (t5n[jr] - tc[jr][5]) * g.hx + (tc[jr][1] - t1_jm) * g.hy + (t3_kp - tc[jr][3]) * g.hz;
+            const double f2 = (t4n[jr] - tc[jr][4]) * g.hx + (t3_jp - tc[jr][3]) * g.hy + (tc[jr][2] - t2_km) * g.hz;
+            if (active) {
+                const size_t uo = ((size_t)i * g.ny + (j0 + jr)) * (2 * (size_t)g.unzcs) + k;
+                u[uo] = f0;
+                u[g.uplane + uo] = f1;
+                u[2 * g.uplane + uo] = f2;
+            }
+            t0_prev[jr] = tc[jr][0];
+        }
+    }
+#undef ROW
+}
+
+template <int UPDATE, int NP>
+static int launch_march(fgb_ctx* ctx, const double* r, const double* p_old, double* p_new, const IsoPhases& M, double cgbeta, double beta,
+                        double gamma) {
+    const GridDev& g = ctx->g;
+    int threads = 256;
+    while (threads > 32 && threads / 2 >= g.nz) threads /= 2;
+    const int kchunks = (g.nz + threads - 1) / threads;
+    int SEG = 16;
+    if (g.lnx < SEG) SEG = g.lnx;
+    const int segs = (g.lnx + SEG - 1) / SEG;
+    if (g.ny % 4 == 0) {
+        dim3 grid(g.ny / 4, segs, kchunks);
+        k_dsd_march<UPDATE, NP, 4><<<grid, threads, 0, ctx->stream>>>(r, p_old, p_new, ctx->ubuf, g, M, cgbeta, beta, gamma, SEG);
+    } else if (g.ny % 2 == 0) {
+        dim3 grid(g.ny / 2, segs, kchunks);
+        k_dsd_march<UPDATE, NP, 2><<<grid, threads, 0, ctx->stream>>>(r, p_old, p_new, ctx->ubuf, g, M, cgbeta, beta, gamma, SEG);
+    } else {
+        dim3 grid(g.ny, segs, kchunks);
+        k_dsd_march<UPDATE, NP, 1><<<grid, threads, 0, ctx->stream>>>(r, p_old, p_new, ctx->ubuf, g, M, cgbeta, beta, gamma, SEG);
+    }
+    FGB_CHECK_LAUNCH(ctx, "k_dsd_march");
+    return FGB_OK;
+}
+
 // eta = E + sym-grad_h u (elasticity), and sum_voxels p:(p - eta) with Voigt weights
 __global__ void __launch_bounds__(256) k_eps_dot6(const double* __restrict__ u, double* __restrict__ eta, const double* __restrict__ p,
                                                   GridDev g, Const9f E, double* __restrict__ partials) {
@@ -233,6 +413,13 @@ int fgb_k_dir_stress_div_iso(fgb_ctx* ctx, const double* r, double cgbeta, const
     int threads = 256;
     while (threads > 32 && threads / 2 >= g.nz) threads /= 2;
     ProfScope ps(ctx, r ? "cg_direction_stress_div" : "stress_div");
+    if (ctx->nphases <= 3 && !getenv("FGB_NO_MARCH")) {
+        switch (ctx->nphases) {
+            case 1: return r ? launch_march<1, 1>(ctx, r, p_old, p_new, M, cgbeta, beta, gamma) : launch_march<0, 1>(ctx, nullptr, p_old, nullptr, M, 0.0, beta, gamma);
+            case 2: return r ? launch_march<1, 2>(ctx, r, p_old, p_new, M, cgbeta, beta, gamma) : launch_march<0, 2>(ctx, nullptr, p_old, nullptr, M, 0.0, beta, gamma);
+            case 3: return r ? launch_march<1, 3>(ctx, r, p_old, p_new, M, cgbeta, beta, gamma) : launch_march<0, 3>(ctx, nullptr, p_old, nullptr, M, 0.0, beta, gamma);
+        }
+    }
     if (r) k_dir_stress_div_iso<1><<<grid, threads, 0, ctx->stream>>>(r, p_old, p_new, ctx->ubuf, g, M, cgbeta, beta, gamma, JB);
     else k_dir_stress_div_iso<0><<<grid, threads, 0, ctx->stream>>>(nullptr, p_old, nullptr, ctx->ubuf, g, M, 0.0, beta, gamma, JB);
     FGB_CHECK_LAUNCH(ctx, "k_dir_stress_div_iso");
