@@ -7,7 +7,8 @@
 A "step" is one CG iteration (runCGElasticity hot loop, fg:23206-23246) = one pass of the hot path
 (material law -> div -> 3-D FFT -> G0 -> inverse FFT -> sym-grad -> dots -> vector updates) over the grid.
 Workload at N=1: BASELINE config 2 -- 256^3 short-fibre composite, linear elasticity, CG, staggered grid,
-Voigt mixing, residual estimator.  N>1: the same per-GPU slab (weak scaling): (256*N) x 256 x 256, x-slabs.
+Voigt mixing, residual estimator.  N>1: weak scaling, 256^3 voxels per GPU, global grid 256x512x256 / 256x512x512 /
+512x512x512 for N = 2 / 4 / 8 (periodic tiling of the same cell), x-slab partition.
 Timing: CUDA events on the launching stream, W warm-up iterations, K timed, barrier + synchronize on both
 sides, max over ranks.  Inputs (3.5 GB of fields) are far larger than the 126 MB L2, so no explicit flush.
 """
@@ -127,14 +128,21 @@ def run_cuda(args):
         dist = dist_
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     base = args.grid
-    n = (base * world, base, base)
+    # weak scaling: every rank owns base^3 voxels; the global grid grows along y, z and x in turn so that no axis exceeds
+    # 2*base (x-slabs of nx/P planes; nx and ny must be divisible by P)
+    mult = {1: (1, 1, 1), 2: (1, 2, 1), 4: (1, 2, 2), 8: (2, 2, 2)}.get(world, (world, 1, 1))
+    if base * mult[0] % world or base * mult[1] % world:
+        mult = (world, 1, 1)
+    n = (base * mult[0], base * mult[1], base * mult[2])
     nxyz = n[0] * n[1] * n[2]
     K, W = args.steps, max(args.warmup, 3)
 
     phi_cell, nfib = microstructure((base, base, base))
     lnx = n[0] // world
-    # every rank owns one periodic copy of the cell (weak scaling, x-slabs)
-    phi_local = phi_cell
+    # the global microstructure is the periodic tiling of the cell; this rank's x-slab of it
+    x0 = rank * lnx
+    reps = (mult[0], mult[1], mult[2])
+    phi_local = np.tile(phi_cell, reps)[x0:x0 + lnx]
     vf = float(phi_cell.mean())
     lam_m, mu_m = lame(E_M, NU_M)
     lam_f, mu_f = lame(E_F, NU_F)

@@ -133,7 +133,7 @@ extern "C" int fgb_create(fgb_ctx** out, int nx, int ny, int nz, double Lx, doub
     for (int a = 0; a < 3; a++) { c->tw_dev[a] = nullptr; c->kpm_dev[a] = nullptr; c->kp_dev[a] = nullptr; c->xi_dev[a] = nullptr; }
     c->d_partials = nullptr; c->d_result = nullptr; c->h_result = nullptr; c->d_scalars = nullptr; c->d_flag = nullptr; c->h_flag = nullptr;
     c->nccl_comm = nullptr; c->nccl_lib = nullptr; c->sbuf = nullptr; c->xbuf = nullptr; c->xbuf_comps = 0; c->xbuf_nzcs = 0;
-    c->halo = nullptr; c->halo_slot = 0; c->d_gather = nullptr; c->visc_tmp = nullptr; c->p2p = false;
+    c->halo = nullptr; c->halo_slot = 0; c->d_gather = nullptr; c->visc_tmp = nullptr; c->p2p = false; c->iso_halo = nullptr; c->phi_halo_valid = false;
     c->launches = 0; c->profiling = false;
     c->bc_active = false; c->bc_relax = 1.0;
     for (int i = 0; i < 81; i++) c->bc_MQ[i] = c->bc_MQC0[i] = 0;
@@ -292,6 +292,7 @@ extern "C" int fgb_set_phase(fgb_ctx* c, int p, const double* phi) {
     CHECK_CTX(c);
     if (p < 0 || p >= c->nphases) return fgb_fail(c, FGB_EINVAL, "phase index %d out of range", p);
     const double* comps[1] = {phi};
+    c->phi_halo_valid = false;
     return upload_planes(c, &c->phi[p], comps, 1);
 }
 
@@ -608,8 +609,10 @@ extern "C" int fgb_basic_step(fgb_ctx* c, int src, int dst, const double* E, dou
     if (c->bc_relax != 1.0 && (rc = fgb_k_component_dot(c, c->fields[src], nullptr, c->F00, 1))) return rc;   // fg:20563-20565
     if (fgb_fused_iso_applicable(c) && !c->bc_active && c->bc_relax == 1.0) {
         // fused: (C-C0):eps and div_h in one sweep, tau never written (calcStressDiff fg:18030 + divOperatorStaggered fg:18853)
+        if (c->nranks > 1 && (rc = fgb_comm_halo_iso(c, nullptr, c->fields[src]))) return rc;
         if ((rc = fgb_k_dir_stress_div_iso(c, nullptr, 0.0, c->fields[src], nullptr, mu0, lambda0, 1.0))) return rc;
         if ((rc = g0_staggered(c, mu0, lambda0, -1.0))) return rc;
+        if (c->nranks > 1 && (rc = fgb_comm_halo_u(c))) return rc;
         return fgb_k_eps(c, c->ubuf, c->fields[dst], E);
     }
     if ((rc = fgb_k_calc_stress(c, c->fields[src], c->fields[dst], mu0, lambda0, 1.0))) return rc;            // calcStressDiff fg:18030
@@ -668,8 +671,10 @@ extern "C" int fgb_cg_step(fgb_ctx* c, int F, int r, double beta, int p_old, int
     int rc;
     if (F < 0 && fgb_fused_iso_applicable(c) && !c->bc_active && c->bc_relax == 1.0 && (r < 0 || p_old != p_new)) {
         double zero[9] = {0};
+        if (c->nranks > 1 && (rc = fgb_comm_halo_iso(c, r >= 0 ? c->fields[r] : nullptr, c->fields[p_old]))) return rc;
         if ((rc = fgb_k_dir_stress_div_iso(c, r >= 0 ? c->fields[r] : nullptr, beta, c->fields[p_old], c->fields[p_new], mu0, lambda0, 1.0))) return rc;
         if ((rc = g0_staggered(c, mu0, lambda0, -1.0))) return rc;
+        if (c->nranks > 1 && (rc = fgb_comm_halo_u(c))) return rc;
         if (pAp) return fgb_k_eps_dot(c, c->ubuf, c->fields[w], zero, c->fields[p_new], pAp);
         return fgb_k_eps(c, c->ubuf, c->fields[w], zero);
     }

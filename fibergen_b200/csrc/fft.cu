@@ -613,7 +613,7 @@ static int launch_x_green(fgb_ctx* ctx, double2* base, const GreenDev& G, long e
     int rc = -1;
     // register budget: NC*R2 complex per thread -> the fast path covers NC <= 3 (staggered / heat); larger tensors use the generic kernel
     if constexpr (NC == 3 && KIND == 1) {
-        if (!getenv("FGB_XG_V1")) {
+        if (getenv("FGB_XG_V2")) {
             switch (nx) {
                 case 64: rc = launch_xg_p2c<64, 8, 8, 8>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt); break;
                 case 128: rc = launch_xg_p2c<128, 16, 8, 8>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt); break;
@@ -628,7 +628,13 @@ static int launch_x_green(fgb_ctx* ctx, double2* base, const GreenDev& G, long e
         switch (nx) {
             case 64: rc = launch_xg_p2<64, 8, 8, NC, KIND, 8>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt); break;
             case 128: rc = launch_xg_p2<128, 16, 8, NC, KIND, 8>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt); break;
-            case 256: rc = launch_xg_p2<256, 16, 16, NC, KIND, 8>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt); break;
+            case 256: {
+                const char* tsel = getenv("FGB_XG_T");
+                const int tt = tsel ? atoi(tsel) : 8;
+                if (tt == 16) rc = launch_xg_p2<256, 16, 16, NC, KIND, 16>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt);
+                else if (tt == 4) rc = launch_xg_p2<256, 16, 16, NC, KIND, 4>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt);
+                else rc = launch_xg_p2<256, 16, 16, NC, KIND, 8>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt);
+            } break;
             case 512: rc = launch_xg_p2<512, 32, 16, NC, KIND, 4>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt); break;
             case 1024: if constexpr (NC == 1) rc = launch_xg_p2<1024, 32, 32, NC, KIND, 2>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt); break;
         }

@@ -102,6 +102,8 @@ struct fgb_ctx {
     double* halo;               // [3 lo slots][3 hi slots] of halo_slot doubles (neighbour x planes for the stencils)
     size_t halo_slot;
     double* d_gather;           // rank-ordered reduction staging
+    double* iso_halo;           // fused isotropic sweep: [r_lo 3][p_lo 3][r_hi 2][p_hi 2][phi_lo P][phi_hi P] planes of ny*nzp doubles
+    bool phi_halo_valid;
     bool p2p;                   // peer buffers mapped: transposes are written by the FFT kernels straight into peer memory
     double* peer_xbuf[8];       // xbuf of every rank (own pointer at [rank])
     double* peer_sbuf[8];
@@ -228,6 +230,9 @@ int fgb_k_eps_dot(fgb_ctx* ctx, const double* u, double* eta, const double* Econ
 
 // comm.cu ------------------------------------------------------------------------------------
 int fgb_comm_free(fgb_ctx* ctx);
+// neighbour planes for the fused isotropic sweep: r/p components 0,1,2 of the left neighbour's last plane, components 5,4 of the
+// right neighbour's first plane, and (once) the phase fractions of both planes; r may be null
+int fgb_comm_halo_iso(fgb_ctx* ctx, const double* r, const double* p_old);
 // slab-partitioned x pass: transpose -> fwd x, Green, inv x -> transpose back
 int fgb_comm_fft_x(fgb_ctx* ctx, double* base, int ncomp, const FftLayout& lay, const GreenArgs* ga);
 int fgb_comm_halo_tau(fgb_ctx* ctx, const double* tau);   // fills ctx->halo for k_div

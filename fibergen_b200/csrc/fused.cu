@@ -208,7 +208,10 @@ __device__ __forceinline__ void diag_from(const IsoPhases& M, const double* phi,
 template <int UPDATE, int NP, int BJ>
 __global__ void __launch_bounds__(256) k_dsd_march(const double* __restrict__ r, const double* __restrict__ p_old, double* __restrict__ p_new,
                                                    double* __restrict__ u, GridDev g, IsoPhases M, double cgbeta, double beta, double gamma,
-                                                   int SEG) {
+                                                   int SEG, const double* __restrict__ halo) {
+    // halo != null (slab partition): planes i = -1 and i = lnx come from the neighbour ranks, layout
+    // [r_lo 3][p_lo 3][r_hi 2][p_hi 2][phi_lo MAXP][phi_hi MAXP], each ny*nzp doubles (comm.cu: fgb_comm_halo_iso)
+    const size_t pe = (size_t)g.ny * g.nzp;
     const int j0 = blockIdx.x * BJ;
     const int i0 = blockIdx.y * SEG;
     const int i1 = min(i0 + SEG, g.lnx);
@@ -228,13 +231,22 @@ __global__ void __launch_bounds__(256) k_dsd_march(const double* __restrict__ r,
     // warm-up: tau_0 of plane i0-1, and tau_5 / tau_4 / phi of plane i0
     {
         const int im = (i0 == 0) ? g.lnx - 1 : i0 - 1;
+        const bool from_halo = (halo != nullptr) && (i0 == 0);
 #pragma unroll
         for (int jr = 0; jr < BJ; jr++) {
             double ph[NP], d1, d2;
             size_t o = ROW(im, j0 + jr) + kc;
-            phi_load<NP>(M, o, ph);
-            diag_from<NP>(M, ph, pval<UPDATE>(r, p_old, o, cgbeta), pval<UPDATE>(r, p_old, P + o, cgbeta),
-                          pval<UPDATE>(r, p_old, 2 * P + o, cgbeta), beta, gamma, t0_prev[jr], d1, d2);
+            if (from_halo) {
+                const size_t oh = (size_t)(j0 + jr) * g.nzp + kc;
+#pragma unroll
+                for (int q = 0; q < NP; q++) ph[q] = __ldg(halo + (10 + q) * pe + oh);
+                diag_from<NP>(M, ph, pval<UPDATE>(halo, halo + 3 * pe, oh, cgbeta), pval<UPDATE>(halo + pe, halo + 4 * pe, oh, cgbeta),
+                              pval<UPDATE>(halo + 2 * pe, halo + 5 * pe, oh, cgbeta), beta, gamma, t0_prev[jr], d1, d2);
+            } else {
+                phi_load<NP>(M, o, ph);
+                diag_from<NP>(M, ph, pval<UPDATE>(r, p_old, o, cgbeta), pval<UPDATE>(r, p_old, P + o, cgbeta),
+                              pval<UPDATE>(r, p_old, 2 * P + o, cgbeta), beta, gamma, t0_prev[jr], d1, d2);
+            }
             o = ROW(i0, j0 + jr) + kc;
             phi_load<NP>(M, o, phin[jr]);
             const double e5 = pval<UPDATE>(r, p_old, 5 * P + o, cgbeta), e4 = pval<UPDATE>(r, p_old, 4 * P + o, cgbeta);
@@ -275,8 +287,18 @@ __global__ void __launch_bounds__(256) k_dsd_march(const double* __restrict__ r,
 #pragma unroll
         for (int jr = 0; jr < BJ; jr++) {
             const size_t o = ROW(ip, j0 + jr) + kc;
-            phi_load<NP>(M, o, phin[jr]);
-            const double e5 = pval<UPDATE>(r, p_old, 5 * P + o, cgbeta), e4 = pval<UPDATE>(r, p_old, 4 * P + o, cgbeta);
+            double e5, e4;
+            if (halo != nullptr && i + 1 == g.lnx) {
+                const size_t oh = (size_t)(j0 + jr) * g.nzp + kc;
+#pragma unroll
+                for (int q = 0; q < NP; q++) phin[jr][q] = __ldg(halo + (10 + FGB_MAX_PHASES + q) * pe + oh);
+                e5 = pval<UPDATE>(halo + 6 * pe, halo + 8 * pe, oh, cgbeta);
+                e4 = pval<UPDATE>(halo + 7 * pe, halo + 9 * pe, oh, cgbeta);
+            } else {
+                phi_load<NP>(M, o, phin[jr]);
+                e5 = pval<UPDATE>(r, p_old, 5 * P + o, cgbeta);
+                e4 = pval<UPDATE>(r, p_old, 4 * P + o, cgbeta);
+            }
             if (UPDATE && active && (i + 1 < i1)) { p_new[5 * P + o] = e5; p_new[4 * P + o] = e4; }
             t5n[jr] = shear_from<NP>(M, phin[jr], e5, beta);
             t4n[jr] = shear_from<NP>(M, phin[jr], e4, beta);
@@ -324,6 +346,7 @@ template <int UPDATE, int NP>
 static int launch_march(fgb_ctx* ctx, const double* r, const double* p_old, double* p_new, const IsoPhases& M, double cgbeta, double beta,
                         double gamma) {
     const GridDev& g = ctx->g;
+    const double* halo = (ctx->nranks > 1) ? ctx->iso_halo : nullptr;
     int threads = 256;
     while (threads > 32 && threads / 2 >= g.nz) threads /= 2;
     const int kchunks = (g.nz + threads - 1) / threads;
@@ -332,13 +355,13 @@ static int launch_march(fgb_ctx* ctx, const double* r, const double* p_old, doub
     const int segs = (g.lnx + SEG - 1) / SEG;
     if (g.ny % 4 == 0) {
         dim3 grid(g.ny / 4, segs, kchunks);
-        k_dsd_march<UPDATE, NP, 4><<<grid, threads, 0, ctx->stream>>>(r, p_old, p_new, ctx->ubuf, g, M, cgbeta, beta, gamma, SEG);
+        k_dsd_march<UPDATE, NP, 4><<<grid, threads, 0, ctx->stream>>>(r, p_old, p_new, ctx->ubuf, g, M, cgbeta, beta, gamma, SEG, halo);
     } else if (g.ny % 2 == 0) {
         dim3 grid(g.ny / 2, segs, kchunks);
-        k_dsd_march<UPDATE, NP, 2><<<grid, threads, 0, ctx->stream>>>(r, p_old, p_new, ctx->ubuf, g, M, cgbeta, beta, gamma, SEG);
+        k_dsd_march<UPDATE, NP, 2><<<grid, threads, 0, ctx->stream>>>(r, p_old, p_new, ctx->ubuf, g, M, cgbeta, beta, gamma, SEG, halo);
     } else {
         dim3 grid(g.ny, segs, kchunks);
-        k_dsd_march<UPDATE, NP, 1><<<grid, threads, 0, ctx->stream>>>(r, p_old, p_new, ctx->ubuf, g, M, cgbeta, beta, gamma, SEG);
+        k_dsd_march<UPDATE, NP, 1><<<grid, threads, 0, ctx->stream>>>(r, p_old, p_new, ctx->ubuf, g, M, cgbeta, beta, gamma, SEG, halo);
     }
     FGB_CHECK_LAUNCH(ctx, "k_dsd_march");
     return FGB_OK;
@@ -346,7 +369,8 @@ static int launch_march(fgb_ctx* ctx, const double* r, const double* p_old, doub
 
 // eta = E + sym-grad_h u (elasticity), and sum_voxels p:(p - eta) with Voigt weights
 __global__ void __launch_bounds__(256) k_eps_dot6(const double* __restrict__ u, double* __restrict__ eta, const double* __restrict__ p,
-                                                  GridDev g, Const9f E, double* __restrict__ partials) {
+                                                  GridDev g, Const9f E, double* __restrict__ partials, const double* __restrict__ halo_lo,
+                                                  const double* __restrict__ halo_hi, size_t hslot) {
     const unsigned nvox = (unsigned)g.lnx * (unsigned)g.ny * (unsigned)g.nz;
     const size_t us = 2 * (size_t)g.unzcs;
     double acc = 0;
@@ -366,13 +390,21 @@ __global__ void __launch_bounds__(256) k_eps_dot6(const double* __restrict__ u, 
         const double* u1p = u + g.uplane;
         const double* u2p = u + 2 * g.uplane;
         const double u0 = u0p[o], u1 = u1p[o], u2 = u2p[o];
+        // slab partition: planes i-1 / i+1 outside the slab come from the halo slots (comm.cu: fgb_comm_halo_u)
+        const size_t oh = (size_t)j * us + k;
+        const bool lo_h = halo_lo != nullptr && i == 0, hi_h = halo_hi != nullptr && i + 1 == g.lnx;
+        const double u0_ip = hi_h ? halo_hi[oh] : u0p[o_ip];
+        const double u0_im = lo_h ? halo_lo[oh] : u0p[o_im];
+        const double u1_im = lo_h ? halo_lo[hslot + oh] : u1p[o_im];
+        const double u2_im = lo_h ? halo_lo[2 * hslot + oh] : u2p[o_im];
+        (void)u0_im;
         double e[6];
-        e[0] = E.v[0] + (u0p[o_ip] - u0) * g.hx;
+        e[0] = E.v[0] + (u0_ip - u0) * g.hx;
         e[1] = E.v[1] + (u1p[o_jp] - u1) * g.hy;
         e[2] = E.v[2] + (u2p[o_kp] - u2) * g.hz;
         e[3] = E.v[3] + 0.5 * ((u2 - u2p[o_jm]) * g.hy + (u1 - u1p[o_km]) * g.hz);
-        e[4] = E.v[4] + 0.5 * ((u2 - u2p[o_im]) * g.hx + (u0 - u0p[o_km]) * g.hz);
-        e[5] = E.v[5] + 0.5 * ((u1 - u1p[o_im]) * g.hx + (u0 - u0p[o_jm]) * g.hy);
+        e[4] = E.v[4] + 0.5 * ((u2 - u2_im) * g.hx + (u0 - u0p[o_km]) * g.hz);
+        e[5] = E.v[5] + 0.5 * ((u1 - u1_im) * g.hx + (u0 - u0p[o_jm]) * g.hy);
         const size_t eo = (size_t)row_ * g.nzp + k;
         double s = 0;
 #pragma unroll
@@ -391,7 +423,8 @@ __global__ void __launch_bounds__(256) k_eps_dot6(const double* __restrict__ u, 
 // returns 1 if the fused path applies to this context (D = 6 elasticity, staggered, Voigt, all phases isotropic, one rank)
 int fgb_fused_iso_applicable(const fgb_ctx* ctx) {
     if (ctx->dim != 6 || ctx->mode != FGB_MODE_ELASTICITY || ctx->scheme != FGB_GAMMA_STAGGERED) return 0;
-    if (ctx->mix != FGB_MIX_VOIGT || ctx->nranks != 1 || ctx->nphases < 1) return 0;
+    if (ctx->mix != FGB_MIX_VOIGT || ctx->nphases < 1) return 0;
+    if (ctx->nranks > 1 && (ctx->nphases > 3 || !ctx->nccl_comm || getenv("FGB_NO_MARCH"))) return 0;   // slab runs need the marching kernel
     for (int p = 0; p < ctx->nphases; p++)
         if (ctx->laws[p].id != FGB_LAW_ISO || !ctx->phi[p]) return 0;
     return 1;
@@ -436,7 +469,9 @@ int fgb_k_eps_dot(fgb_ctx* ctx, const double* u, double* eta, const double* Econ
     const unsigned grid = (unsigned)b;
     {
         ProfScope ps(ctx, "eps_dot");
-        k_eps_dot6<<<grid, 256, 0, ctx->stream>>>(u, eta, p, g, E, ctx->d_partials);
+        const double* lo = (ctx->nranks > 1) ? ctx->halo : nullptr;
+        const double* hi = (ctx->nranks > 1) ? ctx->halo + 3 * ctx->halo_slot : nullptr;
+        k_eps_dot6<<<grid, 256, 0, ctx->stream>>>(u, eta, p, g, E, ctx->d_partials, lo, hi, ctx->halo_slot);
         FGB_CHECK_LAUNCH(ctx, "k_eps_dot6");
     }
     int rc = fgb_reduce_finish(ctx, grid, 1, 0, pAp);
