@@ -126,8 +126,9 @@ __global__ void __launch_bounds__(Max<R1, R2>::v* T) k_ffts_p2(const double2* __
                                                                const double2* __restrict__ tw, PencilMap mi, PencilMap mo, int ninner,
                                                                PeerTable pt) {
     constexpr int TPP = Max<R1, R2>::v;
-    __shared__ double2 tw_s[N];
-    __shared__ double2 X[N * T];
+    extern __shared__ double2 smem_s[];
+    double2* tw_s = smem_s;          // N
+    double2* X = smem_s + N;         // N * T
     const int tid = threadIdx.x;
     for (int i = tid; i < N; i += TPP * T) tw_s[i] = tw[i];
     const int t = tid % T, s = tid / T;
@@ -544,8 +545,14 @@ static void launch_s_p2(fgb_ctx* ctx, const double2* src, double2* dst, const do
                         int ninner, int nouter, int ncomp, int dir, const PeerTable& pt) {
     dim3 grid((ninner + T - 1) / T, nouter, ncomp);
     constexpr int NT = Max<R1, R2>::v * T;
-    if (dir < 0) k_ffts_p2<N, R1, R2, -1, T><<<grid, NT, 0, ctx->stream>>>(src, dst, tw, mi, mo, ninner, pt);
-    else k_ffts_p2<N, R1, R2, +1, T><<<grid, NT, 0, ctx->stream>>>(src, dst, tw, mi, mo, ninner, pt);
+    const size_t smem = sizeof(double2) * (size_t)(N + N * T);
+    if (dir < 0) {
+        set_smem(k_ffts_p2<N, R1, R2, -1, T>, smem);
+        k_ffts_p2<N, R1, R2, -1, T><<<grid, NT, smem, ctx->stream>>>(src, dst, tw, mi, mo, ninner, pt);
+    } else {
+        set_smem(k_ffts_p2<N, R1, R2, +1, T>, smem);
+        k_ffts_p2<N, R1, R2, +1, T><<<grid, NT, smem, ctx->stream>>>(src, dst, tw, mi, mo, ninner, pt);
+    }
 }
 
 int fgb_fft_strided(fgb_ctx* ctx, int axis, const double* src_, double* dst_, const PencilMap& mi, const PencilMap& mo, int ninner,
@@ -564,8 +571,8 @@ int fgb_fft_strided(fgb_ctx* ctx, int axis, const double* src_, double* dst_, co
             case 64: launch_s_p2<64, 8, 8, 8>(ctx, src, dst, tw, mi, mo, ninner, nouter, ncomp, dir, pt); break;
             case 128: launch_s_p2<128, 16, 8, 8>(ctx, src, dst, tw, mi, mo, ninner, nouter, ncomp, dir, pt); break;
             case 256: launch_s_p2<256, 16, 16, 8>(ctx, src, dst, tw, mi, mo, ninner, nouter, ncomp, dir, pt); break;
-            case 512: launch_s_p2<512, 32, 16, 4>(ctx, src, dst, tw, mi, mo, ninner, nouter, ncomp, dir, pt); break;
-            case 1024: launch_s_p2<1024, 32, 32, 2>(ctx, src, dst, tw, mi, mo, ninner, nouter, ncomp, dir, pt); break;
+            case 512: launch_s_p2<512, 32, 16, 8>(ctx, src, dst, tw, mi, mo, ninner, nouter, ncomp, dir, pt); break;
+            case 1024: launch_s_p2<1024, 32, 32, 4>(ctx, src, dst, tw, mi, mo, ninner, nouter, ncomp, dir, pt); break;
         }
         FGB_CHECK_LAUNCH(ctx, "k_ffts_p2");
         return FGB_OK;
