@@ -302,7 +302,8 @@ extern "C" int fgb_set_law(fgb_ctx* c, int p, int law_id, const double* params, 
     static const int need[8] = {2, 36, 5, 1, 6, 2, 2, 2};
     static const int ldim[8] = {6, 6, 6, 0, 3, 9, 9, 9};
     if (law_id < 0 || law_id > FGB_LAW_NH2) return fgb_fail(c, FGB_EUNSUPPORTED, "unknown material law id %d (fg:15285)", law_id);
-    if (nparams != need[law_id]) return fgb_fail(c, FGB_EINVAL, "law %d needs %d parameters, got %d", law_id, need[law_id], nparams);
+    if (nparams != need[law_id] && !(law_id == FGB_LAW_TISO && nparams == 8))
+        return fgb_fail(c, FGB_EINVAL, "law %d needs %d parameters, got %d", law_id, need[law_id], nparams);
     if (ldim[law_id] && ldim[law_id] != c->dim)
         return fgb_fail(c, FGB_EINVAL, "law %d acts on %d components but mode has %d (fg:15211-15294)", law_id, ldim[law_id], c->dim);
     if (law_id == FGB_LAW_SCALAR && c->dim == 9) return fgb_fail(c, FGB_EINVAL, "scalar law is not defined for hyperelasticity");

@@ -292,7 +292,8 @@ static int check_material(fgb_ctx* ctx) {
         if (!ctx->phi[p]) return fgb_fail(ctx, FGB_EINVAL, "phase %d has no volume fraction field", p);
     if (ctx->mix == FGB_MIX_LAMINATE && !ctx->normals) return fgb_fail(ctx, FGB_EINVAL, "laminate mixing needs normals");
     for (int p = 0; p < ctx->nphases; p++)
-        if (ctx->laws[p].id == FGB_LAW_TISO && !ctx->orient) return fgb_fail(ctx, FGB_EINVAL, "tiso law needs the orientation field");
+        if (ctx->laws[p].id == FGB_LAW_TISO && !ctx->orient && ctx->laws[p].p[5] == 0 && ctx->laws[p].p[6] == 0 && ctx->laws[p].p[7] == 0)
+            return fgb_fail(ctx, FGB_EINVAL, "tiso law needs the orientation field or a constant axis");
     return FGB_OK;
 }
 

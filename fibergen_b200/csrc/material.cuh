@@ -132,7 +132,8 @@ __device__ __forceinline__ void nh_products(const double* Finv, const double* W,
 #define ACC(dst, val) dst = gamma ? (dst + (val)) : (val)
 
 struct LawCtx {
-    const double* orient;   // 3 doubles (transversely isotropic axis) or null
+    const double* orient;   // 3 doubles (transversely isotropic axis at this voxel) or null
+    const double* orient0;  // axis at voxel 0: LinearTransverselyIsotropic::dPK1 passes index m = 0 (fg:11582), kept for parity
     int* flag;
 };
 
@@ -164,7 +165,9 @@ __device__ __forceinline__ void law_PK1(const LawDev& L, const LawCtx& lc, const
         case FGB_LAW_TISO: {                                           // fg:11532-11570
             if (D >= 6) {
                 const double two_mu = L.p[0], lam = L.p[1], al = L.p[2], be = L.p[3], two_dmu = L.p[4];
-                const double a0 = lc.orient[0], a1 = lc.orient[1], a2 = lc.orient[2];
+                // constant axis (have_a, fg:11516) in p[5..7] if non-zero, else the orientation field
+                const bool have_a = (L.p[5] != 0 || L.p[6] != 0 || L.p[7] != 0);
+                const double a0 = have_a ? L.p[5] : lc.orient[0], a1 = have_a ? L.p[6] : lc.orient[1], a2 = have_a ? L.p[7] : lc.orient[2];
                 const double A[6] = {a0 * a0, a1 * a1, a2 * a2, a1 * a2, a0 * a2, a0 * a1};
                 const double tr = F[0] + F[1] + F[2];
                 const double aea = A[0] * F[0] + A[1] * F[1] + A[2] * F[2] + 2 * (A[3] * F[3] + A[4] * F[4] + A[5] * F[5]);
@@ -247,9 +250,13 @@ template <int D>
 __device__ __forceinline__ void law_dPK1(const LawDev& L, const LawCtx& lc, const double* F, double alpha, bool gamma, const double* W,
                                          double* dP) {
     switch (L.id) {
+        case FGB_LAW_TISO: {
+            LawCtx l0 = lc;
+            l0.orient = lc.orient0;                                    // quirk fg:11582
+            law_PK1<D>(L, l0, W, alpha, gamma, dP);
+        } break;
         case FGB_LAW_ISO:
         case FGB_LAW_GENERAL:
-        case FGB_LAW_TISO:
         case FGB_LAW_SCALAR:
         case FGB_LAW_ANISO3:
             law_PK1<D>(L, lc, W, alpha, gamma, dP);                     // linear laws: tangent action == law
@@ -473,16 +480,19 @@ struct Mixed {
         LawCtx lc;
         lc.flag = flag;
         lc.orient = nullptr;
+        lc.orient0 = nullptr;
         if (M.orient[0]) {
             abuf[0] = M.orient[0][o]; abuf[1] = M.orient[1][o]; abuf[2] = M.orient[2][o];
+            abuf[3] = M.orient[0][0]; abuf[4] = M.orient[1][0]; abuf[5] = M.orient[2][0];
             lc.orient = abuf;
+            lc.orient0 = abuf + 3;
         }
         return lc;
     }
 
     // P = alpha * P_mix(F)
     __device__ static void PK1(const MaterialDev& M, size_t o, const double* F, double alpha, double* P, int* flag) {
-        double abuf[3];
+        double abuf[6];
         const LawCtx lc = make_ctx(M, o, abuf, flag);
         if (M.mix == FGB_MIX_VOIGT) {                                  // fg:12752-12761
             bool gamma = false;
@@ -502,7 +512,7 @@ struct Mixed {
 
     // dP = alpha * dP_mix/dF(F) : W
     __device__ static void dPK1(const MaterialDev& M, size_t o, const double* F, double alpha, const double* W, double* dP, int* flag) {
-        double abuf[3];
+        double abuf[6];
         const LawCtx lc = make_ctx(M, o, abuf, flag);
         if (M.mix == FGB_MIX_VOIGT) {                                  // fg:12763-12771
             bool gamma = false;
@@ -521,7 +531,7 @@ struct Mixed {
     }
 
     __device__ static double W(const MaterialDev& M, size_t o, const double* F, int* flag) {
-        double abuf[3];
+        double abuf[6];
         const LawCtx lc = make_ctx(M, o, abuf, flag);
         double Fx[9];
 #pragma unroll

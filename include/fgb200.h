@@ -54,7 +54,7 @@ typedef struct fgb_ctx fgb_ctx;
 /* material laws (fg:15211-15294) with their parameter vectors */
 #define FGB_LAW_ISO      0  /* LinearIsotropicMaterialLaw fg:11354           params: mu, lambda            */
 #define FGB_LAW_GENERAL  1  /* LinearGeneralMaterialLaw fg:11233             params: C[36] row-major       */
-#define FGB_LAW_TISO     2  /* LinearTransverselyIsotropic fg:11479          params: 2mu, lambda, alpha, beta, 2dmu */
+#define FGB_LAW_TISO     2  /* LinearTransverselyIsotropic fg:11479          params: 2mu, lambda, alpha, beta, 2dmu [, ax, ay, az] */
 #define FGB_LAW_SCALAR   3  /* ScalarLinearIsotropicMaterialLaw fg:11161     params: mu                    */
 #define FGB_LAW_ANISO3   4  /* MatrixLinearAnisotropicMaterialLaw fg:11089   params: c11,c22,c33,c23,c13,c12 */
 #define FGB_LAW_SVK      5  /* SaintVenantKirchhoffMaterialLaw fg:11598      params: mu, lambda            */

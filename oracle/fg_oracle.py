@@ -205,37 +205,50 @@ class LinearGeneral(Law):
 
 
 class LinearTransverselyIsotropic(Law):
-    """fg:11479-11595.  ``a`` = per-voxel orientation (3,...) supplied at call time."""
+    """fg:11479-11595.  Direction of anisotropy: the constant ``a`` if given (have_a, fg:11516), else the per-voxel
+    orientation field.  Quirk kept for parity: dPK1 passes the loop index m (= 0) instead of the voxel
+    index to PK1 (fg:11582), so tangents read the orientation of voxel 0."""
     dim = 6
 
-    def __init__(self, two_mu, lam, alpha_t, beta_t, two_dmu):
+    def __init__(self, two_mu, lam, alpha_t, beta_t, two_dmu, a=None):
         self.two_mu, self.lam, self.alpha_t, self.beta_t, self.two_dmu = map(float, (two_mu, lam, alpha_t, beta_t, two_dmu))
+        self.a = None if a is None or not np.any(np.asarray(a) != 0) else np.asarray(a, dtype=float)
         self.orientation = None   # (3,nx,ny,nz), set by solver
+        self.sel = None
 
     def _apply(self, E, alpha, a):
         # A = a (x) a ; P = 2 mu e + (lam tr e + alpha_t a'ea) I + (alpha_t tr e + beta_t a'ea) A + 2 dmu (Ae + eA)
         e = mat33_sym(E)
         A = a_outer(a)
         tr = E[0] + E[1] + E[2]
-        aea = np.einsum('...i,...ij,...j->...', np.moveaxis(a, 0, -1), e, np.moveaxis(a, 0, -1))
+        av = np.moveaxis(a, 0, -1)
+        aea = np.einsum('...i,...ij,...j->...', av, e, av)
         I = np.eye(3)
-        P = (self.two_mu * e + (self.lam * tr + self.alpha_t * aea)[..., None, None] * I
-             + (self.alpha_t * tr + self.beta_t * aea)[..., None, None] * A
-             + self.two_dmu * (A @ e + e @ A))
-        P = P * np.asarray(alpha)[..., None, None] if np.ndim(alpha) else P * alpha
+        al = np.asarray(alpha, dtype=float)
+        ex = (lambda x: x[..., None, None]) if (al.ndim or np.ndim(tr)) else (lambda x: x)
+        c_I = al * (self.lam * tr + self.alpha_t * aea)
+        c_E = al * self.two_mu
+        c_A = al * (self.alpha_t * tr + self.beta_t * aea)
+        c_AE = al * self.two_dmu
+        bc = lambda x: ex(np.broadcast_to(x, np.shape(tr)))
+        P = bc(c_E) * e + bc(c_I) * I + bc(c_A) * A + bc(c_AE) * (A @ e + e @ A)
         return np.stack([P[..., ROW[i], COL[i]] for i in range(6)], axis=0)
 
+    def _axis(self, E, voxel0):
+        if self.a is not None:
+            return self.a.reshape((3,) + (1,) * (E.ndim - 1)) * np.ones((1,) + E.shape[1:])
+        o = self.orientation
+        if voxel0:
+            return o[:, 0, 0, 0].reshape((3,) + (1,) * (E.ndim - 1)) * np.ones((1,) + E.shape[1:])
+        if self.sel is not None:
+            o = o[:, self.sel]
+        return o.reshape((3,) + E.shape[1:])
+
     def PK1(self, E, alpha):
-        return self._apply(E, alpha, self.orientation_for(E))
+        return self._apply(E, alpha, self._axis(E, False))
 
     def dPK1(self, E, alpha, W):
-        return self._apply(W, alpha, self.orientation_for(W))
-
-    def orientation_for(self, E):
-        a = self.orientation
-        if a.shape[1:] != E.shape[1:]:
-            a = a.reshape((3,) + (1,) * (E.ndim - 1)) if a.ndim == 1 else a
-        return a
+        return self._apply(W, alpha, self._axis(W, True))
 
 
 def mat33_sym(E6):
@@ -332,6 +345,51 @@ class NeoHooke(Law):
         c_m = a * (self.mu - self.lam * np.log(J))
         c_mu = np.broadcast_to(c_mu, tr.shape)
         dP = ex(c_mu) * Wm + ex(c_tr) * FinvT + ex(np.broadcast_to(c_m, tr.shape)) * FinvTWTFinvT
+        return vec9(dP)
+
+
+class NeoHooke2(Law):
+    """fg:11867-11993: W = 1/2 [mu (J^-2/3 tr C - 3) + K (J-1)^2]"""
+    dim = 9
+    linear = False
+
+    def __init__(self, mu, K):
+        self.mu, self.K = float(mu), float(K)
+
+    def W(self, F):
+        J = np.linalg.det(mat33(F))
+        return 0.5 * (self.mu * (J ** (-2.0 / 3.0) * np.sum(F * F, axis=0) - 3) + self.K * (J - 1) ** 2)
+
+    def PK1(self, F, alpha):
+        Fm = mat33(F)
+        FinvT = np.swapaxes(np.linalg.inv(Fm), -1, -2)
+        trC = np.sum(F * F, axis=0)
+        J = np.linalg.det(Fm)
+        al = np.asarray(alpha, dtype=float)
+        muJ23 = al * self.mu * J ** (-2.0 / 3.0)
+        D = al * self.K * J * (J - 1) - muJ23 * (1.0 / 3.0) * trC
+        ex = (lambda x: np.broadcast_to(x, J.shape)[..., None, None])
+        return vec9(ex(muJ23) * Fm + ex(D) * FinvT)
+
+    def dPK1(self, F, alpha, W):
+        Fm, Wm = mat33(F), mat33(W)
+        Finv = np.linalg.inv(Fm)
+        FinvT = np.swapaxes(Finv, -1, -2)
+        J = np.linalg.det(Fm)
+        trC3 = (1.0 / 3.0) * np.sum(F * F, axis=0)
+        al = np.asarray(alpha, dtype=float)
+        a_muJ23 = al * self.mu * J ** (-2.0 / 3.0)
+        a_KJ = al * self.K * J
+        a_KJJ1 = a_KJ * (J - 1)
+        a_KJJ = a_KJ * (2 * J - 1)
+        A = FinvT @ np.swapaxes(Wm, -1, -2)
+        B = A @ FinvT
+        tr = np.trace(A, axis1=-2, axis2=-1)
+        FW23 = (2.0 / 3.0) * np.sum(F * W, axis=0)
+        FiTW = np.sum(FinvT * Wm, axis=(-1, -2))
+        ex = (lambda x: np.broadcast_to(x, J.shape)[..., None, None])
+        dP = ex(a_muJ23) * (ex(-2.0 / 3.0 * tr) * (Fm - ex(trC3) * FinvT) + Wm - ex(FW23) * FinvT + ex(trC3) * B) \
+            + ex(a_KJJ * FiTW) * FinvT - ex(a_KJJ1) * B
         return vec9(dP)
 
 
@@ -433,6 +491,8 @@ class VoigtMixed(MixedBase):
             use = phi > self.threshold
             if not use.any():
                 continue
+            if hasattr(ph.law, "sel"):
+                ph.law.sel = sel
             c = ph.law.PK1(F, phi * alpha)
             c = np.where(use, c, 0.0)
             P = c if P is None else P + c

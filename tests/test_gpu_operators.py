@@ -271,3 +271,61 @@ def test_pow2_fast_paths(n):
         ctx.gamma(f, E, 1.3, 0.4, -1.0, 0.0)
         assert relerr(ctx.download(f), o.GammaOperator(E, 1.3, 0.4, tau, -1.0, 0.0)) < 2e-12
         ctx.close()
+
+
+def test_general_tiso_and_neohooke2_laws():
+    """LinearGeneral fg:11233, LinearTransverselyIsotropic fg:11479 (orientation field, constant axis and the voxel-0 tangent
+    quirk fg:11582), NeoHooke2 fg:11867 against the oracle"""
+    n = (10, 8, 6)
+    rng = np.random.default_rng(21)
+    phi = sphere_phi(n, R=0.3, sub=2)
+    # --- elasticity: general + tiso
+    A = rng.standard_normal((6, 6))
+    Cg = A @ A.T + 6 * np.eye(6)
+    orient = rng.standard_normal((3,) + n)
+    orient /= np.sqrt((orient ** 2).sum(axis=0))
+    tparams = [2 * 1.3, 0.8, 0.4, 0.9, 2 * 0.5]
+    for axis in (None, (0.6, 0.0, 0.8)):
+        ctx = fb.Context(*n, mode="elasticity", gamma_scheme="staggered")
+        o = fo.LSSolver(*n, mode="elasticity", gamma_scheme="staggered")
+        tp = tparams + (list(axis) if axis else [0.0, 0.0, 0.0])
+        ctx.set_phases([1 - phi, phi], [("general", Cg.ravel()), ("tiso", tp)], orientation=orient)
+        o.add_phase("m", fo.LinearGeneral(Cg), 1 - phi)
+        o.add_phase("f", fo.LinearTransverselyIsotropic(*tparams, a=axis), phi)
+        o.set_orientation(orient)
+        eps, W = rng.standard_normal((6,) + n), rng.standard_normal((6,) + n)
+        fe, fw, fd = ctx.field(eps), ctx.field(W), ctx.field()
+        ctx.chk(ctx.lib.fgb_calc_stress(ctx.h, fe, fd, 1.1, 0.3, -1.0))
+        assert relerr(ctx.download(fd), o.calcStress(1.1, 0.3, eps, -1.0)) < 1e-12
+        ctx.chk(ctx.lib.fgb_calc_stress_deriv(ctx.h, fe, fw, fd, 1.1, 0.3, 1.0))
+        assert relerr(ctx.download(fd), o.calcStressDeriv(1.1, 0.3, eps, W, 1.0)) < 1e-12
+        assert relerr(ctx.mean_pk1(fe), o.calcMeanStress(eps)) < 1e-12
+        lmin, lmax = ctx.ref_material(fe)
+        _, olmin, olmax = o.getRefMaterial(eps, False, False)
+        assert abs(lmax - olmax) <= 1e-11 * abs(olmax) and abs(lmin - max(olmin, 0.0)) <= 1e-11 * abs(olmax)
+        ctx.close()
+    # --- hyperelasticity: Neo-Hooke variant 2 + Neo-Hooke
+    ctx = fb.Context(*n, mode="hyperelasticity", gamma_scheme="staggered")
+    o = fo.LSSolver(*n, mode="hyperelasticity", gamma_scheme="staggered")
+    ctx.set_phases([1 - phi, phi], [("nh2", [3.0, 7.0]), ("nh", [10.0, 20.0])])
+    o.add_phase("m", fo.NeoHooke2(3.0, 7.0), 1 - phi)
+    o.add_phase("f", fo.NeoHooke(10.0, 20.0), phi)
+    F = 0.05 * rng.standard_normal((9,) + n)
+    F[:3] += 1.0
+    W = rng.standard_normal((9,) + n)
+    fe, fw, fd = ctx.field(F), ctx.field(W), ctx.field()
+    ctx.chk(ctx.lib.fgb_calc_stress(ctx.h, fe, fd, 0.0, 0.0, 1.0))
+    assert relerr(ctx.download(fd), o.calcStress(0.0, 0.0, F, 1.0)) < 1e-12
+    ctx.chk(ctx.lib.fgb_calc_stress_deriv(ctx.h, fe, fw, fd, 2.0, 0.5, 1.0))
+    assert relerr(ctx.download(fd), o.calcStressDeriv(2.0, 0.5, F, W, 1.0)) < 1e-11
+    assert abs(ctx.mean_energy(fe) - o.calcMeanEnergy(F)) <= 1e-11 * abs(o.calcMeanEnergy(F))
+    ctx.chk(ctx.lib.fgb_check_numeric(ctx.h))
+    # a non-positive det F must be flagged, not silently propagated (fg:10293, fg:21202)
+    Fbad = F.copy()
+    Fbad[0, 0, 0, 0] = -1.0
+    ctx.upload(fe, Fbad)
+    ctx.chk(ctx.lib.fgb_calc_stress(ctx.h, fe, fd, 0.0, 0.0, 1.0))
+    with pytest.raises(fb.FgbError) as e:
+        ctx.chk(ctx.lib.fgb_check_numeric(ctx.h))
+    assert e.value.code == fb.lib.FGB_ENUMERIC
+    ctx.close()
