@@ -205,8 +205,8 @@ __device__ __forceinline__ void diag_from(const IsoPhases& M, const double* phi,
     if (gamma != 0) { t0 += gamma * tr; t1 += gamma * tr; t2 += gamma * tr; }
 }
 
-template <int UPDATE, int NP, int BJ>
-__global__ void __launch_bounds__(256) k_dsd_march(const double* __restrict__ r, const double* __restrict__ p_old, double* __restrict__ p_new,
+template <int UPDATE, int NP, int BJ, int HALO>
+__global__ void __launch_bounds__(256, 2) k_dsd_march(const double* __restrict__ r, const double* __restrict__ p_old, double* __restrict__ p_new,
                                                    double* __restrict__ u, GridDev g, IsoPhases M, double cgbeta, double beta, double gamma,
                                                    int SEG, const double* __restrict__ halo) {
     // halo != null (slab partition): planes i = -1 and i = lnx come from the neighbour ranks, layout
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(256) k_dsd_march(const double* __restrict__ r,
     // warm-up: tau_0 of plane i0-1, and tau_5 / tau_4 / phi of plane i0
     {
         const int im = (i0 == 0) ? g.lnx - 1 : i0 - 1;
-        const bool from_halo = (halo != nullptr) && (i0 == 0);
+        const bool from_halo = HALO && (i0 == 0);
 #pragma unroll
         for (int jr = 0; jr < BJ; jr++) {
             double ph[NP], d1, d2;
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(256) k_dsd_march(const double* __restrict__ r,
         for (int jr = 0; jr < BJ; jr++) {
             const size_t o = ROW(ip, j0 + jr) + kc;
             double e5, e4;
-            if (halo != nullptr && i + 1 == g.lnx) {
+            if (HALO && i + 1 == g.lnx) {
                 const size_t oh = (size_t)(j0 + jr) * g.nzp + kc;
 #pragma unroll
                 for (int q = 0; q < NP; q++) phin[jr][q] = __ldg(halo + (10 + FGB_MAX_PHASES + q) * pe + oh);
@@ -353,16 +353,16 @@ static int launch_march(fgb_ctx* ctx, const double* r, const double* p_old, doub
     int SEG = 16;
     if (g.lnx < SEG) SEG = g.lnx;
     const int segs = (g.lnx + SEG - 1) / SEG;
-    if (g.ny % 4 == 0) {
-        dim3 grid(g.ny / 4, segs, kchunks);
-        k_dsd_march<UPDATE, NP, 4><<<grid, threads, 0, ctx->stream>>>(r, p_old, p_new, ctx->ubuf, g, M, cgbeta, beta, gamma, SEG, halo);
-    } else if (g.ny % 2 == 0) {
-        dim3 grid(g.ny / 2, segs, kchunks);
-        k_dsd_march<UPDATE, NP, 2><<<grid, threads, 0, ctx->stream>>>(r, p_old, p_new, ctx->ubuf, g, M, cgbeta, beta, gamma, SEG, halo);
-    } else {
-        dim3 grid(g.ny, segs, kchunks);
-        k_dsd_march<UPDATE, NP, 1><<<grid, threads, 0, ctx->stream>>>(r, p_old, p_new, ctx->ubuf, g, M, cgbeta, beta, gamma, SEG, halo);
-    }
+#define LAUNCH_MARCH(BJ_)                                                                                                          \
+    do {                                                                                                                          \
+        dim3 grid(g.ny / BJ_, segs, kchunks);                                                                                     \
+        if (halo) k_dsd_march<UPDATE, NP, BJ_, 1><<<grid, threads, 0, ctx->stream>>>(r, p_old, p_new, ctx->ubuf, g, M, cgbeta, beta, gamma, SEG, halo); \
+        else k_dsd_march<UPDATE, NP, BJ_, 0><<<grid, threads, 0, ctx->stream>>>(r, p_old, p_new, ctx->ubuf, g, M, cgbeta, beta, gamma, SEG, halo);      \
+    } while (0)
+    if (g.ny % 4 == 0) LAUNCH_MARCH(4);
+    else if (g.ny % 2 == 0) LAUNCH_MARCH(2);
+    else LAUNCH_MARCH(1);
+#undef LAUNCH_MARCH
     FGB_CHECK_LAUNCH(ctx, "k_dsd_march");
     return FGB_OK;
 }
