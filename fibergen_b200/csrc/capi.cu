@@ -323,9 +323,8 @@ extern "C" int fgb_set_orientation(fgb_ctx* c, const double* const* comps3) {
 
 extern "C" int fgb_set_mixing(fgb_ctx* c, int rule, const double* lp, int n) {
     CHECK_CTX(c);
-    if (rule == FGB_MIX_REUSS) return fgb_fail(c, FGB_EUNSUPPORTED, "reuss mixing is not available on the device yet");
-    if (rule != FGB_MIX_VOIGT && rule != FGB_MIX_LAMINATE)
-        return fgb_fail(c, FGB_EUNSUPPORTED, "Unknown material mixing rule %d (voigt and laminate only)", rule);
+    if (rule != FGB_MIX_VOIGT && rule != FGB_MIX_LAMINATE && rule != FGB_MIX_REUSS)
+        return fgb_fail(c, FGB_EUNSUPPORTED, "Unknown material mixing rule %d (voigt, reuss and laminate only)", rule);
     c->mix = rule;
     if (lp) {
         if (n != 10) return fgb_fail(c, FGB_EINVAL, "laminate parameter vector must have 10 entries");
@@ -402,6 +401,7 @@ extern "C" int fgb_mean_pk1(fgb_ctx* c, int f, double alpha, double* out) {
 }
 extern "C" int fgb_mean_energy(fgb_ctx* c, int f, double* out) {
     CHECK_CTX(c); CHECK_FIELD(c, f);
+    if (c->mix == FGB_MIX_REUSS) return fgb_fail(c, FGB_EUNSUPPORTED, "Reuss MaterialLaw energy not implemented");   // fg:12660
     int rc = fgb_k_mean_energy(c, c->fields[f], out);
     return rc ? rc : poll_flag(c);
 }

@@ -446,9 +446,61 @@ __device__ void laminate_newton(const LawDev& L1, const LawDev& L2, const LawCtx
     }
 }
 
+// inverse of a D x D row-major matrix by Gauss-Jordan with partial pivoting (InvertMatrix fg:1143); A is destroyed
+template <int D>
+__device__ void invert_dense(double* A, double* R) {
+    for (int i = 0; i < D; i++)
+        for (int j = 0; j < D; j++) R[i * D + j] = (i == j) ? 1.0 : 0.0;
+    for (int c = 0; c < D; c++) {
+        int piv = c;
+        double best = fabs(A[c * D + c]);
+        for (int r = c + 1; r < D; r++) {
+            const double v = fabs(A[r * D + c]);
+            if (v > best) { best = v; piv = r; }
+        }
+        if (piv != c) {
+            for (int k = 0; k < D; k++) {
+                double t = A[c * D + k]; A[c * D + k] = A[piv * D + k]; A[piv * D + k] = t;
+                t = R[c * D + k]; R[c * D + k] = R[piv * D + k]; R[piv * D + k] = t;
+            }
+        }
+        const double id = 1.0 / A[c * D + c];
+        for (int k = 0; k < D; k++) { A[c * D + k] *= id; R[c * D + k] *= id; }
+        for (int r = 0; r < D; r++) {
+            if (r == c) continue;
+            const double f = A[r * D + c];
+            if (f == 0) continue;
+            for (int k = 0; k < D; k++) { A[r * D + k] -= f * A[c * D + k]; R[r * D + k] -= f * R[c * D + k]; }
+        }
+    }
+}
+
 // ---- mixed law at voxel offset o -----------------------------------------------------------------
 template <int D>
 struct Mixed {
+    // ReussMixedMaterialLaw (fg:12653-12724): harmonic mean of the phase tangents on mixed voxels; returns the pure phase
+    // index (>= 0) if the voxel is pure, else -1 with Ceff filled (row-major, as the reference stores it)
+    __device__ static int reuss_matrix(const MaterialDev& M, size_t o, const LawCtx& lc, const double* F, double* Ceff) {
+        double Sum[D * D], C[D * D], Ci[D * D];
+        for (int i = 0; i < D * D; i++) Sum[i] = 0;
+        for (int p = 0; p < M.nphases; p++) {
+            const double phi = M.phi[p][o];
+            if (phi == 0) continue;
+            if (phi == 1) return p;
+            for (int m = 0; m < D; m++) {
+                double e[9], r[9];
+#pragma unroll
+                for (int k = 0; k < 9; k++) e[k] = (k == m) ? 1.0 : 0.0;
+                law_dPK1<D>(M.law[p], lc, F, 1.0, false, e, r);
+                for (int k = 0; k < D; k++) C[m * D + k] = r[k];
+            }
+            invert_dense<D>(C, Ci);
+            for (int i = 0; i < D * D; i++) Sum[i] += phi * Ci[i];
+        }
+        invert_dense<D>(Sum, Ceff);
+        return -1;
+    }
+
     // phase selection of the laminate rule (get_mix fg:13456-13525): returns number of phases (1 or 2)
     __device__ static int laminate_split(const MaterialDev& M, size_t o, const LawCtx& lc, const double* F, int& p1, int& p2, double& c1,
                                          double& c2, double* F1, double* F2) {
@@ -507,6 +559,15 @@ struct Mixed {
             const int np = laminate_split(M, o, lc, F, p1, p2, c1, c2, F1, F2);
             law_PK1<D>(M.law[p1], lc, F1, c1 * alpha, false, P);
             if (np == 2) law_PK1<D>(M.law[p2], lc, F2, c2 * alpha, true, P);
+        } else if (M.mix == FGB_MIX_REUSS) {                           // fg:12663-12688
+            double C[D * D];
+            const int pure = reuss_matrix(M, o, lc, F, C);
+            if (pure >= 0) { law_PK1<D>(M.law[pure], lc, F, alpha, false, P); return; }
+            for (int k = 0; k < D; k++) {
+                double s = 0;
+                for (int j = 0; j < D; j++) s += alpha * C[k * D + j] * F[j];
+                P[k] = s;
+            }
         }
     }
 
@@ -527,6 +588,15 @@ struct Mixed {
             const int np = laminate_split(M, o, lc, F, p1, p2, c1, c2, F1, F2);
             law_dPK1<D>(M.law[p1], lc, F1, c1 * alpha, false, W, dP);
             if (np == 2) law_dPK1<D>(M.law[p2], lc, F2, c2 * alpha, true, W, dP);
+        } else if (M.mix == FGB_MIX_REUSS) {                           // fg:12690-12718
+            double C[D * D];
+            const int pure = reuss_matrix(M, o, lc, F, C);
+            if (pure >= 0) { law_dPK1<D>(M.law[pure], lc, F, alpha, false, W, dP); return; }
+            for (int k = 0; k < D; k++) {
+                double s = 0;
+                for (int j = 0; j < D; j++) s += alpha * C[k * D + j] * W[j];
+                dP[k] = s;
+            }
         }
     }
 

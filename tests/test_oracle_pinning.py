@@ -108,3 +108,31 @@ def test_homogeneous_one_iteration(method):
     Sm = s.calcMeanStress()
     assert np.allclose(Sm, fo.LinearIsotropic(mu, lam).PK1(E.reshape(6, 1), 1.0)[:, 0], rtol=1e-13)
     assert len(s.residuals) <= 2
+
+
+def hashin_phases(n=(64, 64, 64), sub=4):
+    """demo/elasticity/hashin/project.xml:8-27: inner sphere R=0.2 (mat1), shell R=0.4 (mat2), matrix; volume fractions by
+    sub-sampling, then normalizePhi (fg:17588-17646: the last material has the highest priority)"""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from microstructures import sphere_phi
+    p1 = np.minimum(1.0, sphere_phi(n, R=0.2, sub=sub))
+    rem = 1 - p1
+    p2 = np.minimum(rem, sphere_phi(n, R=0.4, sub=sub))
+    return [("matrix", (1.0, 3.63867684478), rem - p2), ("mat2", (3.0, 2.0), p2), ("mat1", (5.0, 4.0), p1)]
+
+
+def test_hashin_coated_sphere_known_answer():
+    """demo/elasticity/hashin/project.xml:30-32 documents <sigma> = 12.9152*I (k_eff 4.30507, theory 4.305343511446667) for the
+    default solver (CG, staggered, Voigt, tol 1e-10) at 64^3 under e = I.  The reference's composite-voxel integration
+    (initPhi fg:16622-17581, out of scope) is replaced by sub-sampled volume fractions here, which moves the third digit of the
+    discretisation error, so the pin is 1e-3 relative -- enough to catch any error in mixing, operator or scheme."""
+    s = fo.LSSolver(64, 64, 64, mode="elasticity", tol=1e-10)
+    for name, (mu, lam), phi in hashin_phases():
+        s.add_phase(name, fo.LinearIsotropic(mu, lam), phi)
+    s.setStrain([1, 1, 1, 0, 0, 0])
+    s.run()
+    sm = s.calcMeanStress()
+    assert np.allclose(sm[:3], 12.9152, rtol=1e-3)
+    assert np.abs(sm[3:]).max() < 1e-3
+    assert abs(sm[:3].mean() / 3 - 4.305343511446667) / 4.305343511446667 < 1e-3
