@@ -5,6 +5,7 @@
 // fg:18501-18506/18548-18553, G0OperatorFourierStaggered* fg:19749-19927, GammaOperatorFourierCollocated* fg:19302-19745.
 #include "fft_generic.cuh"
 #include "fft_pow2.cuh"
+#include "fft_pow2_3.cuh"
 #include <cmath>
 #include <complex>
 #include <cstdlib>
@@ -138,7 +139,6 @@ __global__ void __launch_bounds__(Max<R1, R2>::v* T) k_ffts_p2(const double2* __
     const long coff = (long)blockIdx.z * mo.cstride + (long)blockIdx.y * mo.ostride + inner;
     double2 v[R1];
     if (s < R2) {
-#pragma unroll
         if (mi.seglen >= N) {
 #pragma unroll
             for (int n1 = 0; n1 < R1; n1++) v[n1] = valid ? gi[(long)(R2 * n1 + s) * mi.estride] : make_double2(0, 0);
@@ -400,6 +400,122 @@ static int launch_xg_p2c(fgb_ctx* ctx, double2* base, const GreenDev& G, long es
 }
 
 // =================================================================================================
+// three-pass power-of-two kernels (N = 512, 1024): fft_pow2_3.cuh
+// =================================================================================================
+template <int R1, int R2, int R3, int DIR, int T>
+__global__ void __launch_bounds__(p3::Plan<R1, R2, R3, T>::TPP* T) k_ffts_p3(const double2* __restrict__ src, double2* __restrict__ dst,
+                                                                            const double2* __restrict__ tw, PencilMap mi, PencilMap mo,
+                                                                            int ninner, PeerTable pt) {
+    using P = p3::Plan<R1, R2, R3, T>;
+    constexpr int N = P::N, M = P::M;
+    extern __shared__ double2 smem_s3[];
+    double2* tw_s = smem_s3;             // N
+    double2* B = smem_s3 + N;            // P::INPLACE_ELEMS
+    const int tid = threadIdx.x;
+    for (int i = tid; i < N; i += P::TPP * T) tw_s[i] = tw[i];
+    const int t = tid % T, s = tid / T;
+    const int inner = blockIdx.x * T + t;
+    const bool valid = inner < ninner;
+    const double2* gi = src + (long)blockIdx.z * mi.cstride + (long)blockIdx.y * mi.ostride + inner;
+    const long coff = (long)blockIdx.z * mo.cstride + (long)blockIdx.y * mo.ostride + inner;
+    double2 v[R1];
+    if (s < M) {
+        if (mi.seglen >= N) {
+#pragma unroll
+            for (int n1 = 0; n1 < R1; n1++) v[n1] = valid ? gi[(long)(M * n1 + s) * mi.estride] : make_double2(0, 0);
+        } else {
+#pragma unroll
+            for (int n1 = 0; n1 < R1; n1++) v[n1] = valid ? gi[mi.at(M * n1 + s)] : make_double2(0, 0);
+        }
+    }
+    __syncthreads();
+    double2 w[R3];
+    P::template forward_inplace<DIR>(v, w, s, t, B, tw_s);
+    if (s < R1 * R2 && valid) {
+        if (mo.seglen >= N) {
+#pragma unroll
+            for (int k3 = 0; k3 < R3; k3++) dst[coff + (long)(s + R1 * R2 * k3) * mo.estride] = w[k3];
+        } else {
+#pragma unroll
+            for (int k3 = 0; k3 < R3; k3++) {
+                const int e = s + R1 * R2 * k3;
+                double2* b = pt.n ? pt.p[e / mo.seglen] : dst;
+                b[coff + mo.at(e)] = w[k3];
+            }
+        }
+    }
+}
+
+// fused x pass: forward (three passes, one component at a time through the two exchange buffers), Green operator on the
+// NC*R3 register values of a thread, mirrored inverse back to the distribution that was loaded.
+template <int R1, int R2, int R3, int NC, int KIND, int T, int MINB>
+__global__ void __launch_bounds__(p3::Plan<R1, R2, R3, T>::TPP* T, MINB)
+    k_fftx_green_p3(double2* __restrict__ base, const double2* __restrict__ tw, GreenDev G, long estride, int ninner, long ostride,
+                    long cstride, int jbase, PencilMap xo, PeerTable pt) {
+    using P = p3::Plan<R1, R2, R3, T>;
+    constexpr int N = P::N, M = P::M;
+    extern __shared__ double2 smem_x3[];
+    double2* tw_s = smem_x3;
+    double2* B1 = smem_x3 + N;
+    double2* B2 = B1 + P::BUF1;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < N; i += P::TPP * T) tw_s[i] = tw[i];
+    const int t = tid % T, s = tid / T;
+    const int inner = blockIdx.x * T + t;
+    const bool valid = inner < ninner;
+    double2* g = base + (long)blockIdx.y * ostride + inner;
+    __syncthreads();
+
+    double2 w[NC][R3];
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        double2 v[R1];
+        if (s < M) {
+#pragma unroll
+            for (int n1 = 0; n1 < R1; n1++) v[n1] = valid ? g[c * cstride + (long)(M * n1 + s) * estride] : make_double2(0, 0);
+        }
+        P::template forward<-1>(v, w[c], s, t, B1, B2, tw_s);
+    }
+    if (s < R1 * R2 && valid) {
+        const int jj = jbase + blockIdx.y;
+        const int kk = inner;
+#pragma unroll
+        for (int k3 = 0; k3 < R3; k3++) {
+            const int ii = s + R1 * R2 * k3;
+            double2 f[NC];
+#pragma unroll
+            for (int c = 0; c < NC; c++) f[c] = w[c][k3];
+            if (ii == 0 && jj == 0 && kk == 0) {
+#pragma unroll
+                for (int c = 0; c < NC; c++) f[c] = make_double2(G.dc[c], 0.0);
+            } else {
+                if (KIND == 1) green_staggered(G, ii, jj, kk, f);
+                if (KIND == 2) green_staggered_heat(G, ii, jj, kk, f);
+                if (KIND == 3) green_colloc_el(G, ii, jj, kk, f);
+                if (KIND == 4) green_colloc_heat(G, ii, jj, kk, f);
+                if (KIND == 5) green_colloc_hyper(G, ii, jj, kk, f);
+            }
+#pragma unroll
+            for (int c = 0; c < NC; c++) w[c][k3] = f[c];
+        }
+    }
+    __syncthreads();          // forward pass-3 reads of B2 are done before the inverse overwrites it
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        double2 o[R1];
+        P::inverse(w[c], o, s, t, B1, B2, tw_s);
+        if (s < M && valid) {
+#pragma unroll
+            for (int na = 0; na < R1; na++) {
+                const int e = s + M * na;
+                double2* b = pt.n ? pt.p[e / xo.seglen] : base;
+                b[c * xo.cstride + (long)blockIdx.y * xo.ostride + inner + xo.at(e)] = o[na];
+            }
+        }
+    }
+}
+
+// =================================================================================================
 // host side: plans, tables, launches
 // =================================================================================================
 static void factorize(int n, FftPlanDev& P) {
@@ -555,6 +671,22 @@ static void launch_s_p2(fgb_ctx* ctx, const double2* src, double2* dst, const do
     }
 }
 
+template <int R1, int R2, int R3, int T>
+static void launch_s_p3(fgb_ctx* ctx, const double2* src, double2* dst, const double2* tw, const PencilMap& mi, const PencilMap& mo,
+                        int ninner, int nouter, int ncomp, int dir, const PeerTable& pt) {
+    using P = p3::Plan<R1, R2, R3, T>;
+    dim3 grid((ninner + T - 1) / T, nouter, ncomp);
+    constexpr int NT = P::TPP * T;
+    const size_t smem = sizeof(double2) * (size_t)(P::N + P::INPLACE_ELEMS);
+    if (dir < 0) {
+        set_smem(k_ffts_p3<R1, R2, R3, -1, T>, smem);
+        k_ffts_p3<R1, R2, R3, -1, T><<<grid, NT, smem, ctx->stream>>>(src, dst, tw, mi, mo, ninner, pt);
+    } else {
+        set_smem(k_ffts_p3<R1, R2, R3, +1, T>, smem);
+        k_ffts_p3<R1, R2, R3, +1, T><<<grid, NT, smem, ctx->stream>>>(src, dst, tw, mi, mo, ninner, pt);
+    }
+}
+
 int fgb_fft_strided(fgb_ctx* ctx, int axis, const double* src_, double* dst_, const PencilMap& mi, const PencilMap& mo, int ninner,
                     int nouter, int ncomp, int dir, const PeerTable* peers) {
     const int n = ctx->plan[axis].n;
@@ -566,6 +698,13 @@ int fgb_fft_strided(fgb_ctx* ctx, int axis, const double* src_, double* dst_, co
     if (ninner == 0 || nouter == 0) return FGB_OK;
     if (n == 1 && src == dst) return FGB_OK;
     const double2* tw = ctx->plan[axis].tw;
+    // 512: three passes of radix 8 (64 registers, 3 CTAs/SM) beat the 32x16 two-pass kernel; at 1024 the two-pass kernel wins
+    static const bool no_p3 = getenv("FGB_NO_P3") != nullptr;
+    if (n == 512 && !no_p3) {
+        launch_s_p3<8, 8, 8, 8>(ctx, src, dst, tw, mi, mo, ninner, nouter, ncomp, dir, pt);
+        FGB_CHECK_LAUNCH(ctx, "k_ffts_p3");
+        return FGB_OK;
+    }
     if (is_fast_pow2(n)) {
         switch (n) {
             case 64: launch_s_p2<64, 8, 8, 8>(ctx, src, dst, tw, mi, mo, ninner, nouter, ncomp, dir, pt); break;
@@ -613,6 +752,21 @@ static int launch_xg_p2(fgb_ctx* ctx, double2* base, const GreenDev& G, long est
     return FGB_OK;
 }
 
+template <int R1, int R2, int R3, int NC, int KIND, int T, int MINB>
+static int launch_xg_p3(fgb_ctx* ctx, double2* base, const GreenDev& G, long estride, int ninner, int nouter, long ostride, long cstride,
+                        int jbase, const PencilMap& xo, const PeerTable& pt) {
+    using P = p3::Plan<R1, R2, R3, T>;
+    constexpr int NT = P::TPP * T;
+    const size_t smem = (size_t)(P::N + P::SMEM_ELEMS) * sizeof(double2);
+    if (smem > ctx->smem_optin) return -1;
+    dim3 grid((ninner + T - 1) / T, nouter, 1);
+    FGB_CUDA(ctx, set_smem(k_fftx_green_p3<R1, R2, R3, NC, KIND, T, MINB>, smem));
+    k_fftx_green_p3<R1, R2, R3, NC, KIND, T, MINB><<<grid, NT, smem, ctx->stream>>>(base, ctx->plan[0].tw, G, estride, ninner, ostride, cstride,
+                                                                                   jbase, xo, pt);
+    FGB_CHECK_LAUNCH(ctx, "k_fftx_green_p3");
+    return FGB_OK;
+}
+
 template <int NC, int KIND>
 static int launch_x_green(fgb_ctx* ctx, double2* base, const GreenDev& G, long estride, int ninner, int nouter, long ostride, long cstride,
                           int jbase, const PencilMap& xo, const PeerTable& pt) {
@@ -630,6 +784,24 @@ static int launch_x_green(fgb_ctx* ctx, double2* base, const GreenDev& G, long e
             }
             if (rc != -1) return rc;
         }
+    }
+    // three-pass kernels: NC*R3 complex values per thread, so every tensor rank stays in registers.  They carry nx = 512 / 1024 for
+    // all operators and the 6- and 9-component (collocated) operators at every power of two; the 1- and 3-component operators at
+    // nx <= 256 are faster with the two-pass kernel below.
+    static const bool no_p3 = getenv("FGB_NO_P3") != nullptr;
+    static const bool xg_p3 = getenv("FGB_XG_P3") != nullptr;
+    constexpr int MB = (NC <= 3 ? 2 : 1);
+    if (!no_p3) {
+#define XG3(R1, R2, R3, T) rc = launch_xg_p3<R1, R2, R3, NC, KIND, T, MB>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt)
+        if (nx == 512) XG3(8, 8, 8, 4);
+        else if (nx == 1024) XG3(16, 8, 8, 2);
+        else if (NC > 3 || xg_p3) {
+            if (nx == 64) XG3(4, 4, 4, 8);
+            else if (nx == 128) XG3(8, 4, 4, 8);
+            else if (nx == 256) XG3(8, 8, 4, 4);
+        }
+#undef XG3
+        if (rc != -1) return rc;
     }
     if constexpr (NC <= 3) {
         switch (nx) {

@@ -242,7 +242,8 @@ def test_blas_and_reductions(n, mode, d):
     ctx.close()
 
 
-@pytest.mark.parametrize("n", [(64, 64, 64), (128, 64, 256), (256, 128, 64), (64, 512, 128), (512, 64, 64), (64, 64, 1024), (1024, 64, 64)])
+@pytest.mark.parametrize("n", [(64, 64, 64), (128, 64, 256), (256, 128, 64), (64, 512, 128), (512, 64, 64), (64, 64, 512),
+                               (64, 64, 1024), (1024, 64, 64), (64, 1024, 64)])
 def test_pow2_fast_paths(n):
     """register-resident radix-8/16/32 passes (fft_pow2.cuh) on every supported axis length, forward/backward transform
     and the fused x pass with the staggered / collocated Green operators"""
@@ -264,9 +265,11 @@ def test_pow2_fast_paths(n):
     ctx.gamma(f, E, 0.7, 0.0, -1.0, 0.5)
     assert relerr(ctx.download(f), o.GammaOperator(E, 0.7, 0.0, x, -1.0, 0.5)) < 2e-12
     ctx.close()
-    for mode, d in (("elasticity", 6), ("heat", 3)):
-        ctx = fb.Context(*n, *L, mode=mode, gamma_scheme="staggered")
-        o = fo.LSSolver(*n, *L, mode=mode, gamma_scheme="staggered")
+    # 6- and 9-component collocated operators run the three-pass x kernel (fft_pow2_3.cuh) at every power of two
+    for mode, d, scheme in (("elasticity", 6, "staggered"), ("heat", 3, "staggered"), ("elasticity", 6, "collocated"),
+                            ("hyperelasticity", 9, "collocated")):
+        ctx = fb.Context(*n, *L, mode=mode, gamma_scheme=scheme)
+        o = fo.LSSolver(*n, *L, mode=mode, gamma_scheme=scheme)
         o.set_reference(1.3, 0.4)
         o.setBCProjector(fo.Id4(d))
         tau = rng.standard_normal((d,) + n)
