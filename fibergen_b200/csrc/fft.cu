@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(Max<R1, R2>::v* T) k_ffts_p2(const double2* __
 //   operator: every thread owns all NC components at its R2 frequencies (registers)
 //   inverse : threads k1: R2-point inverse FFT over k2, twiddle conj W_N^(k1 na) | exchange | threads na: R1-point inverse FFT over k1
 //             -> x[na + R2 nb], the same distribution the forward pass loaded, stored straight back to HBM.
-template <int N, int R1, int R2, int NC, int KIND, int T>
+template <int N, int R1, int R2, int NC, int KIND, int T, int ASYNC>
 __global__ void __launch_bounds__(Max<R1, R2>::v* T) k_fftx_green_p2(double2* __restrict__ base, const double2* __restrict__ tw, GreenDev G,
                                                                      long estride, int ninner, long ostride, long cstride, int jbase,
                                                                      PencilMap xo, PeerTable pt) {
@@ -197,14 +197,42 @@ __global__ void __launch_bounds__(Max<R1, R2>::v* T) k_fftx_green_p2(double2* __
     double2* g = base + (long)blockIdx.y * ostride + inner;
     __syncthreads();
 
-    // ---- forward pass 1 (per component; one component in registers at a time)
+    // ---- forward pass 1 (per component; one component in registers at a time).  All NC*R1 loads of a thread are issued up front
+    // as 16-byte asynchronous copies into the exchange buffer (element x of component c at Sc[x*T + t], exactly where the
+    // thread stores its pass-1 result for k1 = x / R2), one commit group per component, so the whole tile is in flight while
+    // the first component is being transformed.
     if (s < R2) {
+        if (ASYNC) {
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                double2* Sc = S + (size_t)c * N * T;
+#pragma unroll
+                for (int n1 = 0; n1 < R1; n1++) {
+                    double2* d = Sc + ((R2 * n1 + s) * T + t);
+                    if (valid) {
+                        const unsigned sa = (unsigned)__cvta_generic_to_shared(d);
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(g + c * cstride + (long)(R2 * n1 + s) * estride) : "memory");
+                    } else {
+                        *d = make_double2(0, 0);
+                    }
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            }
+        }
 #pragma unroll
         for (int c = 0; c < NC; c++) {
             double2* Sc = S + (size_t)c * N * T;
             double2 v[R1];
+            if (ASYNC) {
+                if (c == 0) asm volatile("cp.async.wait_group %0;" ::"n"(NC - 1) : "memory");
+                else if (c == 1) asm volatile("cp.async.wait_group %0;" ::"n"(NC > 2 ? NC - 2 : 0) : "memory");
+                else asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
-            for (int n1 = 0; n1 < R1; n1++) v[n1] = valid ? g[c * cstride + (long)(R2 * n1 + s) * estride] : make_double2(0, 0);
+                for (int n1 = 0; n1 < R1; n1++) v[n1] = Sc[(R2 * n1 + s) * T + t];
+            } else {
+#pragma unroll
+                for (int n1 = 0; n1 < R1; n1++) v[n1] = valid ? g[c * cstride + (long)(R2 * n1 + s) * estride] : make_double2(0, 0);
+            }
             p2::pass1<R1, R2, -1>(v, s, tw_s);
 #pragma unroll
             for (int k1 = 0; k1 < R1; k1++) Sc[(k1 * R2 + s) * T + t] = v[k1];
@@ -746,8 +774,14 @@ static int launch_xg_p2(fgb_ctx* ctx, double2* base, const GreenDev& G, long est
     const size_t smem = (size_t)(N + (size_t)NC * N * T) * sizeof(double2);
     if (smem > ctx->smem_optin) return -1;
     dim3 grid((ninner + T - 1) / T, nouter, 1);
-    FGB_CUDA(ctx, set_smem(k_fftx_green_p2<N, R1, R2, NC, KIND, T>, smem));
-    k_fftx_green_p2<N, R1, R2, NC, KIND, T><<<grid, NT, smem, ctx->stream>>>(base, ctx->plan[0].tw, G, estride, ninner, ostride, cstride, jbase, xo, pt);
+    static const bool no_async = getenv("FGB_XG_NOASYNC") != nullptr;
+    if (no_async) {
+        FGB_CUDA(ctx, set_smem(k_fftx_green_p2<N, R1, R2, NC, KIND, T, 0>, smem));
+        k_fftx_green_p2<N, R1, R2, NC, KIND, T, 0><<<grid, NT, smem, ctx->stream>>>(base, ctx->plan[0].tw, G, estride, ninner, ostride, cstride, jbase, xo, pt);
+    } else {
+        FGB_CUDA(ctx, set_smem(k_fftx_green_p2<N, R1, R2, NC, KIND, T, 1>, smem));
+        k_fftx_green_p2<N, R1, R2, NC, KIND, T, 1><<<grid, NT, smem, ctx->stream>>>(base, ctx->plan[0].tw, G, estride, ninner, ostride, cstride, jbase, xo, pt);
+    }
     FGB_CHECK_LAUNCH(ctx, "k_fftx_green_p2");
     return FGB_OK;
 }

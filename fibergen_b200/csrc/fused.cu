@@ -9,8 +9,9 @@
 //   k_eps_dot            : eta = E + sym-grad_h u                      (epsOperatorStaggered fg:18614, applyBCProjector fg:20263)
 //                          <p, p - eta>                                (innerProductL2 fg:20871) in the same pass.
 #include "fgb_internal.h"
-#include "reduce.cuh"
+#include <cmath>
 #include <cstdlib>
+#include "reduce.cuh"
 
 struct IsoPhases {
     int n;
@@ -205,7 +206,7 @@ __device__ __forceinline__ void diag_from(const IsoPhases& M, const double* phi,
     if (gamma != 0) { t0 += gamma * tr; t1 += gamma * tr; t2 += gamma * tr; }
 }
 
-template <int UPDATE, int NP, int BJ, int HALO>
+template <int UPDATE, int NP, int BJ, int HALO, int ZW>
 __global__ void __launch_bounds__(256, 2) k_dsd_march(const double* __restrict__ r, const double* __restrict__ p_old, double* __restrict__ p_new,
                                                    double* __restrict__ u, GridDev g, IsoPhases M, double cgbeta, double beta, double gamma,
                                                    int SEG, const double* __restrict__ halo) {
@@ -217,14 +218,19 @@ __global__ void __launch_bounds__(256, 2) k_dsd_march(const double* __restrict__
     const int i1 = min(i0 + SEG, g.lnx);
     const int k = blockIdx.z * blockDim.x + threadIdx.x;
     const bool active = k < g.nz;
-    const int kc = active ? k : 0;                      // inactive lanes shadow k = 0 (no stores) so that shuffles stay uniform
-    const int lane = threadIdx.x & 31;
+    const int kc = active ? k : 0;                      // inactive lanes shadow k = 0 (no stores)
     const size_t P = g.plane;
     const int jm0 = (j0 == 0) ? g.ny - 1 : j0 - 1;
     const int jpB = (j0 + BJ == g.ny) ? 0 : j0 + BJ;
     const int kp = (kc + 1 == g.nz) ? 0 : kc + 1, km = (kc == 0) ? g.nz - 1 : kc - 1;
-    const bool edge_hi = (lane == 31) || (threadIdx.x == blockDim.x - 1) || (kc + 1 >= g.nz);
-    const bool edge_lo = (lane == 0) || (kc == 0);
+    // z neighbours travel through shared memory (double-buffered: one barrier per plane).  ZW: the CTA holds the whole z row, the
+    // periodic wrap is a slot index; otherwise the two threads at the CTA's ends recompute their neighbour from memory.
+    __shared__ double zx[2][3 * BJ][256];
+    const int tid = threadIdx.x;
+    const bool edge_hi = !ZW && ((tid == (int)blockDim.x - 1) || (kc + 1 >= g.nz));
+    const bool edge_lo = !ZW && ((tid == 0) || (kc == 0));
+    const int nb_hi = ZW ? ((kc + 1 == g.nz) ? 0 : tid + 1) : min(tid + 1, (int)blockDim.x - 1);
+    const int nb_lo = ZW ? ((kc == 0) ? g.nz - 1 : tid - 1) : max(tid - 1, 0);
 #define ROW(i, j) (((size_t)(i) * g.ny + (j)) * g.nzp)
 
     double t0_prev[BJ], t5n[BJ], t4n[BJ], phin[BJ][NP];
@@ -303,12 +309,20 @@ __global__ void __launch_bounds__(256, 2) k_dsd_march(const double* __restrict__
             t5n[jr] = shear_from<NP>(M, phin[jr], e5, beta);
             t4n[jr] = shear_from<NP>(M, phin[jr], e4, beta);
         }
+        double(*zb)[256] = zx[(i - i0) & 1];
+#pragma unroll
+        for (int jr = 0; jr < BJ; jr++) {
+            zb[3 * jr][tid] = tc[jr][4];
+            zb[3 * jr + 1][tid] = tc[jr][3];
+            zb[3 * jr + 2][tid] = tc[jr][2];
+        }
+        __syncthreads();
 #pragma unroll
         for (int jr = 0; jr < BJ; jr++) {
             // z neighbours
-            double t4_kp = __shfl_down_sync(0xffffffffu, tc[jr][4], 1);
-            double t3_kp = __shfl_down_sync(0xffffffffu, tc[jr][3], 1);
-            double t2_km = __shfl_up_sync(0xffffffffu, tc[jr][2], 1);
+            double t4_kp = zb[3 * jr][nb_hi];
+            double t3_kp = zb[3 * jr + 1][nb_hi];
+            double t2_km = zb[3 * jr + 2][nb_lo];
             if (edge_hi) {
                 double ph[NP];
                 const size_t o = ROW(i, j0 + jr) + kp;
@@ -350,14 +364,33 @@ static int launch_march(fgb_ctx* ctx, const double* r, const double* p_old, doub
     int threads = 256;
     while (threads > 32 && threads / 2 >= g.nz) threads /= 2;
     const int kchunks = (g.nz + threads - 1) / threads;
+    // x segment length: each segment pays one warm-up plane, and the grid should fill whole waves of 2 CTAs per SM
+    const int BJsel = (g.ny % 4 == 0) ? 4 : (g.ny % 2 == 0) ? 2 : 1;
     int SEG = 16;
+    if (const char* e = getenv("FGB_MARCH_SEG")) SEG = atoi(e);
+    else {
+        double best = 0;
+        for (int nseg = 1; nseg <= (g.lnx + 7) / 8; nseg++) {
+            const int cand = (g.lnx + nseg - 1) / nseg;          // balanced segments
+            const long ctas = (long)(g.ny / BJsel) * ((g.lnx + cand - 1) / cand) * kchunks;
+            const double waves = (double)ctas / (2.0 * ctx->sm_count);
+            const double score = waves / std::ceil(waves) * cand / (cand + 1.0);
+            if (score > best * 1.005) { best = score; SEG = cand; }
+        }
+    }
     if (g.lnx < SEG) SEG = g.lnx;
+    if (SEG < 1) SEG = 1;
     const int segs = (g.lnx + SEG - 1) / SEG;
 #define LAUNCH_MARCH(BJ_)                                                                                                          \
     do {                                                                                                                          \
         dim3 grid(g.ny / BJ_, segs, kchunks);                                                                                     \
-        if (halo) k_dsd_march<UPDATE, NP, BJ_, 1><<<grid, threads, 0, ctx->stream>>>(r, p_old, p_new, ctx->ubuf, g, M, cgbeta, beta, gamma, SEG, halo); \
-        else k_dsd_march<UPDATE, NP, BJ_, 0><<<grid, threads, 0, ctx->stream>>>(r, p_old, p_new, ctx->ubuf, g, M, cgbeta, beta, gamma, SEG, halo);      \
+        if (halo) {                                                                                                               \
+            if (kchunks == 1) k_dsd_march<UPDATE, NP, BJ_, 1, 1><<<grid, threads, 0, ctx->stream>>>(r, p_old, p_new, ctx->ubuf, g, M, cgbeta, beta, gamma, SEG, halo); \
+            else k_dsd_march<UPDATE, NP, BJ_, 1, 0><<<grid, threads, 0, ctx->stream>>>(r, p_old, p_new, ctx->ubuf, g, M, cgbeta, beta, gamma, SEG, halo);             \
+        } else {                                                                                                                  \
+            if (kchunks == 1) k_dsd_march<UPDATE, NP, BJ_, 0, 1><<<grid, threads, 0, ctx->stream>>>(r, p_old, p_new, ctx->ubuf, g, M, cgbeta, beta, gamma, SEG, halo); \
+            else k_dsd_march<UPDATE, NP, BJ_, 0, 0><<<grid, threads, 0, ctx->stream>>>(r, p_old, p_new, ctx->ubuf, g, M, cgbeta, beta, gamma, SEG, halo);             \
+        }                                                                                                                         \
     } while (0)
     if (g.ny % 4 == 0) LAUNCH_MARCH(4);
     else if (g.ny % 2 == 0) LAUNCH_MARCH(2);
