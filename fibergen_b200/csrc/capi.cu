@@ -153,6 +153,8 @@ extern "C" int fgb_create(fgb_ctx** out, int nx, int ny, int nz, double Lx, doub
     c->stream = c->own_stream;
     c->red_blocks = c->sm_count * 8;
     CREATE_CUDA(cudaMalloc(&c->d_partials, sizeof(double) * 32 * (size_t)c->red_blocks));
+    c->partials_cap = (size_t)c->red_blocks;
+    c->implicit_w_of = -1;
     CREATE_CUDA(cudaMalloc(&c->d_result, sizeof(double) * 64));
     CREATE_CUDA(cudaMallocHost(&c->h_result, sizeof(double) * 64));
     CREATE_CUDA(cudaMalloc(&c->d_flag, sizeof(int)));
@@ -478,6 +480,7 @@ static int g0_staggered(fgb_ctx* c, double mu0, double lambda0, double alpha) {
     green_args(c, ga, mu0, lambda0, alpha, 0.0);
     int rc;
     const FftLayout lay = {c->g.unzcs};
+    c->implicit_w_of = -1;
     if ((rc = fgb_fft_z_forward(c, c->ubuf, c->udim, lay))) return rc;
     if (c->nranks > 1) {
         // slab partition: the y passes are part of the transposed x pass (they read/write the all-to-all staging layout)
@@ -558,6 +561,7 @@ extern "C" int fgb_eps_staggered(fgb_ctx* c, int f, const double* E) {
 extern "C" int fgb_u_upload(fgb_ctx* c, const double* const* comps, int n) {
     CHECK_CTX(c);
     if (!c->ubuf || n != c->udim) return fgb_fail(c, FGB_EINVAL, "u buffer has %d components", c->udim);
+    c->implicit_w_of = -1;
     for (int d = 0; d < n; d++)
         FGB_CUDA(c, cudaMemcpy2DAsync(c->ubuf + (size_t)d * c->g.uplane, sizeof(double) * 2 * c->g.unzcs, comps[d], sizeof(double) * c->g.nzp,
                                       sizeof(double) * c->g.nzp, (size_t)c->g.lnx * c->g.ny, cudaMemcpyHostToDevice, c->stream));
@@ -664,18 +668,32 @@ extern "C" int fgb_cg_apply(fgb_ctx* c, int F, int p, int w, double mu0, double 
 
 // One fused CG operator application: p_new = r + beta*p_old (skipped when r < 0, then p_new must equal p_old),
 // w = -Gamma0:(C-C0):p_new (or the tangent operator at F), pAp = <p_new, p_new - w>.
+// 1 if fgb_cg_step / fgb_cg_update accept w = FGB_W_IMPLICIT on this context (fused linear-elastic staggered path, no BC projector)
+static bool cg_fused_path(const fgb_ctx* c) { return fgb_fused_iso_applicable(c) && !c->bc_active && c->bc_relax == 1.0; }
+extern "C" int fgb_cg_implicit_w_supported(const fgb_ctx* c) { return (c && cg_fused_path(c)) ? 1 : 0; }
+
 extern "C" int fgb_cg_step(fgb_ctx* c, int F, int r, double beta, int p_old, int p_new, int w, double mu0, double lambda0, double* pAp) {
-    CHECK_CTX(c); CHECK_FIELD(c, p_old); CHECK_FIELD(c, p_new); CHECK_FIELD(c, w);
+    CHECK_CTX(c); CHECK_FIELD(c, p_old); CHECK_FIELD(c, p_new);
+    const bool implicit_w = (w == FGB_W_IMPLICIT);
+    if (!implicit_w) CHECK_FIELD(c, w);
     if (r >= 0) CHECK_FIELD(c, r);
     if (r < 0 && p_old != p_new) return fgb_fail(c, FGB_EINVAL, "fgb_cg_step without a direction update needs p_new == p_old");
     if (p_new == w) return fgb_fail(c, FGB_EINVAL, "krylovOperator cannot work in place (fg:20581)");
+    if (implicit_w && !(F < 0 && cg_fused_path(c) && r >= 0 && p_old != p_new && pAp))
+        return fgb_fail(c, FGB_EUNSUPPORTED, "w = FGB_W_IMPLICIT needs the fused linear CG step (see fgb_cg_implicit_w_supported)");
     int rc;
-    if (F < 0 && fgb_fused_iso_applicable(c) && !c->bc_active && c->bc_relax == 1.0 && (r < 0 || p_old != p_new)) {
+    if (F < 0 && cg_fused_path(c) && (r < 0 || p_old != p_new)) {
         double zero[9] = {0};
         if (c->nranks > 1 && (rc = fgb_comm_halo_iso(c, r >= 0 ? c->fields[r] : nullptr, c->fields[p_old]))) return rc;
         if ((rc = fgb_k_dir_stress_div_iso(c, r >= 0 ? c->fields[r] : nullptr, beta, c->fields[p_old], c->fields[p_new], mu0, lambda0, 1.0))) return rc;
         if ((rc = g0_staggered(c, mu0, lambda0, -1.0))) return rc;
         if (c->nranks > 1 && (rc = fgb_comm_halo_u(c))) return rc;
+        if (implicit_w) {
+            // w = sym-grad(u) is not written out: the sum is taken on the fly and fgb_cg_update re-evaluates w from u
+            if ((rc = fgb_k_eps_dot(c, c->ubuf, nullptr, zero, c->fields[p_new], pAp))) return rc;
+            c->implicit_w_of = p_new;
+            return FGB_OK;
+        }
         if (pAp) return fgb_k_eps_dot(c, c->ubuf, c->fields[w], zero, c->fields[p_new], pAp);
         return fgb_k_eps(c, c->ubuf, c->fields[w], zero);
     }
@@ -684,7 +702,14 @@ extern "C" int fgb_cg_step(fgb_ctx* c, int F, int r, double beta, int p_old, int
 }
 
 extern "C" int fgb_cg_update(fgb_ctx* c, int x, int r, int p, int w, double a, double* delta) {
-    CHECK_CTX(c); CHECK_FIELD(c, x); CHECK_FIELD(c, r); CHECK_FIELD(c, p); CHECK_FIELD(c, w);
+    CHECK_CTX(c); CHECK_FIELD(c, x); CHECK_FIELD(c, r); CHECK_FIELD(c, p);
+    if (w == FGB_W_IMPLICIT) {
+        if (c->implicit_w_of != p || x == p || r == p || x == r)
+            return fgb_fail(c, FGB_EINVAL, "fgb_cg_update: no implicit operator result for field %d (call fgb_cg_step with w = FGB_W_IMPLICIT first)", p);
+        const double zero[9] = {0};
+        return fgb_k_cg_update_implicit(c, c->ubuf, zero, c->fields[x], c->fields[r], c->fields[p], a, delta);
+    }
+    CHECK_FIELD(c, w);
     return fgb_k_cg_update(c, c->fields[x], c->fields[r], c->fields[p], c->fields[w], a, delta);
 }
 

@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(Max<R1, R2>::v* T) k_fftx_green_p2(double2* __
                 asm volatile("cp.async.commit_group;" ::: "memory");
             }
         }
-#pragma unroll
+#pragma unroll(ASYNC == 2 ? 1 : NC)
         for (int c = 0; c < NC; c++) {
             double2* Sc = S + (size_t)c * N * T;
             double2 v[R1];
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(Max<R1, R2>::v* T) k_fftx_green_p2(double2* __
     __syncthreads();
     // ---- inverse pass 2: thread na gathers Y[k1][na] over k1, R1-point inverse FFT, output x[na + R2*nb]
     if (s < R2) {
-#pragma unroll
+#pragma unroll(ASYNC == 2 ? 1 : NC)
         for (int c = 0; c < NC; c++) {
             const double2* Sc = S + (size_t)c * N * T;
             double2 v[R1];
@@ -774,8 +774,14 @@ static int launch_xg_p2(fgb_ctx* ctx, double2* base, const GreenDev& G, long est
     const size_t smem = (size_t)(N + (size_t)NC * N * T) * sizeof(double2);
     if (smem > ctx->smem_optin) return -1;
     dim3 grid((ninner + T - 1) / T, nouter, 1);
+    // default: asynchronous tile prefetch, component loops of the first and last pass not unrolled (smaller code, fewer
+    // instruction-cache misses); FGB_XG_UNROLLED / FGB_XG_NOASYNC select the older variants for comparison
     static const bool no_async = getenv("FGB_XG_NOASYNC") != nullptr;
-    if (no_async) {
+    static const bool rolled = getenv("FGB_XG_UNROLLED") == nullptr && !no_async;
+    if (rolled) {
+        FGB_CUDA(ctx, set_smem(k_fftx_green_p2<N, R1, R2, NC, KIND, T, 2>, smem));
+        k_fftx_green_p2<N, R1, R2, NC, KIND, T, 2><<<grid, NT, smem, ctx->stream>>>(base, ctx->plan[0].tw, G, estride, ninner, ostride, cstride, jbase, xo, pt);
+    } else if (no_async) {
         FGB_CUDA(ctx, set_smem(k_fftx_green_p2<N, R1, R2, NC, KIND, T, 0>, smem));
         k_fftx_green_p2<N, R1, R2, NC, KIND, T, 0><<<grid, NT, smem, ctx->stream>>>(base, ctx->plan[0].tw, G, estride, ninner, ostride, cstride, jbase, xo, pt);
     } else {

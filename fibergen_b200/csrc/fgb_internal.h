@@ -61,6 +61,8 @@ struct fgb_ctx {
     int device;
     int rank, nranks;
     int sm_count;
+    size_t partials_cap;          // blocks d_partials has room for
+    int implicit_w_of;            // field id p whose operator result w = sym-grad(u) is held implicitly in ubuf (-1: none)
     size_t smem_optin;
     cudaStream_t stream, own_stream;
     std::string err;
@@ -218,6 +220,7 @@ int fgb_k_component_dot(fgb_ctx* ctx, const double* a, const double* b, double* 
 int fgb_k_cg_update(fgb_ctx* ctx, double* x, double* r, const double* p, const double* w, double a, double* delta);
 // finish a block-partial reduction of `nvals` sums (or mins/maxs) and copy to host; op 0 sum, 1 min, 2 max
 int fgb_reduce_finish(fgb_ctx* ctx, int nblocks, int nvals, int op, double* host_out);
+int fgb_reduce_reserve(fgb_ctx* ctx, size_t nblocks);      // room for nblocks per-block partials (grows d_partials)
 int fgb_allreduce_host(fgb_ctx* ctx, double* vals, int n, int op);
 
 // fused.cu -----------------------------------------------------------------------------------
@@ -227,6 +230,7 @@ int fgb_k_dir_stress_div_iso(fgb_ctx* ctx, const double* r, double cgbeta, const
                              double alpha);
 // eta = E + sym-grad u and pAp = <p, p - eta>
 int fgb_k_eps_dot(fgb_ctx* ctx, const double* u, double* eta, const double* Econst, const double* p, double* pAp);
+int fgb_k_cg_update_implicit(fgb_ctx* ctx, const double* u, const double* Econst, double* x, double* r, const double* p, double a, double* delta);
 
 // comm.cu ------------------------------------------------------------------------------------
 int fgb_comm_free(fgb_ctx* ctx);

@@ -356,31 +356,44 @@ __global__ void __launch_bounds__(256, 2) k_dsd_march(const double* __restrict__
 #undef ROW
 }
 
+// marching tiles: block size along z, rows per thread, and the x segment length.  Each segment pays one warm-up plane, and the
+// grid should fill whole waves of 2 CTAs per SM.
+struct MarchTile {
+    int threads, kchunks, BJ, SEG, segs;
+};
+static MarchTile march_tile(const fgb_ctx* ctx) {
+    const GridDev& g = ctx->g;
+    MarchTile t;
+    t.threads = 256;
+    while (t.threads > 32 && t.threads / 2 >= g.nz) t.threads /= 2;
+    t.kchunks = (g.nz + t.threads - 1) / t.threads;
+    t.BJ = (g.ny % 4 == 0) ? 4 : (g.ny % 2 == 0) ? 2 : 1;
+    t.SEG = 16;
+    if (const char* e = getenv("FGB_MARCH_SEG")) t.SEG = atoi(e);
+    else {
+        double best = 0;
+        for (int nseg = 1; nseg <= (g.lnx + 7) / 8; nseg++) {
+            const int cand = (g.lnx + nseg - 1) / nseg;          // balanced segments
+            const long ctas = (long)(g.ny / t.BJ) * ((g.lnx + cand - 1) / cand) * t.kchunks;
+            const double waves = (double)ctas / (2.0 * ctx->sm_count);
+            const double score = waves / std::ceil(waves) * cand / (cand + 1.0);
+            if (score > best * 1.005) { best = score; t.SEG = cand; }
+        }
+    }
+    if (g.lnx < t.SEG) t.SEG = g.lnx;
+    if (t.SEG < 1) t.SEG = 1;
+    t.segs = (g.lnx + t.SEG - 1) / t.SEG;
+    return t;
+}
+
 template <int UPDATE, int NP>
 static int launch_march(fgb_ctx* ctx, const double* r, const double* p_old, double* p_new, const IsoPhases& M, double cgbeta, double beta,
                         double gamma) {
     const GridDev& g = ctx->g;
     const double* halo = (ctx->nranks > 1) ? ctx->iso_halo : nullptr;
-    int threads = 256;
-    while (threads > 32 && threads / 2 >= g.nz) threads /= 2;
-    const int kchunks = (g.nz + threads - 1) / threads;
-    // x segment length: each segment pays one warm-up plane, and the grid should fill whole waves of 2 CTAs per SM
-    const int BJsel = (g.ny % 4 == 0) ? 4 : (g.ny % 2 == 0) ? 2 : 1;
-    int SEG = 16;
-    if (const char* e = getenv("FGB_MARCH_SEG")) SEG = atoi(e);
-    else {
-        double best = 0;
-        for (int nseg = 1; nseg <= (g.lnx + 7) / 8; nseg++) {
-            const int cand = (g.lnx + nseg - 1) / nseg;          // balanced segments
-            const long ctas = (long)(g.ny / BJsel) * ((g.lnx + cand - 1) / cand) * kchunks;
-            const double waves = (double)ctas / (2.0 * ctx->sm_count);
-            const double score = waves / std::ceil(waves) * cand / (cand + 1.0);
-            if (score > best * 1.005) { best = score; SEG = cand; }
-        }
-    }
-    if (g.lnx < SEG) SEG = g.lnx;
-    if (SEG < 1) SEG = 1;
-    const int segs = (g.lnx + SEG - 1) / SEG;
+    const MarchTile mt = march_tile(ctx);
+    const int threads = mt.threads, kchunks = mt.kchunks, SEG = mt.SEG;
+    const int segs = mt.segs;
 #define LAUNCH_MARCH(BJ_)                                                                                                          \
     do {                                                                                                                          \
         dim3 grid(g.ny / BJ_, segs, kchunks);                                                                                     \
@@ -392,8 +405,8 @@ static int launch_march(fgb_ctx* ctx, const double* r, const double* p_old, doub
             else k_dsd_march<UPDATE, NP, BJ_, 0, 0><<<grid, threads, 0, ctx->stream>>>(r, p_old, p_new, ctx->ubuf, g, M, cgbeta, beta, gamma, SEG, halo);             \
         }                                                                                                                         \
     } while (0)
-    if (g.ny % 4 == 0) LAUNCH_MARCH(4);
-    else if (g.ny % 2 == 0) LAUNCH_MARCH(2);
+    if (mt.BJ == 4) LAUNCH_MARCH(4);
+    else if (mt.BJ == 2) LAUNCH_MARCH(2);
     else LAUNCH_MARCH(1);
 #undef LAUNCH_MARCH
     FGB_CHECK_LAUNCH(ctx, "k_dsd_march");
@@ -401,9 +414,14 @@ static int launch_march(fgb_ctx* ctx, const double* r, const double* p_old, doub
 }
 
 // eta = E + sym-grad_h u (elasticity), and sum_voxels p:(p - eta) with Voigt weights
+// MODE 0: store eta, sum p:(p - eta).  MODE 1: the sum only (eta stays implicit in u).  MODE 2: the CG update with the implicit eta:
+// x += a p ; r -= a (p - eta) ; sum r:r  (fg:23221, fg:23237, fg:23240) -- eta is re-evaluated with the same expressions (scalar
+// variant, kept for comparison: FGB_CGU_SCALAR; the production kernel is k_cg_update_u6 below).
+template <int MODE>
 __global__ void __launch_bounds__(256) k_eps_dot6(const double* __restrict__ u, double* __restrict__ eta, const double* __restrict__ p,
                                                   GridDev g, Const9f E, double* __restrict__ partials, const double* __restrict__ halo_lo,
-                                                  const double* __restrict__ halo_hi, size_t hslot) {
+                                                  const double* __restrict__ halo_hi, size_t hslot, double* __restrict__ x,
+                                                  double* __restrict__ r, double a) {
     const unsigned nvox = (unsigned)g.lnx * (unsigned)g.ny * (unsigned)g.nz;
     const size_t us = 2 * (size_t)g.unzcs;
     double acc = 0;
@@ -442,9 +460,16 @@ __global__ void __launch_bounds__(256) k_eps_dot6(const double* __restrict__ u, 
         double s = 0;
 #pragma unroll
         for (int d = 0; d < 6; d++) {
-            eta[d * g.plane + eo] = e[d];
             const double pv = __ldg(p + d * g.plane + eo);
-            s += ((d >= 3) ? 2.0 : 1.0) * pv * (pv - e[d]);
+            if (MODE == 2) {
+                x[d * g.plane + eo] = x[d * g.plane + eo] + a * pv;
+                const double rv = r[d * g.plane + eo] + (-a) * (pv - e[d]);
+                r[d * g.plane + eo] = rv;
+                s += ((d >= 3) ? 2.0 : 1.0) * rv * rv;
+            } else {
+                if (MODE == 0) eta[d * g.plane + eo] = e[d];
+                s += ((d >= 3) ? 2.0 : 1.0) * pv * (pv - e[d]);
+            }
         }
         acc += s;
     }
@@ -465,6 +490,7 @@ int fgb_fused_iso_applicable(const fgb_ctx* ctx) {
 
 int fgb_k_dir_stress_div_iso(fgb_ctx* ctx, const double* r, double cgbeta, const double* p_old, double* p_new, double mu0, double lambda0,
                              double alpha) {
+    ctx->implicit_w_of = -1;          // the u buffer is overwritten
     IsoPhases M;
     M.n = ctx->nphases;
     for (int p = 0; p < ctx->nphases; p++) {
@@ -492,7 +518,87 @@ int fgb_k_dir_stress_div_iso(fgb_ctx* ctx, const double* r, double cgbeta, const
     return FGB_OK;
 }
 
-int fgb_k_eps_dot(fgb_ctx* ctx, const double* u, double* eta, const double* Econst, const double* p, double* pAp) {
+// The CG update with the implicit operator result, two voxels (k, k+1) per thread so that x, r and p move as 16-byte accesses:
+//   eta = sym-grad_h u (same expressions as k_eps_dot6) ; x += a p ; r -= a (p - eta) ; sum r:r
+__global__ void __launch_bounds__(256) k_cg_update_u6(const double* __restrict__ u, const double* __restrict__ p, double* __restrict__ x,
+                                                      double* __restrict__ r, double a, GridDev g, Const9f E, double* __restrict__ partials,
+                                                      const double* __restrict__ halo_lo, const double* __restrict__ halo_hi, size_t hslot) {
+    const unsigned nzh = (unsigned)(g.nz + 1) / 2;
+    const unsigned npairs = (unsigned)g.lnx * (unsigned)g.ny * nzh;
+    const size_t us = 2 * (size_t)g.unzcs;
+    const double* u0p = u;
+    const double* u1p = u + g.uplane;
+    const double* u2p = u + 2 * g.uplane;
+    double acc = 0;
+    for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v < npairs; v += gridDim.x * blockDim.x) {
+        const unsigned row_ = v / nzh;
+        const int k = 2 * (int)(v - row_ * nzh);
+        const int i = (int)(row_ / (unsigned)g.ny);
+        const int j = (int)(row_ - (unsigned)i * (unsigned)g.ny);
+        const bool second = k + 1 < g.nz;
+        const int im = (i == 0) ? g.lnx - 1 : i - 1, ip = (i + 1 == g.lnx) ? 0 : i + 1;
+        const int jm = (j == 0) ? g.ny - 1 : j - 1, jp = (j + 1 == g.ny) ? 0 : j + 1;
+        const int km = (k == 0) ? g.nz - 1 : k - 1;
+        const int kp2 = (k + 2 >= g.nz) ? k + 2 - g.nz : k + 2;          // neighbour above the second voxel
+        const size_t o = (size_t)row_ * us + k;
+        const size_t o_im = ((size_t)im * g.ny + j) * us + k, o_ip = ((size_t)ip * g.ny + j) * us + k;
+        const size_t o_jm = ((size_t)i * g.ny + jm) * us + k, o_jp = ((size_t)i * g.ny + jp) * us + k;
+        const size_t oh = (size_t)j * us + k;
+        const bool lo_h = halo_lo != nullptr && i == 0, hi_h = halo_hi != nullptr && i + 1 == g.lnx;
+#define LD2(ptr) (*reinterpret_cast<const double2*>(ptr))
+        // rows are 16-byte aligned and k is even; the element after the last voxel of a row is padding (never used when !second)
+        const double2 u0 = LD2(u0p + o), u1 = LD2(u1p + o), u2 = LD2(u2p + o);
+        const double2 u0_ip = hi_h ? LD2(halo_hi + oh) : LD2(u0p + o_ip);
+        const double2 u1_im = lo_h ? LD2(halo_lo + hslot + oh) : LD2(u1p + o_im);
+        const double2 u2_im = lo_h ? LD2(halo_lo + 2 * hslot + oh) : LD2(u2p + o_im);
+        const double2 u1_jp = LD2(u1p + o_jp), u2_jm = LD2(u2p + o_jm), u0_jm = LD2(u0p + o_jm);
+        const double u0_km = u0p[(size_t)row_ * us + km], u1_km = u1p[(size_t)row_ * us + km];
+        const double u2_kp2 = u2p[(size_t)row_ * us + kp2];
+        double e0[6], e1[6];
+        // first voxel (k): neighbours k-1 -> *_km, k+1 -> .y of the pair (or the wrap when nz == k+1)
+        const double u2_k1 = second ? u2.y : u2p[(size_t)row_ * us];      // u2 at (k+1) mod nz
+        e0[0] = E.v[0] + (u0_ip.x - u0.x) * g.hx;
+        e0[1] = E.v[1] + (u1_jp.x - u1.x) * g.hy;
+        e0[2] = E.v[2] + (u2_k1 - u2.x) * g.hz;
+        e0[3] = E.v[3] + 0.5 * ((u2.x - u2_jm.x) * g.hy + (u1.x - u1_km) * g.hz);
+        e0[4] = E.v[4] + 0.5 * ((u2.x - u2_im.x) * g.hx + (u0.x - u0_km) * g.hz);
+        e0[5] = E.v[5] + 0.5 * ((u1.x - u1_im.x) * g.hx + (u0.x - u0_jm.x) * g.hy);
+        // second voxel (k+1): neighbours k -> .x of the pair, k+2 -> u2_kp2
+        e1[0] = E.v[0] + (u0_ip.y - u0.y) * g.hx;
+        e1[1] = E.v[1] + (u1_jp.y - u1.y) * g.hy;
+        e1[2] = E.v[2] + (u2_kp2 - u2.y) * g.hz;
+        e1[3] = E.v[3] + 0.5 * ((u2.y - u2_jm.y) * g.hy + (u1.y - u1.x) * g.hz);
+        e1[4] = E.v[4] + 0.5 * ((u2.y - u2_im.y) * g.hx + (u0.y - u0.x) * g.hz);
+        e1[5] = E.v[5] + 0.5 * ((u1.y - u1_im.y) * g.hx + (u0.y - u0_jm.y) * g.hy);
+#undef LD2
+        const size_t eo = (size_t)row_ * g.nzp + k;
+        double s0 = 0, s1 = 0;
+#pragma unroll
+        for (int d = 0; d < 6; d++) {
+            const size_t oo = (size_t)d * g.plane + eo;
+            const double2 pv = *reinterpret_cast<const double2*>(p + oo);
+            double2 xv = *reinterpret_cast<double2*>(x + oo);
+            double2 rv = *reinterpret_cast<double2*>(r + oo);
+            xv.x = xv.x + a * pv.x;
+            xv.y = xv.y + a * pv.y;
+            rv.x = rv.x + (-a) * (pv.x - e0[d]);
+            rv.y = rv.y + (-a) * (pv.y - e1[d]);
+            if (!second) { xv.y = 0.0; rv.y = 0.0; }          // padding column: keep it finite (the explicit update leaves garbage here too)
+            *reinterpret_cast<double2*>(x + oo) = xv;
+            *reinterpret_cast<double2*>(r + oo) = rv;
+            const double wgt = (d >= 3) ? 2.0 : 1.0;
+            s0 += wgt * rv.x * rv.x;
+            s1 += wgt * rv.y * rv.y;
+        }
+        acc += s0;
+        if (second) acc += s1;
+    }
+    double vals[1] = {acc};
+    block_reduce_store<1, 0>(vals, partials);
+}
+
+static int eps_dot_launch(fgb_ctx* ctx, int mode, const double* u, double* eta, const double* Econst, const double* p, double* x, double* r,
+                          double a, double* out) {
     const GridDev& g = ctx->g;
     Const9f E;
     for (int i = 0; i < 9; i++) E.v[i] = i < 6 ? Econst[i] : 0.0;
@@ -501,14 +607,43 @@ int fgb_k_eps_dot(fgb_ctx* ctx, const double* u, double* eta, const double* Econ
     if (b > (size_t)ctx->red_blocks) b = ctx->red_blocks;
     const unsigned grid = (unsigned)b;
     {
-        ProfScope ps(ctx, "eps_dot");
+        ProfScope ps(ctx, mode == 2 ? "cg_update" : "eps_dot");
         const double* lo = (ctx->nranks > 1) ? ctx->halo : nullptr;
         const double* hi = (ctx->nranks > 1) ? ctx->halo + 3 * ctx->halo_slot : nullptr;
-        k_eps_dot6<<<grid, 256, 0, ctx->stream>>>(u, eta, p, g, E, ctx->d_partials, lo, hi, ctx->halo_slot);
+        if (mode == 0) k_eps_dot6<0><<<grid, 256, 0, ctx->stream>>>(u, eta, p, g, E, ctx->d_partials, lo, hi, ctx->halo_slot, x, r, a);
+        else if (mode == 1) k_eps_dot6<1><<<grid, 256, 0, ctx->stream>>>(u, eta, p, g, E, ctx->d_partials, lo, hi, ctx->halo_slot, x, r, a);
+        else k_eps_dot6<2><<<grid, 256, 0, ctx->stream>>>(u, eta, p, g, E, ctx->d_partials, lo, hi, ctx->halo_slot, x, r, a);
         FGB_CHECK_LAUNCH(ctx, "k_eps_dot6");
     }
-    int rc = fgb_reduce_finish(ctx, grid, 1, 0, pAp);
+    int rc = fgb_reduce_finish(ctx, grid, 1, 0, out);
     if (rc) return rc;
-    pAp[0] /= (double)g.nx * g.ny * g.nz;
+    out[0] /= (double)g.nx * g.ny * g.nz;
+    return FGB_OK;
+}
+
+// eta == nullptr: eta is not stored (it stays implicit in u for fgb_k_cg_update_implicit)
+int fgb_k_eps_dot(fgb_ctx* ctx, const double* u, double* eta, const double* Econst, const double* p, double* pAp) {
+    return eps_dot_launch(ctx, eta ? 0 : 1, u, eta, Econst, p, nullptr, nullptr, 0.0, pAp);
+}
+
+int fgb_k_cg_update_implicit(fgb_ctx* ctx, const double* u, const double* Econst, double* x, double* r, const double* p, double a, double* delta) {
+    const GridDev& g = ctx->g;
+    if (getenv("FGB_CGU_SCALAR")) return eps_dot_launch(ctx, 2, u, nullptr, Econst, p, x, r, a, delta);
+    Const9f E;
+    for (int i = 0; i < 9; i++) E.v[i] = i < 6 ? Econst[i] : 0.0;
+    const size_t npairs = (size_t)g.lnx * g.ny * ((g.nz + 1) / 2);
+    size_t b = (npairs + 255) / 256;
+    if (b > (size_t)ctx->red_blocks) b = ctx->red_blocks;
+    const unsigned grid = (unsigned)b;
+    {
+        ProfScope ps(ctx, "cg_update");
+        const double* lo = (ctx->nranks > 1) ? ctx->halo : nullptr;
+        const double* hi = (ctx->nranks > 1) ? ctx->halo + 3 * ctx->halo_slot : nullptr;
+        k_cg_update_u6<<<grid, 256, 0, ctx->stream>>>(u, p, x, r, a, g, E, ctx->d_partials, lo, hi, ctx->halo_slot);
+        FGB_CHECK_LAUNCH(ctx, "k_cg_update_u6");
+    }
+    int rc = fgb_reduce_finish(ctx, grid, 1, 0, delta);
+    if (rc) return rc;
+    delta[0] /= (double)g.nx * g.ny * g.nz;
     return FGB_OK;
 }

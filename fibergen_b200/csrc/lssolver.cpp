@@ -660,8 +660,11 @@ void LSSolver::runCGElasticity(const Vec& E0, const Vec& S0) {
     if (_update_ref != "never") calcRefMaterial();
     Vec E = calcBCMean(E0, S0);
     std::unique_ptr<ErrorEstimator> ee(create_error_estimator());
-    const int r = field(_f1), w = field(_f3);
+    const int r = field(_f1);
     int p = field(_f2), p2 = field(_f4);                                                    // direction vector, ping-pong
+    // the operator result w is only consumed by the residual update: on the fused path it is never written to memory
+    // (fgb200.h: FGB_W_IMPLICIT); the exact-residual variant and every other configuration keep the explicit field
+    const int w = (_cg_reinit <= 0 && fgb_cg_implicit_w_supported(_ctx)) ? FGB_W_IMPLICIT : field(_f3);
     check(fgb_set_constant(_ctx, _epsilon, E.data()));
     check(fgb_cg_step(_ctx, -1, -1, 0.0, _epsilon, _epsilon, r, _mu_0, _lambda_0, nullptr)); // krylovOperator(epsilon -> r)
     check(fgb_adjust_residual(_ctx, r, E.data(), _epsilon));

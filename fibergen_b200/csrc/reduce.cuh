@@ -22,25 +22,30 @@ __device__ __forceinline__ double warp_max(double v) {
     return v;
 }
 
-// OP: 0 sum, 1 min, 2 max.  vals[NV] per thread -> partials[blockIdx.x*FGB_RED_MAXV + v]
+// OP: 0 sum, 1 min, 2 max.  vals[NV] per thread -> partials[bid*FGB_RED_MAXV + v] (bid: linear block index);
+// sh: NV*32 doubles of shared memory that no thread of the block still reads
 template <int NV, int OP>
-__device__ __forceinline__ void block_reduce_store(double* vals, double* __restrict__ partials) {
-    __shared__ double sh[NV][32];
+__device__ __forceinline__ void block_reduce_store_sh(double* vals, double* __restrict__ partials, size_t bid, double* sh) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int nw = (blockDim.x + 31) >> 5;
 #pragma unroll
     for (int v = 0; v < NV; v++) {
         double x = vals[v];
         x = (OP == 0) ? warp_sum(x) : (OP == 1 ? warp_min(x) : warp_max(x));
-        if (lane == 0) sh[v][wid] = x;
+        if (lane == 0) sh[v * 32 + wid] = x;
     }
     __syncthreads();
     if (wid == 0) {
 #pragma unroll
         for (int v = 0; v < NV; v++) {
-            double x = (lane < nw) ? sh[v][lane] : (OP == 0 ? 0.0 : (OP == 1 ? INFINITY : -INFINITY));
+            double x = (lane < nw) ? sh[v * 32 + lane] : (OP == 0 ? 0.0 : (OP == 1 ? INFINITY : -INFINITY));
             x = (OP == 0) ? warp_sum(x) : (OP == 1 ? warp_min(x) : warp_max(x));
-            if (lane == 0) partials[(size_t)blockIdx.x * FGB_RED_MAXV + v] = x;
+            if (lane == 0) partials[bid * FGB_RED_MAXV + v] = x;
         }
     }
+}
+template <int NV, int OP>
+__device__ __forceinline__ void block_reduce_store(double* vals, double* __restrict__ partials) {
+    __shared__ double sh[NV * 32];
+    block_reduce_store_sh<NV, OP>(vals, partials, (size_t)blockIdx.x, sh);
 }

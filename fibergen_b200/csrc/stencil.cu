@@ -146,6 +146,7 @@ static void halo_ptrs(fgb_ctx* ctx, const double** lo, const double** hi) {
 }
 
 int fgb_k_div(fgb_ctx* ctx, const double* tau, double* u) {
+    ctx->implicit_w_of = -1;          // the u buffer is overwritten
     const GridDev& g = ctx->g;
     const size_t nvox = (size_t)g.lnx * g.ny * g.nz;
     const double *lo, *hi;

@@ -81,6 +81,7 @@ PROTOTYPES = {
     "fgb_cg_apply": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, c_dp]),
     "fgb_cg_step": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, c_dp]),
     "fgb_cg_update": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, c_dp]),
+    "fgb_cg_implicit_w_supported": (C.c_int, [C.c_void_p]),
     "fgb_cg_direction": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double]),
     "fgb_check_numeric": (C.c_int, [C.c_void_p]),
     "fgb_launch_count": (C.c_uint64, [C.c_void_p]),

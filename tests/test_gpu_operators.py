@@ -336,3 +336,61 @@ def test_general_tiso_and_neohooke2_laws():
         ctx.chk(ctx.lib.fgb_check_numeric(ctx.h))
     assert e.value.code == fb.lib.FGB_ENUMERIC
     ctx.close()
+
+
+@pytest.mark.parametrize("n", [(16, 12, 10), (9, 7, 5), (4, 6, 300)])
+def test_cg_step_explicit_and_implicit_w(n):
+    """fgb_cg_step / fgb_cg_update (runCGElasticity fg:23206-23246): the fused sweeps against the oracle's unfused sequence
+    p = r + beta p (fg:23245), w = krylovOperator(p) (fg:20583), <p, p-w>, x += a p, r -= a (p-w) (fg:23221, fg:23237), and the
+    FGB_W_IMPLICIT form (w never stored) against the explicit one: identical <p, p-w> and x, r equal to rounding (the update
+    re-evaluates w in another kernel, where the compiler may contract multiply-adds differently)."""
+    import ctypes as C
+    rng = np.random.default_rng(5)
+    phi = sphere_phi(n, R=0.3, sub=2)
+    lam1, mu1 = fb.lame(1.0, 0.3)
+    lam2, mu2 = fb.lame(25.0, 0.2)
+    mu0, lam0 = 3.1, 0.0
+    o = fo.LSSolver(*n, mode="elasticity", gamma_scheme="staggered")
+    o.add_phase("matrix", fo.LinearIsotropic(mu1, lam1), 1 - phi)
+    o.add_phase("sphere", fo.LinearIsotropic(mu2, lam2), phi)
+    o.set_reference(mu0, lam0)
+    o.setBCProjector(fo.Id4(6))
+    r0, p0, x0 = (rng.standard_normal((6,) + n) for _ in range(3))
+    beta, a = 0.37, 0.81
+    p1 = r0 + beta * p0
+    w1 = o.krylovOperator(p1)
+    pAp_o = o.innerProduct(p1, p1 - w1)
+    x1 = x0 + a * p1
+    r1 = r0 + (-a) * (p1 - w1)
+    res = {}
+    for implicit in (False, True):
+        ctx = fb.Context(*n, mode="elasticity", gamma_scheme="staggered")
+        ctx.set_phases([1 - phi, phi], [("iso", [mu1, lam1]), ("iso", [mu2, lam2])])
+        assert ctx.lib.fgb_cg_implicit_w_supported(ctx.h) == 1
+        fr, fp, fp2, fx = ctx.field(r0), ctx.field(p0), ctx.field(), ctx.field(x0)
+        fw = -2 if implicit else ctx.field()
+        pAp, delta = C.c_double(), C.c_double()
+        if implicit:
+            # nothing pending yet
+            assert ctx.lib.fgb_cg_update(ctx.h, fx, fr, fp2, -2, a, C.byref(delta)) < 0
+        ctx.chk(ctx.lib.fgb_cg_step(ctx.h, -1, fr, beta, fp, fp2, fw, mu0, lam0, C.byref(pAp)))
+        assert relerr(ctx.download(fp2), p1) < 1e-15
+        if not implicit:
+            assert relerr(ctx.download(fw), w1) < 1e-11
+        assert abs(pAp.value - pAp_o) < 1e-11 * abs(pAp_o)
+        ctx.chk(ctx.lib.fgb_cg_update(ctx.h, fx, fr, fp2, fw, a, C.byref(delta)))
+        res[implicit] = (pAp.value, delta.value, ctx.download(fx), ctx.download(fr))
+        assert relerr(res[implicit][2], x1) < 1e-15
+        assert relerr(res[implicit][3], r1) < 1e-11
+        assert abs(delta.value - o.innerProduct(r1, r1)) < 1e-11 * delta.value
+        if implicit:
+            # the implicit result dies with the u buffer
+            ctx.gamma(fp, np.zeros(6), mu0, lam0)
+            assert ctx.lib.fgb_cg_update(ctx.h, fx, fr, fp2, -2, a, C.byref(delta)) < 0
+            # and is refused where the fused path does not apply (BC projector active / direction update missing)
+            assert ctx.lib.fgb_cg_step(ctx.h, -1, -1, 0.0, fp2, fp2, -2, mu0, lam0, C.byref(pAp)) < 0
+        ctx.close()
+    assert res[False][0] == res[True][0]
+    assert np.array_equal(res[False][2], res[True][2])
+    assert np.abs(res[False][3] - res[True][3]).max() <= 1e-14 * np.abs(res[False][3]).max()
+    assert abs(res[False][1] - res[True][1]) <= 1e-13 * res[False][1]
