@@ -39,6 +39,8 @@ KERNEL_BYTES_PER_VOXEL = {
     "fft_x_green": 2 * 3 * 8, "fft_y_bwd": 2 * 3 * 8, "fft_z_c2r": 2 * 3 * 8, "eps_staggered": (3 + 6) * 8,
     "inner_product": 2 * 6 * 8 + 6 * 8, "cg_update": 6 * 6 * 8, "xpay": 3 * 6 * 8,
     "cg_direction_stress_div": (12 + 1 + 6 + 3) * 8, "stress_div": (6 + 1 + 3) * 8, "eps_dot": (3 + 6 + 6) * 8,
+    # implicit operator result (FGB_W_IMPLICIT): the sum reads u and p only, the update reads x, r, p, u and writes x, r
+    "eps_dot_implicit": (3 + 6) * 8, "cg_update_implicit": (3 * 6 + 3 + 2 * 6) * 8,
 }
 
 
@@ -259,15 +261,19 @@ def run_cuda(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s2.set_strain([1, 0, 0, 0, 0, 0])
     barrier()
+    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     s2.set_phase(0, hp[0], padded=True)            # H2D from pinned memory
     s2.set_phase(1, hp[1], padded=True)
+    ea.record(stream)
     s2.run()
+    eb.record(stream)
     s2.get_field("epsilon", padded=True, out=host_eps.numpy())      # D2H of the solution
     sm = s2.get_mean_stress()
     e1.record(stream)
     barrier()
     e2e_ms = e0.elapsed_time(e1)
+    e2e_parts = {"h2d_ms": e0.elapsed_time(ea), "solve_ms": ea.elapsed_time(eb), "d2h_and_mean_stress_ms": eb.elapsed_time(e1)}
     t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -276,7 +282,7 @@ def run_cuda(args):
     res_last = float(s2.get_residuals()[-1])
     e2e = {"value": nxyz * iters / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(host_phi.numel() * 8 * world / iters),
            "d2h_bytes_per_step": int(host_eps.numel() * 8 * world / iters), "iterations": iters, "ms_total": e2e_ms,
-           "final_residual": res_last, "mean_stress_11": float(sm[0]),
+           "final_residual": res_last, "mean_stress_11": float(sm[0]), "parts": e2e_parts,
            "what": "fgls: set_phase (H2D, pinned) + run() to tol 1e-6 + get_field('epsilon') (D2H) + mean stress"}
     s2.close()
 

@@ -314,119 +314,6 @@ __global__ void __launch_bounds__(Max<R1, R2>::v* T) k_fftx_green_p2(double2* __
     }
 }
 
-// Component-parallel variant for the 3-component staggered operator (KIND 1): the three components of a pencil lane are
-// transformed by three adjacent lanes (a group of 4 lanes, one idle), so a thread holds R2 complex values instead of 3*R2
-// (about 90 registers instead of 255 -> 4x the resident warps).  The Green operator needs all components of a frequency:
-// they are fetched from the two sibling lanes with warp shuffles and every lane computes its own output component.
-template <int N, int R1, int R2, int T>
-__global__ void __launch_bounds__(Max<R1, R2>::v* T * 4) k_fftx_g0_p2c(double2* __restrict__ base, const double2* __restrict__ tw, GreenDev G,
-                                                                       long estride, int ninner, long ostride, long cstride, int jbase,
-                                                                       PencilMap xo, PeerTable pt) {
-    constexpr int TPP = Max<R1, R2>::v;
-    constexpr int NT = TPP * T * 4;
-    extern __shared__ double2 smem[];
-    double2* tw_s = smem;                 // N
-    double2* S = smem + N;                // 3 * N * T
-    const int tid = threadIdx.x;
-    for (int i = tid; i < N; i += NT) tw_s[i] = tw[i];
-    const int c = tid & 3;                // component (3 = idle lane)
-    const int t = (tid >> 2) % T, s = (tid >> 2) / T;
-    const int cc = c < 3 ? c : 0;
-    const int inner = blockIdx.x * T + t;
-    const bool valid = inner < ninner;
-    const bool work = valid && c < 3;
-    double2* g = base + (long)blockIdx.y * ostride + inner + cc * cstride;
-    double2* Sc = S + (size_t)cc * N * T;
-    __syncthreads();
-    if (s < R2 && c < 3) {
-        double2 v[R1];
-#pragma unroll
-        for (int n1 = 0; n1 < R1; n1++) v[n1] = valid ? g[(long)(R2 * n1 + s) * estride] : make_double2(0, 0);
-        p2::pass1<R1, R2, -1>(v, s, tw_s);
-#pragma unroll
-        for (int k1 = 0; k1 < R1; k1++) Sc[(k1 * R2 + s) * T + t] = v[k1];
-    }
-    __syncthreads();
-    double2 w[R2];
-#pragma unroll
-    for (int n2 = 0; n2 < R2; n2++) w[n2] = make_double2(0, 0);
-    if (s < R1 && c < 3) {
-#pragma unroll
-        for (int n2 = 0; n2 < R2; n2++) w[n2] = Sc[(s * R2 + n2) * T + t];
-        p2::RegFFT<R2, -1>::run(w);
-    }
-    // Green operator G0OperatorFourierStaggeredGeneral (fg:19834-19927), one output component per lane
-    {
-        const int lane = tid & 31;
-        const int gbase = lane & ~3;
-        const int jj = jbase + blockIdx.y;
-        const int kk = valid ? inner : 0;
-        const double s1 = __ldg(G.kpm[1] + jj), s2 = __ldg(G.kpm[2] + kk);
-        const double2 kp1 = __ldg(G.kp[1] + jj), kp2 = __ldg(G.kp[2] + kk);
-#pragma unroll
-        for (int k2 = 0; k2 < R2; k2++) {
-            const int ii = (s < R1 ? s : 0) + R1 * k2;
-            double2 f0, f1, f2;
-            f0.x = __shfl_sync(0xffffffffu, w[k2].x, gbase + 0); f0.y = __shfl_sync(0xffffffffu, w[k2].y, gbase + 0);
-            f1.x = __shfl_sync(0xffffffffu, w[k2].x, gbase + 1); f1.y = __shfl_sync(0xffffffffu, w[k2].y, gbase + 1);
-            f2.x = __shfl_sync(0xffffffffu, w[k2].x, gbase + 2); f2.y = __shfl_sync(0xffffffffu, w[k2].y, gbase + 2);
-            const double s0 = __ldg(G.kpm[0] + ii);
-            const double2 kp0 = __ldg(G.kp[0] + ii);
-            const double norm = s0 * s0 + s1 * s1 + s2 * s2;
-            const double c1 = G.c10 / norm;
-            const double c2 = G.c20 / (norm * norm);
-            const double2 fkp = cadd(cadd(cmul(f0, kp0), cmul(f1, kp1)), cmul(f2, kp2));
-            const double2 c2fkp = cscale(c2, fkp);
-            const double2 kpc = (cc == 0) ? kp0 : (cc == 1 ? kp1 : kp2);
-            double2 eta = cadd(cscale(c1, w[k2]), cmul(c2fkp, make_double2(-kpc.x, kpc.y)));
-            if (ii == 0 && jj == 0 && kk == 0) eta = make_double2(cc == 0 ? G.dc[0] : (cc == 1 ? G.dc[1] : G.dc[2]), 0.0);
-            w[k2] = eta;
-        }
-    }
-    if (s < R1 && c < 3) {
-        p2::RegFFT<R2, +1>::run(w);
-#pragma unroll
-        for (int na = 1; na < R2; na++) {
-            double2 tws = tw_s[s * na];
-            tws.y = -tws.y;
-            w[na] = p2::pmul(w[na], tws);
-        }
-    }
-    __syncthreads();
-    if (s < R1 && c < 3) {
-#pragma unroll
-        for (int na = 0; na < R2; na++) Sc[(na * R1 + s) * T + t] = w[na];
-    }
-    __syncthreads();
-    if (s < R2 && c < 3) {
-        double2 v[R1];
-#pragma unroll
-        for (int k1 = 0; k1 < R1; k1++) v[k1] = Sc[(s * R1 + k1) * T + t];
-        p2::RegFFT<R1, +1>::run(v);
-        if (work) {
-#pragma unroll
-            for (int nb = 0; nb < R1; nb++) {
-                const int e = s + R2 * nb;
-                double2* b = pt.n ? pt.p[e / xo.seglen] : base;
-                b[cc * xo.cstride + (long)blockIdx.y * xo.ostride + inner + xo.at(e)] = v[nb];
-            }
-        }
-    }
-}
-
-template <int N, int R1, int R2, int T>
-static int launch_xg_p2c(fgb_ctx* ctx, double2* base, const GreenDev& G, long estride, int ninner, int nouter, long ostride, long cstride,
-                         int jbase, const PencilMap& xo, const PeerTable& pt) {
-    constexpr int NT = Max<R1, R2>::v * T * 4;
-    const size_t smem = (size_t)(N + (size_t)3 * N * T) * sizeof(double2);
-    if (smem > ctx->smem_optin) return -1;
-    dim3 grid((ninner + T - 1) / T, nouter, 1);
-    FGB_CUDA(ctx, set_smem(k_fftx_g0_p2c<N, R1, R2, T>, smem));
-    k_fftx_g0_p2c<N, R1, R2, T><<<grid, NT, smem, ctx->stream>>>(base, ctx->plan[0].tw, G, estride, ninner, ostride, cstride, jbase, xo, pt);
-    FGB_CHECK_LAUNCH(ctx, "k_fftx_g0_p2c");
-    return FGB_OK;
-}
-
 // =================================================================================================
 // three-pass power-of-two kernels (N = 512, 1024): fft_pow2_3.cuh
 // =================================================================================================
@@ -813,18 +700,6 @@ static int launch_x_green(fgb_ctx* ctx, double2* base, const GreenDev& G, long e
     const int nx = ctx->g.nx;
     int rc = -1;
     // register budget: NC*R2 complex per thread -> the fast path covers NC <= 3 (staggered / heat); larger tensors use the generic kernel
-    if constexpr (NC == 3 && KIND == 1) {
-        if (getenv("FGB_XG_V2")) {
-            switch (nx) {
-                case 64: rc = launch_xg_p2c<64, 8, 8, 8>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt); break;
-                case 128: rc = launch_xg_p2c<128, 16, 8, 8>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt); break;
-                case 256: rc = launch_xg_p2c<256, 16, 16, 8>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt); break;
-                case 512: rc = launch_xg_p2c<512, 32, 16, 4>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt); break;
-                case 1024: rc = launch_xg_p2c<1024, 32, 32, 2>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt); break;
-            }
-            if (rc != -1) return rc;
-        }
-    }
     // three-pass kernels: NC*R3 complex values per thread, so every tensor rank stays in registers.  They carry nx = 512 / 1024 for
     // all operators and the 6- and 9-component (collocated) operators at every power of two; the 1- and 3-component operators at
     // nx <= 256 are faster with the two-pass kernel below.
@@ -847,13 +722,7 @@ static int launch_x_green(fgb_ctx* ctx, double2* base, const GreenDev& G, long e
         switch (nx) {
             case 64: rc = launch_xg_p2<64, 8, 8, NC, KIND, 8>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt); break;
             case 128: rc = launch_xg_p2<128, 16, 8, NC, KIND, 8>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt); break;
-            case 256: {
-                const char* tsel = getenv("FGB_XG_T");
-                const int tt = tsel ? atoi(tsel) : 8;
-                if (tt == 16) rc = launch_xg_p2<256, 16, 16, NC, KIND, 16>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt);
-                else if (tt == 4) rc = launch_xg_p2<256, 16, 16, NC, KIND, 4>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt);
-                else rc = launch_xg_p2<256, 16, 16, NC, KIND, 8>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt);
-            } break;
+            case 256: rc = launch_xg_p2<256, 16, 16, NC, KIND, 8>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt); break;
             case 512: rc = launch_xg_p2<512, 32, 16, NC, KIND, 4>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt); break;
             case 1024: if constexpr (NC == 1) rc = launch_xg_p2<1024, 32, 32, NC, KIND, 2>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt); break;
         }

@@ -518,8 +518,9 @@ int fgb_k_dir_stress_div_iso(fgb_ctx* ctx, const double* r, double cgbeta, const
     return FGB_OK;
 }
 
-// The CG update with the implicit operator result, two voxels (k, k+1) per thread so that x, r and p move as 16-byte accesses:
-//   eta = sym-grad_h u (same expressions as k_eps_dot6) ; x += a p ; r -= a (p - eta) ; sum r:r
+// The two sweeps of the implicit-operator-result form, two voxels (k, k+1) per thread so that x, r and p move as 16-byte accesses:
+//   eta = sym-grad_h u (same expressions as k_eps_dot6);  DOT_ONLY: sum p:(p - eta);  else: x += a p ; r -= a (p - eta) ; sum r:r
+template <int DOT_ONLY>
 __global__ void __launch_bounds__(256) k_cg_update_u6(const double* __restrict__ u, const double* __restrict__ p, double* __restrict__ x,
                                                       double* __restrict__ r, double a, GridDev g, Const9f E, double* __restrict__ partials,
                                                       const double* __restrict__ halo_lo, const double* __restrict__ halo_hi, size_t hslot) {
@@ -577,6 +578,12 @@ __global__ void __launch_bounds__(256) k_cg_update_u6(const double* __restrict__
         for (int d = 0; d < 6; d++) {
             const size_t oo = (size_t)d * g.plane + eo;
             const double2 pv = *reinterpret_cast<const double2*>(p + oo);
+            const double wgt = (d >= 3) ? 2.0 : 1.0;
+            if (DOT_ONLY) {
+                s0 += wgt * pv.x * (pv.x - e0[d]);
+                s1 += wgt * pv.y * (pv.y - e1[d]);
+                continue;
+            }
             double2 xv = *reinterpret_cast<double2*>(x + oo);
             double2 rv = *reinterpret_cast<double2*>(r + oo);
             xv.x = xv.x + a * pv.x;
@@ -586,7 +593,6 @@ __global__ void __launch_bounds__(256) k_cg_update_u6(const double* __restrict__
             if (!second) { xv.y = 0.0; rv.y = 0.0; }          // padding column: keep it finite (the explicit update leaves garbage here too)
             *reinterpret_cast<double2*>(x + oo) = xv;
             *reinterpret_cast<double2*>(r + oo) = rv;
-            const double wgt = (d >= 3) ? 2.0 : 1.0;
             s0 += wgt * rv.x * rv.x;
             s1 += wgt * rv.y * rv.y;
         }
@@ -607,7 +613,7 @@ static int eps_dot_launch(fgb_ctx* ctx, int mode, const double* u, double* eta, 
     if (b > (size_t)ctx->red_blocks) b = ctx->red_blocks;
     const unsigned grid = (unsigned)b;
     {
-        ProfScope ps(ctx, mode == 2 ? "cg_update" : "eps_dot");
+        ProfScope ps(ctx, mode == 2 ? "cg_update_implicit" : (mode == 1 ? "eps_dot_implicit" : "eps_dot"));
         const double* lo = (ctx->nranks > 1) ? ctx->halo : nullptr;
         const double* hi = (ctx->nranks > 1) ? ctx->halo + 3 * ctx->halo_slot : nullptr;
         if (mode == 0) k_eps_dot6<0><<<grid, 256, 0, ctx->stream>>>(u, eta, p, g, E, ctx->d_partials, lo, hi, ctx->halo_slot, x, r, a);
@@ -622,13 +628,16 @@ static int eps_dot_launch(fgb_ctx* ctx, int mode, const double* u, double* eta, 
 }
 
 // eta == nullptr: eta is not stored (it stays implicit in u for fgb_k_cg_update_implicit)
+static int implicit_sweep(fgb_ctx* ctx, bool dot_only, const double* u, const double* Econst, double* x, double* r, const double* p, double a,
+                          double* out);
 int fgb_k_eps_dot(fgb_ctx* ctx, const double* u, double* eta, const double* Econst, const double* p, double* pAp) {
+    if (!eta && !getenv("FGB_CGU_SCALAR")) return implicit_sweep(ctx, true, u, Econst, nullptr, nullptr, p, 0.0, pAp);
     return eps_dot_launch(ctx, eta ? 0 : 1, u, eta, Econst, p, nullptr, nullptr, 0.0, pAp);
 }
 
-int fgb_k_cg_update_implicit(fgb_ctx* ctx, const double* u, const double* Econst, double* x, double* r, const double* p, double a, double* delta) {
+static int implicit_sweep(fgb_ctx* ctx, bool dot_only, const double* u, const double* Econst, double* x, double* r, const double* p, double a,
+                          double* out) {
     const GridDev& g = ctx->g;
-    if (getenv("FGB_CGU_SCALAR")) return eps_dot_launch(ctx, 2, u, nullptr, Econst, p, x, r, a, delta);
     Const9f E;
     for (int i = 0; i < 9; i++) E.v[i] = i < 6 ? Econst[i] : 0.0;
     const size_t npairs = (size_t)g.lnx * g.ny * ((g.nz + 1) / 2);
@@ -636,14 +645,20 @@ int fgb_k_cg_update_implicit(fgb_ctx* ctx, const double* u, const double* Econst
     if (b > (size_t)ctx->red_blocks) b = ctx->red_blocks;
     const unsigned grid = (unsigned)b;
     {
-        ProfScope ps(ctx, "cg_update");
+        ProfScope ps(ctx, dot_only ? "eps_dot_implicit" : "cg_update_implicit");
         const double* lo = (ctx->nranks > 1) ? ctx->halo : nullptr;
         const double* hi = (ctx->nranks > 1) ? ctx->halo + 3 * ctx->halo_slot : nullptr;
-        k_cg_update_u6<<<grid, 256, 0, ctx->stream>>>(u, p, x, r, a, g, E, ctx->d_partials, lo, hi, ctx->halo_slot);
+        if (dot_only) k_cg_update_u6<1><<<grid, 256, 0, ctx->stream>>>(u, p, x, r, a, g, E, ctx->d_partials, lo, hi, ctx->halo_slot);
+        else k_cg_update_u6<0><<<grid, 256, 0, ctx->stream>>>(u, p, x, r, a, g, E, ctx->d_partials, lo, hi, ctx->halo_slot);
         FGB_CHECK_LAUNCH(ctx, "k_cg_update_u6");
     }
-    int rc = fgb_reduce_finish(ctx, grid, 1, 0, delta);
+    int rc = fgb_reduce_finish(ctx, grid, 1, 0, out);
     if (rc) return rc;
-    delta[0] /= (double)g.nx * g.ny * g.nz;
+    out[0] /= (double)g.nx * g.ny * g.nz;
     return FGB_OK;
+}
+
+int fgb_k_cg_update_implicit(fgb_ctx* ctx, const double* u, const double* Econst, double* x, double* r, const double* p, double a, double* delta) {
+    if (getenv("FGB_CGU_SCALAR")) return eps_dot_launch(ctx, 2, u, nullptr, Econst, p, x, r, a, delta);
+    return implicit_sweep(ctx, false, u, Econst, x, r, p, a, delta);
 }

@@ -342,7 +342,7 @@ def test_general_tiso_and_neohooke2_laws():
 def test_cg_step_explicit_and_implicit_w(n):
     """fgb_cg_step / fgb_cg_update (runCGElasticity fg:23206-23246): the fused sweeps against the oracle's unfused sequence
     p = r + beta p (fg:23245), w = krylovOperator(p) (fg:20583), <p, p-w>, x += a p, r -= a (p-w) (fg:23221, fg:23237), and the
-    FGB_W_IMPLICIT form (w never stored) against the explicit one: identical <p, p-w> and x, r equal to rounding (the update
+    FGB_W_IMPLICIT form (w never stored) against the explicit one: the same <p, p-w>, x and r up to rounding (the update
     re-evaluates w in another kernel, where the compiler may contract multiply-adds differently)."""
     import ctypes as C
     rng = np.random.default_rng(5)
@@ -390,7 +390,7 @@ def test_cg_step_explicit_and_implicit_w(n):
             # and is refused where the fused path does not apply (BC projector active / direction update missing)
             assert ctx.lib.fgb_cg_step(ctx.h, -1, -1, 0.0, fp2, fp2, -2, mu0, lam0, C.byref(pAp)) < 0
         ctx.close()
-    assert res[False][0] == res[True][0]
+    assert abs(res[False][0] - res[True][0]) <= 1e-13 * abs(res[False][0])
     assert np.array_equal(res[False][2], res[True][2])
     assert np.abs(res[False][3] - res[True][3]).max() <= 1e-14 * np.abs(res[False][3]).max()
     assert abs(res[False][1] - res[True][1]) <= 1e-13 * res[False][1]
