@@ -256,10 +256,18 @@ def run_cuda(args):
     s.close()
 
     # ---------------- end to end: host phase planes in, strain field out, complete solve ----------------
-    s2 = make_solver(tol=1e-6, maxiter=args.e2e_maxiter)
+    # A fresh solver pays one-time costs on its first run (field allocation, peer-memory mapping, NCCL connection set-up) that a
+    # user amortises over the load cases of one job (calc_effective_properties runs 6): warm the solver with a 3-iteration run,
+    # then time a complete cold-data solve: phase planes from pinned host memory in, converged strain field out.
+    s2 = make_solver(tol=1e-6, maxiter=3)
     s2.lib.fgb_set_stream(s2.ctx(), stream.cuda_stream)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s2.set_strain([1, 0, 0, 0, 0, 0])
+    s2.set_phase(0, hp[0], padded=True)
+    s2.set_phase(1, hp[1], padded=True)
+    s2.run()
+    s2.get_field("epsilon", padded=True, out=host_eps.numpy())
+    s2.set("maxiter", args.e2e_maxiter)
     barrier()
     ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -283,7 +291,7 @@ def run_cuda(args):
     e2e = {"value": nxyz * iters / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(host_phi.numel() * 8 * world / iters),
            "d2h_bytes_per_step": int(host_eps.numel() * 8 * world / iters), "iterations": iters, "ms_total": e2e_ms,
            "final_residual": res_last, "mean_stress_11": float(sm[0]), "parts": e2e_parts,
-           "what": "fgls: set_phase (H2D, pinned) + run() to tol 1e-6 + get_field('epsilon') (D2H) + mean stress"}
+           "what": "fgls (warm solver): set_phase (H2D, pinned) + run() to tol 1e-6 + get_field('epsilon') (D2H) + mean stress"}
     s2.close()
 
     # ---------------- CPU baseline: the oracle port on this host, bounded sample ----------------

@@ -407,6 +407,11 @@ extern "C" int fgb_mean_energy(fgb_ctx* c, int f, double* out) {
     int rc = fgb_k_mean_energy(c, c->fields[f], out);
     return rc ? rc : poll_flag(c);
 }
+extern "C" int fgb_mean_cauchy(fgb_ctx* c, int f, double alpha, double* out) {
+    CHECK_CTX(c); CHECK_FIELD(c, f);
+    int rc = fgb_k_mean_cauchy(c, c->fields[f], alpha, out);
+    return rc ? rc : poll_flag(c);
+}
 extern "C" int fgb_min_detF(fgb_ctx* c, int f, double* out) { CHECK_CTX(c); CHECK_FIELD(c, f); return fgb_k_min_detF(c, c->fields[f], out); }
 extern "C" int fgb_ref_material(fgb_ctx* c, int f, int zt, double* lmin, double* lmax) {
     CHECK_CTX(c); CHECK_FIELD(c, f);
@@ -458,11 +463,11 @@ static int bc_term(fgb_ctx* c, const double* tau, double* R) {
     return FGB_OK;
 }
 
-static int green_args(fgb_ctx* c, GreenArgs& ga, double mu0, double lambda0, double alpha, double beta) {
+static int green_args(fgb_ctx* c, GreenArgs& ga, double mu0, double lambda0, double alpha, double beta, bool staggered) {
     memset(&ga, 0, sizeof(ga));
     ga.beta = beta;
     ga.freq_hack = c->freq_hack;
-    if (c->scheme == FGB_GAMMA_STAGGERED) {
+    if (staggered) {
         if (c->dim == 3) { ga.kind = 2; ga.c10 = -alpha / (2 * mu0); }                                              // fg:19758-19763
         else if (c->dim == 6) { ga.kind = 1; ga.c10 = -alpha / mu0; ga.c20 = -alpha / (mu0 * (1 + mu0 / (lambda0 + mu0))); }   // fg:19749-19755
         else { ga.kind = 1; ga.c10 = -alpha / (2 * mu0); ga.c20 = -alpha / (2 * mu0 * (1 + 2 * mu0 / lambda0)); }  // fg:19768-19774
@@ -474,10 +479,18 @@ static int green_args(fgb_ctx* c, GreenArgs& ga, double mu0, double lambda0, dou
     return FGB_OK;
 }
 
+// the displacement buffer exists from the start in staggered contexts; collocated contexts get it on first use of a
+// staggered-grid operator (get_raw_field('u') always uses them, fg:15517-15557)
+static int ensure_ubuf(fgb_ctx* c) {
+    if (c->ubuf) return FGB_OK;
+    FGB_CUDA(c, cudaMalloc(&c->ubuf, sizeof(double) * c->g.uplane * c->udim));
+    return FGB_OK;
+}
+
 // G0OperatorStaggered* (fg:20101-20153) on the u buffer
 static int g0_staggered(fgb_ctx* c, double mu0, double lambda0, double alpha) {
     GreenArgs ga;
-    green_args(c, ga, mu0, lambda0, alpha, 0.0);
+    green_args(c, ga, mu0, lambda0, alpha, 0.0, true);
     int rc;
     const FftLayout lay = {c->g.unzcs};
     c->implicit_w_of = -1;
@@ -507,7 +520,7 @@ static int gamma_impl(fgb_ctx* c, double* field, const double* E, double mu0, do
         return fgb_k_eps(c, c->ubuf, field, Ec);
     }
     GreenArgs ga;                                                                   // GammaOperatorCollocated* fg:20302-20340
-    green_args(c, ga, mu0, lambda0, alpha, beta);
+    green_args(c, ga, mu0, lambda0, alpha, beta, false);
     for (int i = 0; i < c->dim; i++) ga.dc[i] = Ec[i];
     const FftLayout lay = {c->g.nzc};
     if ((rc = fgb_fft_z_forward(c, field, c->dim, lay))) return rc;
@@ -541,26 +554,47 @@ extern "C" int fgb_gamma(fgb_ctx* c, int f, const double* E, double mu0, double 
 
 extern "C" int fgb_div_staggered(fgb_ctx* c, int f) {
     CHECK_CTX(c); CHECK_FIELD(c, f);
-    if (!c->ubuf) return fgb_fail(c, FGB_EINVAL, "context was not created with the staggered scheme");
+    if (int rcu = ensure_ubuf(c)) return rcu;
     int rc;
     if (c->nranks > 1 && (rc = fgb_comm_halo_tau(c, c->fields[f]))) return rc;
     return fgb_k_div(c, c->fields[f], c->ubuf);
 }
 extern "C" int fgb_g0_staggered(fgb_ctx* c, double mu0, double lambda0, double alpha) {
     CHECK_CTX(c);
-    if (!c->ubuf) return fgb_fail(c, FGB_EINVAL, "context was not created with the staggered scheme");
+    if (int rcu = ensure_ubuf(c)) return rcu;
     return g0_staggered(c, mu0, lambda0, alpha);
+}
+// get_raw_field('u') fg:15517-15557: u = G0 div_h tau(eps) into the u buffer (read it with fgb_u_download)
+extern "C" int fgb_calc_displacement(fgb_ctx* c, int eps, int tmp, double mu0, double lambda0) {
+    CHECK_CTX(c); CHECK_FIELD(c, eps); CHECK_FIELD(c, tmp);
+    if (eps == tmp) return fgb_fail(c, FGB_EINVAL, "fgb_calc_displacement needs a scratch field different from the strain field");
+    int rc = ensure_ubuf(c);
+    if (rc) return rc;
+    double m = mu0, l = lambda0, a = 1.0;
+    if (c->mode == FGB_MODE_VISCOSITY) {
+        if ((rc = fgb_k_calc_stress(c, c->fields[eps], c->fields[tmp], mu0, lambda0, 1.0))) return rc;      // calcStressDiff fg:18030
+        m = 1 / (4 * mu0); l = INFINITY; a = 1 / (2 * mu0);                                                // fg:15535
+    } else if (c->mode == FGB_MODE_HYPERELASTICITY) {
+        if ((rc = fgb_k_calc_stress(c, c->fields[eps], c->fields[tmp], mu0, lambda0, 1.0))) return rc;
+    } else {
+        if ((rc = fgb_k_calc_stress_const(c, c->fields[eps], c->fields[tmp], mu0, lambda0))) return rc;    // fg:17973
+    }
+    if ((rc = poll_flag(c))) return rc;
+    if (c->nranks > 1 && (rc = fgb_comm_halo_tau(c, c->fields[tmp]))) return rc;
+    if ((rc = fgb_k_div(c, c->fields[tmp], c->ubuf))) return rc;
+    return g0_staggered(c, m, l, a);
 }
 extern "C" int fgb_eps_staggered(fgb_ctx* c, int f, const double* E) {
     CHECK_CTX(c); CHECK_FIELD(c, f);
-    if (!c->ubuf) return fgb_fail(c, FGB_EINVAL, "context was not created with the staggered scheme");
+    if (int rcu = ensure_ubuf(c)) return rcu;
     int rc;
     if (c->nranks > 1 && (rc = fgb_comm_halo_u(c))) return rc;
     return fgb_k_eps(c, c->ubuf, c->fields[f], E);
 }
 extern "C" int fgb_u_upload(fgb_ctx* c, const double* const* comps, int n) {
     CHECK_CTX(c);
-    if (!c->ubuf || n != c->udim) return fgb_fail(c, FGB_EINVAL, "u buffer has %d components", c->udim);
+    if (int rcu = ensure_ubuf(c)) return rcu;
+    if (n != c->udim) return fgb_fail(c, FGB_EINVAL, "u buffer has %d components", c->udim);
     c->implicit_w_of = -1;
     for (int d = 0; d < n; d++)
         FGB_CUDA(c, cudaMemcpy2DAsync(c->ubuf + (size_t)d * c->g.uplane, sizeof(double) * 2 * c->g.unzcs, comps[d], sizeof(double) * c->g.nzp,
@@ -570,7 +604,8 @@ extern "C" int fgb_u_upload(fgb_ctx* c, const double* const* comps, int n) {
 }
 extern "C" int fgb_u_download(fgb_ctx* c, double* const* comps, int n) {
     CHECK_CTX(c);
-    if (!c->ubuf || n != c->udim) return fgb_fail(c, FGB_EINVAL, "u buffer has %d components", c->udim);
+    if (int rcu = ensure_ubuf(c)) return rcu;
+    if (n != c->udim) return fgb_fail(c, FGB_EINVAL, "u buffer has %d components", c->udim);
     for (int d = 0; d < n; d++)
         FGB_CUDA(c, cudaMemcpy2DAsync(comps[d], sizeof(double) * c->g.nzp, c->ubuf + (size_t)d * c->g.uplane, sizeof(double) * 2 * c->g.unzcs,
                                       sizeof(double) * c->g.nzp, (size_t)c->g.lnx * c->g.ny, cudaMemcpyDeviceToHost, c->stream));

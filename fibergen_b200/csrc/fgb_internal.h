@@ -205,6 +205,7 @@ int fgb_k_calc_stress_deriv(fgb_ctx* ctx, const double* F, const double* W, doub
 int fgb_k_calc_polarization(fgb_ctx* ctx, const double* src, double* dst, double mu0, int inv);
 int fgb_k_mean_pk1(fgb_ctx* ctx, const double* src, double alpha, double* out);
 int fgb_k_mean_energy(fgb_ctx* ctx, const double* src, double* out);
+int fgb_k_mean_cauchy(fgb_ctx* ctx, const double* src, double alpha, double* out);
 int fgb_k_min_detF(fgb_ctx* ctx, const double* src, double* out);
 int fgb_k_ref_material(fgb_ctx* ctx, const double* src, int zero_trace, double* lmin, double* lmax);
 

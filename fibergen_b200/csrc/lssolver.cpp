@@ -492,6 +492,11 @@ Vec LSSolver::calcMeanStrain() {
     check(fgb_average(_ctx, _epsilon, out.data()));
     return out;
 }
+Vec LSSolver::calcMeanCauchyStress() {
+    Vec out(9);
+    check(fgb_mean_cauchy(_ctx, _epsilon, 1.0, out.data()));
+    return out;
+}
 double LSSolver::calcMeanEnergy() {
     double w = 0;
     check(fgb_mean_energy(_ctx, _epsilon, &w));
@@ -780,9 +785,23 @@ Mat LSSolver::calcEffectiveProperties() {
     return C;
 }
 
+int LSSolver::fieldComponents(const std::string& name) const {
+    if (name == "epsilon" || name == "sigma") return _dim;
+    if (name == "u") return _dim == 3 ? 1 : 3;
+    return -1;
+}
+
 void LSSolver::getField(const std::string& name, double* const* comps) {
+    // get_raw_field fg:15396-15557: derived fields are evaluated on the device from the converged strain field
     if (name == "epsilon") check(fgb_field_download(_ctx, _epsilon, comps));
-    else fail("Unknown field '" + name + "'");
+    else if (name == "sigma") {                                                             // calcStress(epsilon, sigma) fg:15500
+        const int t = field(_f5);
+        check(fgb_calc_stress(_ctx, _epsilon, t, 0.0, 0.0, 1.0));
+        check(fgb_field_download(_ctx, t, comps));
+    } else if (name == "u") {                                                               // fg:15517-15557
+        check(fgb_calc_displacement(_ctx, _epsilon, field(_f5), _mu_0, _lambda_0));
+        check(fgb_u_download(_ctx, comps, fieldComponents(name)));
+    } else fail("Unknown field '" + name + "'");
 }
 
 int LSSolver::localNx() const { return fgb_local_nx(_ctx); }
@@ -860,6 +879,8 @@ int fgls_get_residuals(const fgls_solver* h, double* out, int n) {
 int fgls_mean_stress(fgls_solver* h, double* out) { FGLS_TRY(fgb::Vec v = h->s->calcMeanStress(); std::copy(v.begin(), v.end(), out)) }
 int fgls_mean_strain(fgls_solver* h, double* out) { FGLS_TRY(fgb::Vec v = h->s->calcMeanStrain(); std::copy(v.begin(), v.end(), out)) }
 int fgls_mean_energy(fgls_solver* h, double* out) { FGLS_TRY(*out = h->s->calcMeanEnergy()) }
+int fgls_mean_cauchy_stress(fgls_solver* h, double* out) { FGLS_TRY(fgb::Vec v = h->s->calcMeanCauchyStress(); std::copy(v.begin(), v.end(), out)) }
+int fgls_field_components(fgls_solver* h, const char* name) { return h ? h->s->fieldComponents(name) : -1; }
 int fgls_effective_properties(fgls_solver* h, double* C) { FGLS_TRY(fgb::Mat m = h->s->calcEffectiveProperties(); std::copy(m.begin(), m.end(), C)) }
 int fgls_get_field(fgls_solver* h, const char* name, double* const* comps) { FGLS_TRY(h->s->getField(name, comps)) }
 int fgls_ref_material(fgls_solver* h, double* mu0, double* lambda0) { FGLS_TRY(*mu0 = h->s->mu0(); *lambda0 = h->s->lambda0()) }

@@ -186,6 +186,29 @@ __global__ void __launch_bounds__(256) k_mean_pk1(const double* __restrict__ src
     block_reduce_store<D, 0>(s, partials);
 }
 
+// mean Cauchy stress: sigma = P(F) F^T / det F per voxel (Cauchy fg:10326-10346, meanCauchy fg:12268-12308); 9 components
+__global__ void __launch_bounds__(256) k_mean_cauchy(const double* __restrict__ src, GridDev g, MaterialDev M, double alpha,
+                                                     double* __restrict__ partials, int* flag) {
+    // stored component order as a matrix (fg:9262-9276)
+    const int IDX[3][3] = {{0, 5, 4}, {8, 1, 3}, {7, 6, 2}};
+    double s[9];
+#pragma unroll
+    for (int d = 0; d < 9; d++) s[d] = 0;
+    VOXEL_LOOP(g) {
+        VOXEL_OFFSET(g)
+        double F[9], P[9];
+#pragma unroll
+        for (int d = 0; d < 9; d++) F[d] = src[(size_t)d * g.plane + o];
+        const double c = 1.0 / det9(F);
+        Mixed<9>::PK1(M, o, F, c * alpha, P, flag);
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) s[IDX[i][j]] += P[IDX[i][0]] * F[IDX[j][0]] + P[IDX[i][1]] * F[IDX[j][1]] + P[IDX[i][2]] * F[IDX[j][2]];
+    }
+    block_reduce_store<9, 0>(s, partials);
+}
+
 template <int D>
 __global__ void __launch_bounds__(256) k_mean_energy(const double* __restrict__ src, GridDev g, MaterialDev M,
                                                      double* __restrict__ partials, int* flag) {
@@ -362,6 +385,22 @@ int fgb_k_mean_pk1(fgb_ctx* ctx, const double* src, double alpha, double* out) {
         FGB_CHECK_LAUNCH(ctx, "k_mean_pk1");
     }
     return fgb_reduce_finish(ctx, grid, ctx->dim, 0, out);
+}
+
+int fgb_k_mean_cauchy(fgb_ctx* ctx, const double* src, double alpha, double* out) {
+    int rc = check_material(ctx);
+    if (rc) return rc;
+    if (ctx->dim != 9) return fgb_fail(ctx, FGB_EINVAL, "the Cauchy stress needs the 9-component deformation gradient (hyperelasticity)");
+    const MaterialDev M = fgb_material_dev(ctx);
+    const size_t nvox = (size_t)ctx->g.lnx * ctx->g.ny * ctx->g.nz;
+    const double a = alpha / ((double)ctx->g.nx * ctx->g.ny * ctx->g.nz);               // fg:12274
+    const unsigned grid = grid_for(ctx, nvox, 256);
+    {
+        ProfScope ps(ctx, "mean_cauchy");
+        k_mean_cauchy<<<grid, 256, 0, ctx->stream>>>(src, ctx->g, M, a, ctx->d_partials, ctx->d_flag);
+        FGB_CHECK_LAUNCH(ctx, "k_mean_cauchy");
+    }
+    return fgb_reduce_finish(ctx, grid, 9, 0, out);
 }
 
 int fgb_k_mean_energy(fgb_ctx* ctx, const double* src, double* out) {

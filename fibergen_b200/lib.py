@@ -63,6 +63,8 @@ PROTOTYPES = {
     "fgb_mean_pk1": (C.c_int, [C.c_void_p, C.c_int, C.c_double, c_dp]),
     "fgb_mean_energy": (C.c_int, [C.c_void_p, C.c_int, c_dp]),
     "fgb_min_detF": (C.c_int, [C.c_void_p, C.c_int, c_dp]),
+    "fgb_mean_cauchy": (C.c_int, [C.c_void_p, C.c_int, C.c_double, c_dp]),
+    "fgb_calc_displacement": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double]),
     "fgb_ref_material": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_dp, c_dp]),
     "fgb_calc_stress": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]),
     "fgb_calc_stress_deriv": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]),
@@ -113,6 +115,8 @@ PROTOTYPES = {
     "fgls_mean_stress": (C.c_int, [C.c_void_p, c_dp]),
     "fgls_mean_strain": (C.c_int, [C.c_void_p, c_dp]),
     "fgls_mean_energy": (C.c_int, [C.c_void_p, c_dp]),
+    "fgls_mean_cauchy_stress": (C.c_int, [C.c_void_p, c_dp]),
+    "fgls_field_components": (C.c_int, [C.c_void_p, C.c_char_p]),
     "fgls_effective_properties": (C.c_int, [C.c_void_p, c_dp]),
     "fgls_get_field": (C.c_int, [C.c_void_p, C.c_char_p, c_dpp]),
     "fgls_ref_material": (C.c_int, [C.c_void_p, c_dp, c_dp]),

@@ -317,11 +317,20 @@ class LSSolver:
         return out.reshape(self.dim, self.dim)
 
     def get_field(self, name="epsilon", padded=False, out=None):
+        """get_raw_field fg:15396: "epsilon", "sigma" (dim planes) or "u" (3 planes, 1 for heat)"""
+        ncomp = self.lib.fgls_field_components(self.h, name.encode())
+        if ncomp < 0:
+            raise L.FgbError(-1, "Unknown field '%s'" % name)
         if out is None:
-            out = np.empty((self.dim, self.lnx, self.ny, self.nzp))
+            out = np.empty((ncomp, self.lnx, self.ny, self.nzp))
         ptrs, keep = _planes(out)
         self.chk(self.lib.fgls_get_field(self.h, name.encode(), ptrs))
         return keep if padded else unpad(keep, self.nz)
+
+    def get_mean_cauchy_stress(self):
+        out = np.zeros(9)
+        self.chk(self.lib.fgls_mean_cauchy_stress(self.h, _dp(out)))
+        return out
 
     def ref_material(self):
         a, b = C.c_double(), C.c_double()

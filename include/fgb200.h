@@ -138,6 +138,8 @@ int  fgb_component_dot(fgb_ctx* ctx, int a, int b, double* out_dim);            
 int  fgb_mean_pk1(fgb_ctx* ctx, int field, double alpha, double* out_dim);       /* meanPK1 fg:12312        */
 int  fgb_mean_energy(fgb_ctx* ctx, int field, double* out);                      /* meanW fg:12239          */
 int  fgb_min_detF(fgb_ctx* ctx, int field, double* out);                         /* calcMinDetF fg:17871    */
+/* mean Cauchy stress <P(F) F^T / det F> * alpha, 9 components (hyperelasticity): meanCauchy fg:12268, Cauchy fg:10326 */
+int  fgb_mean_cauchy(fgb_ctx* ctx, int field, double alpha, double* out9);
 /* getRefMaterial (fg:12153-12236): min/max eigenvalue of the tangent over all voxels */
 int  fgb_ref_material(fgb_ctx* ctx, int field, int zero_trace, double* lmin, double* lmax);
 
@@ -162,6 +164,10 @@ int  fgb_gamma(fgb_ctx* ctx, int field, const double* E, double mu0, double lamb
 int  fgb_div_staggered(fgb_ctx* ctx, int field);                                 /* divOperatorStaggered* fg:18853-19071: field -> u buffer */
 int  fgb_g0_staggered(fgb_ctx* ctx, double mu0, double lambda0, double alpha);   /* G0OperatorStaggered* fg:20101-20153 on the u buffer     */
 int  fgb_eps_staggered(fgb_ctx* ctx, int field, const double* E);                /* epsOperatorStaggered* fg:18614-18846: u buffer -> field */
+/* displacement fluctuation of a strain field, get_raw_field("u") fg:15517-15557: u = G0 div_h tau(eps) with tau = C0:eps
+ * (elasticity, heat), (P - C0):F (hyperelasticity) or the viscosity dual form; always the staggered-grid operators, alpha = 1.
+ * tmp is a scratch field (overwritten); the result is left in the u buffer (fgb_u_download: 3 components, 1 for heat). */
+int  fgb_calc_displacement(fgb_ctx* ctx, int eps, int tmp, double mu0, double lambda0);
 int  fgb_u_upload(fgb_ctx* ctx, const double* const* comps, int ncomp);          /* test access to the displacement buffer */
 int  fgb_u_download(fgb_ctx* ctx, double* const* comps, int ncomp);
 /* fftTensor / fftInvTensor (fg:18531-18584) on all components of a field, in place (forward scaled by 1/nxyz) */

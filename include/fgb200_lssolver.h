@@ -66,8 +66,10 @@ public:
     Vec    calcMeanStress();                                                         // fg:17793
     Vec    calcMeanStrain();                                                         // _epsilon->average()
     double calcMeanEnergy();                                                         // fg:17765
+    Vec    calcMeanCauchyStress();                                                   // fg:17920 (hyperelasticity)
     Mat    calcEffectiveProperties();                                                // fg:26030-26160 (Voigt form)
-    void   getField(const std::string& name, double* const* comps);                 // get_raw_field fg:15396 ("epsilon")
+    void   getField(const std::string& name, double* const* comps);                 // get_raw_field fg:15396: "epsilon", "sigma", "u"
+    int    fieldComponents(const std::string& name) const;                          // planes getField(name) writes
     double mu0() const { return _mu_0; }
     double lambda0() const { return _lambda_0; }
     int    dim() const { return _dim; }
@@ -167,6 +169,8 @@ int  fgls_get_residuals(const fgls_solver* s, double* out, int n);
 int  fgls_mean_stress(fgls_solver* s, double* out);
 int  fgls_mean_strain(fgls_solver* s, double* out);
 int  fgls_mean_energy(fgls_solver* s, double* out);
+int  fgls_mean_cauchy_stress(fgls_solver* s, double* out9);
+int  fgls_field_components(fgls_solver* s, const char* name);      /* planes fgls_get_field writes; < 0: unknown field */
 int  fgls_effective_properties(fgls_solver* s, double* Ceff_voigt);            /* dim x dim row-major */
 int  fgls_get_field(fgls_solver* s, const char* name, double* const* comps);
 int  fgls_ref_material(fgls_solver* s, double* mu0, double* lambda0);

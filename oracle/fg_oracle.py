@@ -1087,6 +1087,34 @@ class LSSolver:
         eps = self.epsilon if eps is None else eps
         return float(np.sum(self.mat.W(eps))) / self.nxyz
 
+    def calcMeanCauchyStress(self, eps=None):
+        """fg:17920-17941 -> meanCauchy fg:12268-12308 -> Cauchy fg:10326-10346: per voxel sigma = P(F) F^T / det F with the mixed
+        law's PK1, averaged over the voxels (hyperelasticity, 9 components)"""
+        eps = self.epsilon if eps is None else eps
+        if self.dim != 9:
+            raise RuntimeError("oracle: Cauchy stress needs the 9-component deformation gradient")
+        F = mat33(eps.reshape(9, -1))                                   # (n, 3, 3)
+        c = 1.0 / np.linalg.det(F)
+        P = mat33(self.mat.PK1(eps, 1.0).reshape(9, -1)) * (c / self.nxyz)[:, None, None]
+        return vec9(np.einsum('nik,njk->nij', P, F)).sum(axis=1)
+
+    def calcDisplacement(self, eps=None):
+        """get_raw_field('u') fg:15517-15557: the displacement fluctuation u = G0 div_h tau of the converged field, tau = C0:eps
+        (elasticity, heat: calcStressConst fg:17973), (P - C0):F (hyperelasticity: calcStressDiff fg:18030), always with the
+        staggered-grid operators and alpha = 1; viscosity uses the dual reference 1/(4 mu0), lambda0 = inf, alpha = 1/(2 mu0)"""
+        eps = self.epsilon if eps is None else eps
+        if self.mode == "viscosity":
+            tau = self.calcStressDiff(eps)
+            m, l, a = 1 / (4 * self.mu_0), math.inf, 1 / (2 * self.mu_0)
+        elif self.mode == "hyperelasticity":
+            tau = self.calcStressDiff(eps)
+            m, l, a = self.mu_0, self.lambda_0, 1.0
+        else:
+            tau = self.calcStressConst(self.mu_0, self.lambda_0, eps)
+            m, l, a = self.mu_0, self.lambda_0, 1.0
+        f = self.divOperatorStaggered(tau)
+        return self.ifft(self.G0OperatorFourierStaggered(m, l, self.fft(f), a))
+
     # -- FFT wrappers (fg:18481-18584): forward scaled 1/nxyz, backward unscaled ---------
     def fft(self, x):
         return sfft.rfftn(x, axes=(-3, -2, -1), norm="forward", workers=FFT_WORKERS)

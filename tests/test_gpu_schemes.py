@@ -12,6 +12,7 @@ pytestmark = pytest.mark.gpu
 
 RES_RTOL = 1e-10
 EFF_RTOL = 1e-9
+FIELD_RTOL = 1e-8      # per-voxel derived fields (stress, displacement) of a strain field that agrees to 1e-9
 
 
 def build_pair(n, L=(1., 1., 1.), mode="elasticity", phases=None, normals=None, **kw):
@@ -51,6 +52,16 @@ def compare(s, o, E=None, S=None, P=None):
     assert np.abs(sm - om).max() <= EFF_RTOL * np.abs(om).max()
     assert np.abs(s.get_field() - o.epsilon).max() <= 1e-9 * max(np.abs(o.epsilon).max(), 1e-300)
     assert abs(s.ref_material()[0] - o.mu_0) <= 1e-12 * abs(o.mu_0)
+    # derived fields of the converged solution, evaluated on the device (get_raw_field fg:15496-15557)
+    sig_o = o.calcStress(0.0, 0.0, o.epsilon)
+    assert np.abs(s.get_field("sigma") - sig_o).max() <= FIELD_RTOL * np.abs(sig_o).max()
+    u_o = o.calcDisplacement()
+    u_s = s.get_field("u")
+    assert u_s.shape == u_o.shape
+    assert np.abs(u_s - u_o).max() <= FIELD_RTOL * max(np.abs(u_o).max(), 1e-300)
+    if o.dim == 9:
+        c_o = o.calcMeanCauchyStress()
+        assert np.abs(s.get_mean_cauchy_stress() - c_o).max() <= EFF_RTOL * np.abs(c_o).max()
     return rs
 
 
