@@ -221,10 +221,11 @@ int fgb_reduce_reserve(fgb_ctx* ctx, size_t nblocks) {
 int fgb_reduce_finish(fgb_ctx* ctx, int nblocks, int nvals, int op, double* host_out) {
     k_reduce_finish<<<nvals, 256, 0, ctx->stream>>>(ctx->d_partials, nblocks, nvals, op, ctx->d_result);
     FGB_CHECK_LAUNCH(ctx, "k_reduce_finish");
+    // slab partition: the per-rank results are gathered on the device and combined in rank order (one host synchronisation)
+    if (ctx->nranks > 1) return fgb_allreduce_host(ctx, host_out, nvals, op);
     FGB_CUDA(ctx, cudaMemcpyAsync(ctx->h_result, ctx->d_result, sizeof(double) * nvals, cudaMemcpyDeviceToHost, ctx->stream));
     FGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < nvals; i++) host_out[i] = ctx->h_result[i];
-    if (ctx->nranks > 1) return fgb_allreduce_host(ctx, host_out, nvals, op);
     return FGB_OK;
 }
 

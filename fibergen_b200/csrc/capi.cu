@@ -134,6 +134,8 @@ extern "C" int fgb_create(fgb_ctx** out, int nx, int ny, int nz, double Lx, doub
     c->d_partials = nullptr; c->d_result = nullptr; c->h_result = nullptr; c->d_scalars = nullptr; c->d_flag = nullptr; c->h_flag = nullptr;
     c->nccl_comm = nullptr; c->nccl_lib = nullptr; c->sbuf = nullptr; c->xbuf = nullptr; c->xbuf_comps = 0; c->xbuf_nzcs = 0;
     c->halo = nullptr; c->halo_slot = 0; c->d_gather = nullptr; c->visc_tmp = nullptr; c->p2p = false; c->iso_halo = nullptr; c->phi_halo_valid = false;
+    c->halo_base = nullptr; c->iso_set = 0; c->halo_seq = c->iso_seq = 0;
+    for (int q = 0; q < 8; q++) c->peer_halo[q] = nullptr;
     c->launches = 0; c->profiling = false;
     c->bc_active = false; c->bc_relax = 1.0;
     for (int i = 0; i < 81; i++) c->bc_MQ[i] = c->bc_MQC0[i] = 0;

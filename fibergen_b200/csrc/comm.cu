@@ -96,14 +96,15 @@ static int comm_barrier(fgb_ctx* ctx) {
 static int map_peers(fgb_ctx* ctx) {
     ctx->p2p = false;
     const int P = ctx->nranks, me = ctx->rank;
-    for (int q = 0; q < 8; q++) ctx->peer_xbuf[q] = ctx->peer_sbuf[q] = nullptr;
+    for (int q = 0; q < 8; q++) ctx->peer_xbuf[q] = ctx->peer_sbuf[q] = ctx->peer_halo[q] = nullptr;
     if (P > 8) return FGB_OK;
-    struct Handles { cudaIpcMemHandle_t x, s; double ok; };
+    struct Handles { cudaIpcMemHandle_t x, s, h; double ok; };
     static_assert(sizeof(Handles) % 8 == 0, "handle record must be a multiple of 8 bytes");
     Handles mine;
     memset(&mine, 0, sizeof(mine));
     bool ok = getenv("FGB_NO_P2P") == nullptr;
-    if (ok) ok = cudaIpcGetMemHandle(&mine.x, ctx->xbuf) == cudaSuccess && cudaIpcGetMemHandle(&mine.s, ctx->sbuf) == cudaSuccess;
+    if (ok) ok = cudaIpcGetMemHandle(&mine.x, ctx->xbuf) == cudaSuccess && cudaIpcGetMemHandle(&mine.s, ctx->sbuf) == cudaSuccess &&
+                 cudaIpcGetMemHandle(&mine.h, ctx->halo_base) == cudaSuccess;
     cudaGetLastError();
     mine.ok = ok ? 1.0 : 0.0;
     Handles* d_all = nullptr;
@@ -118,12 +119,14 @@ static int map_peers(fgb_ctx* ctx) {
     for (int q = 0; q < P; q++) ok = ok && all[q].ok == 1.0;
     if (ok) {
         for (int q = 0; q < P && ok; q++) {
-            if (q == me) { ctx->peer_xbuf[q] = ctx->xbuf; ctx->peer_sbuf[q] = ctx->sbuf; continue; }
-            void *px = nullptr, *psb = nullptr;
+            if (q == me) { ctx->peer_xbuf[q] = ctx->xbuf; ctx->peer_sbuf[q] = ctx->sbuf; ctx->peer_halo[q] = ctx->halo_base; continue; }
+            void *px = nullptr, *psb = nullptr, *ph = nullptr;
             ok = cudaIpcOpenMemHandle(&px, all[q].x, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess &&
-                 cudaIpcOpenMemHandle(&psb, all[q].s, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+                 cudaIpcOpenMemHandle(&psb, all[q].s, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess &&
+                 cudaIpcOpenMemHandle(&ph, all[q].h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
             ctx->peer_xbuf[q] = (double*)px;
             ctx->peer_sbuf[q] = (double*)psb;
+            ctx->peer_halo[q] = (double*)ph;
         }
         cudaGetLastError();
     }
@@ -165,7 +168,13 @@ extern "C" int fgb_comm_init(fgb_ctx* ctx, const void* id128) {
     // halo slots: a full x plane of one component in either layout
     size_t a = (size_t)g.ny * g.nzp, b = (size_t)g.ny * 2 * g.unzcs;
     ctx->halo_slot = a > b ? a : b;
-    FGB_CUDA(ctx, cudaMalloc(&ctx->halo, sizeof(double) * 6 * ctx->halo_slot));
+    // two alternating sets of each halo buffer (an exchange may start while a neighbour still reads the previous one)
+    ctx->iso_set = a * (10 + 2 * FGB_MAX_PHASES);
+    FGB_CUDA(ctx, cudaMalloc(&ctx->halo_base, sizeof(double) * 2 * (6 * ctx->halo_slot + ctx->iso_set)));
+    ctx->halo = ctx->halo_base;
+    ctx->iso_halo = ctx->halo_base + 12 * ctx->halo_slot;
+    ctx->halo_seq = ctx->iso_seq = 0;
+    ctx->phi_halo_valid = false;
     FGB_CUDA(ctx, cudaMalloc(&ctx->d_gather, sizeof(double) * 64 * ctx->nranks));
     // transposition buffers are allocated once (their addresses are exported to the peers)
     const bool stag = ctx->scheme == FGB_GAMMA_STAGGERED;
@@ -181,13 +190,13 @@ int fgb_comm_free(fgb_ctx* ctx) {
             if (q != ctx->rank) {
                 if (ctx->peer_xbuf[q]) cudaIpcCloseMemHandle(ctx->peer_xbuf[q]);
                 if (ctx->peer_sbuf[q]) cudaIpcCloseMemHandle(ctx->peer_sbuf[q]);
+                if (ctx->peer_halo[q]) cudaIpcCloseMemHandle(ctx->peer_halo[q]);
             }
     ctx->p2p = false;
     if (ctx->sbuf) cudaFree(ctx->sbuf);
     if (ctx->xbuf) cudaFree(ctx->xbuf);
-    if (ctx->halo) cudaFree(ctx->halo);
-    if (ctx->iso_halo) cudaFree(ctx->iso_halo);
-    ctx->iso_halo = nullptr;
+    if (ctx->halo_base) cudaFree(ctx->halo_base);
+    ctx->halo_base = ctx->iso_halo = nullptr;
     if (ctx->d_gather) cudaFree(ctx->d_gather);
     ctx->sbuf = ctx->xbuf = ctx->halo = ctx->d_gather = nullptr;
     return FGB_OK;
@@ -284,6 +293,29 @@ int fgb_comm_fft_x(fgb_ctx* ctx, double* base, int ncomp, const FftLayout& lay, 
     return FGB_OK;
 }
 
+// Direct halo push over peer memory: one kernel copies this rank's boundary planes straight into the neighbours' halo buffers
+// (16-byte accesses), followed by one stream-ordered barrier -- instead of ~20 grouped ncclSend/ncclRecv operations.
+struct HaloJobs {
+    int n;
+    const double* src[20];
+    double* dst[20];
+};
+__global__ void __launch_bounds__(256) k_halo_push(HaloJobs J, size_t n2) {
+    const double2* s = reinterpret_cast<const double2*>(J.src[blockIdx.y]);
+    double2* d = reinterpret_cast<double2*>(J.dst[blockIdx.y]);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) d[i] = s[i];
+}
+static int halo_push(fgb_ctx* ctx, const HaloJobs& J, size_t plane_elems) {
+    if (J.n == 0) return comm_barrier(ctx);
+    const size_t n2 = plane_elems / 2;
+    unsigned gx = (unsigned)((n2 + 255) / 256);
+    if (gx > 64) gx = 64;
+    dim3 grid(gx, J.n);
+    k_halo_push<<<grid, 256, 0, ctx->stream>>>(J, n2);
+    FGB_CHECK_LAUNCH(ctx, "k_halo_push");
+    return comm_barrier(ctx);
+}
+
 // neighbour planes: lo slot s <- plane lnx-1 of lo_src[s] on the left rank, hi slot s <- plane 0 of hi_src[s] on the right rank
 static int halo_exchange(fgb_ctx* ctx, const double* const* lo_src, int nlo, const double* const* hi_src, int nhi, size_t plane_elems,
                          size_t comp_stride_unused) {
@@ -294,9 +326,23 @@ static int halo_exchange(fgb_ctx* ctx, const double* const* lo_src, int nlo, con
     const int P = ctx->nranks, me = ctx->rank;
     const int left = (me - 1 + P) % P, right = (me + 1) % P;
     const GridDev& g = ctx->g;
+    // alternate between the two halo sets
+    const bool push = ctx->p2p && (plane_elems % 2) == 0 && !getenv("FGB_HALO_NCCL");
+    const size_t set_off = push ? (size_t)(ctx->halo_seq++ & 1u) * 6 * ctx->halo_slot : 0;
+    ctx->halo = ctx->halo_base + set_off;
     double* lo = ctx->halo;
     double* hi = ctx->halo + 3 * ctx->halo_slot;
     ProfScope ps(ctx, "halo_exchange");
+    if (push) {
+        HaloJobs J;
+        J.n = 0;
+        for (int s = 0; s < nhi; s++) { J.src[J.n] = hi_src[s]; J.dst[J.n++] = ctx->peer_halo[left] + set_off + (3 + s) * ctx->halo_slot; }
+        for (int s = 0; s < nlo; s++) {
+            J.src[J.n] = lo_src[s] + (size_t)(g.lnx - 1) * plane_elems;
+            J.dst[J.n++] = ctx->peer_halo[right] + set_off + s * ctx->halo_slot;
+        }
+        return halo_push(ctx, J, plane_elems);
+    }
     FGB_NCCL(ctx, g_nccl.GroupStart());
     // my first planes go to the left rank (its hi halo); my last planes go to the right rank (its lo halo)
     for (int s = 0; s < nhi; s++) FGB_NCCL(ctx, g_nccl.Send(hi_src[s], plane_elems, ncclDouble, left, comm, ctx->stream));
@@ -361,10 +407,9 @@ int fgb_comm_halo_iso(fgb_ctx* ctx, const double* r, const double* p_old) {
     const int P = ctx->nranks, me = ctx->rank, NPH = ctx->nphases;
     const int left = (me - 1 + P) % P, right = (me + 1) % P;
     const size_t pe = (size_t)g.ny * g.nzp;
-    if (!ctx->iso_halo) {
-        FGB_CUDA(ctx, cudaMalloc(&ctx->iso_halo, sizeof(double) * pe * (10 + 2 * FGB_MAX_PHASES)));
-        ctx->phi_halo_valid = false;
-    }
+    const bool push = ctx->p2p && !getenv("FGB_HALO_NCCL");
+    const size_t iso_off = 12 * ctx->halo_slot + (push ? (size_t)(ctx->iso_seq++ & 1u) * ctx->iso_set : 0);
+    ctx->iso_halo = ctx->halo_base + iso_off;
     double* H = ctx->iso_halo;
     double* r_lo = H;            double* p_lo = H + 3 * pe;
     double* r_hi = H + 6 * pe;   double* p_hi = H + 8 * pe;
@@ -372,6 +417,40 @@ int fgb_comm_halo_iso(fgb_ctx* ctx, const double* r, const double* p_old) {
     const size_t last = (size_t)(g.lnx - 1) * pe;
     static const int lo_c[3] = {0, 1, 2}, hi_c[2] = {5, 4};
     ProfScope ps(ctx, "halo_exchange");
+    // the phase fractions do not change between exchanges: they are sent once, into both sets
+    const bool send_phi = !ctx->phi_halo_valid;
+    if (push) {
+        HaloJobs J;
+        J.n = 0;
+        double* L = ctx->peer_halo[left] + iso_off;       // the left rank's current set: my first planes are its hi halo
+        double* R = ctx->peer_halo[right] + iso_off;      // the right rank's current set: my last planes are its lo halo
+        for (int s = 0; s < 2; s++) {
+            if (r) { J.src[J.n] = r + (size_t)hi_c[s] * g.plane; J.dst[J.n++] = L + (6 + s) * pe; }
+            J.src[J.n] = p_old + (size_t)hi_c[s] * g.plane; J.dst[J.n++] = L + (8 + s) * pe;
+        }
+        for (int s = 0; s < 3; s++) {
+            if (r) { J.src[J.n] = r + (size_t)lo_c[s] * g.plane + last; J.dst[J.n++] = R + s * pe; }
+            J.src[J.n] = p_old + (size_t)lo_c[s] * g.plane + last; J.dst[J.n++] = R + (3 + s) * pe;
+        }
+        if (send_phi) {
+            // separate launch (job table size): both sets of both neighbours
+            HaloJobs Jp;
+            Jp.n = 0;
+            for (int set = 0; set < 2; set++) {
+                double* Ls = ctx->peer_halo[left] + 12 * ctx->halo_slot + (size_t)set * ctx->iso_set;
+                double* Rs = ctx->peer_halo[right] + 12 * ctx->halo_slot + (size_t)set * ctx->iso_set;
+                for (int q = 0; q < NPH; q++) {
+                    Jp.src[Jp.n] = ctx->phi[q]; Jp.dst[Jp.n++] = Ls + (10 + FGB_MAX_PHASES + q) * pe;
+                    Jp.src[Jp.n] = ctx->phi[q] + last; Jp.dst[Jp.n++] = Rs + (10 + q) * pe;
+                }
+            }
+            if (Jp.n > 20) return fgb_fail(ctx, FGB_EUNSUPPORTED, "too many phases for the halo push");
+            k_halo_push<<<dim3(64, Jp.n), 256, 0, ctx->stream>>>(Jp, pe / 2);
+            FGB_CHECK_LAUNCH(ctx, "k_halo_push");
+            ctx->phi_halo_valid = true;
+        }
+        return halo_push(ctx, J, pe);
+    }
     FGB_NCCL(ctx, g_nccl.GroupStart());
     // sends: first planes (components 5,4 [+phi]) to the left rank, last planes (components 0,1,2 [+phi]) to the right rank
     for (int s = 0; s < 2; s++) {

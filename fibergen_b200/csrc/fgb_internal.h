@@ -108,6 +108,10 @@ struct fgb_ctx {
     bool phi_halo_valid;
     bool p2p;                   // peer buffers mapped: transposes are written by the FFT kernels straight into peer memory
     double* peer_xbuf[8];       // xbuf of every rank (own pointer at [rank])
+    double* halo_base;            // one allocation: [halo set 0][halo set 1][iso set 0][iso set 1]; halo / iso_halo point at the current set
+    double* peer_halo[8];         // halo_base of every rank (CUDA IPC), for the direct halo push
+    size_t iso_set;               // doubles per iso-halo set
+    unsigned halo_seq, iso_seq;   // exchange counters (set = seq & 1)
     double* peer_sbuf[8];
 
     // mixed boundary conditions (fgb_set_bc): row-major dim x dim matrices MQ and M:(QC0)
