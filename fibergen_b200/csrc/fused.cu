@@ -170,8 +170,10 @@ __global__ void __launch_bounds__(256) k_dir_stress_div_iso(const double* __rest
 // x-marching version of the fused sweep.  A thread owns one k column of BJ consecutive y rows and walks along x:
 //   * y neighbours (tau_1 at j-1, tau_5 / tau_3 at j+1) are its own registers (plus one halo row on either side),
 //   * the previous x plane's tau_0 and the next x plane's tau_5 / tau_4 (with its phi) are carried in registers,
-//   * z neighbours come from the adjacent lanes by warp shuffle (direct evaluation at warp / chunk edges),
-// so every r, p_old and phi value of the CTA's own rows is loaded exactly once; no shared memory, no barriers.
+//   * z neighbours are exchanged through a double-buffered shared-memory row (one barrier per plane),
+// so every r, p_old and phi value of the CTA's own rows is loaded exactly once.
+// (Tried and rejected on B200: software L2 prefetch of the next plane, 0.67 -> 0.81 ms; selecting halo planes by pointer
+// instead of by branch, 0.64 -> 0.67 ms.)
 template <int NP>
 __device__ __forceinline__ void phi_load(const IsoPhases& M, size_t o, double* phi) {
 #pragma unroll

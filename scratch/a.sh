@@ -1,2 +1,7 @@
 cd /root/repo
-timeout 1500 python -m pytest tests/test_gpu_schemes.py -m gpu -x -q --tb=short 2>&1 | tail -15
+timeout 900 python -m pytest tests/test_gpu_schemes.py -m gpu -x -q -k "cg_staggered" 2>&1 | tail -2
+for v in "" "FGB_MARCH_PF=1"; do
+env $v timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --e2e-maxiter 100 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('$v',d['ms_per_step'], d['value'], d['e2e']['value'], d['e2e']['parts'], {k:round(x['avg_ms'],3) for k,x in d['kernels'].items()})"
+done
