@@ -5,6 +5,22 @@
 #include "fgb_internal.h"
 #include "reduce.cuh"
 
+unsigned fgb_wave_grid(fgb_ctx* ctx, const void* kernel, int block, size_t n, size_t cap) {
+    size_t b = (n + block - 1) / block;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    auto it = ctx->occupancy.find(kernel);
+    int occ;
+    if (it == ctx->occupancy.end()) {
+        occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, 0) != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 0; }
+        ctx->occupancy[kernel] = occ;
+    } else occ = it->second;
+    const size_t wave = (size_t)occ * ctx->sm_count;
+    if (wave > 0 && b > wave) b = (b / wave) * wave;
+    return (unsigned)b;
+}
+
 static unsigned grid_for(const fgb_ctx* ctx, size_t n, int block) {
     size_t b = (n + block - 1) / block;
     size_t cap = (size_t)ctx->red_blocks;
@@ -295,7 +311,9 @@ int fgb_k_calc_stress_const(fgb_ctx* ctx, const double* src, double* dst, double
 static size_t npairs_of(const fgb_ctx* ctx) { return (size_t)ctx->g.lnx * ctx->g.ny * ((ctx->g.nz + 1) / 2); }
 
 int fgb_k_inner(fgb_ctx* ctx, const double* a, const double* b, const double* c, double* out) {
-    const unsigned grid = grid_for(ctx, npairs_of(ctx), 256);
+    const void* kp = (c ? (ctx->dim == 3 ? (const void*)k_inner<3, 1> : ctx->dim == 6 ? (const void*)k_inner<6, 1> : (const void*)k_inner<9, 1>)
+                        : (ctx->dim == 3 ? (const void*)k_inner<3, 0> : ctx->dim == 6 ? (const void*)k_inner<6, 0> : (const void*)k_inner<9, 0>));
+    const unsigned grid = fgb_wave_grid(ctx, kp, 256, npairs_of(ctx), ctx->red_blocks);
     {
         ProfScope ps(ctx, "inner_product");
         if (c) {
@@ -316,7 +334,9 @@ int fgb_k_inner(fgb_ctx* ctx, const double* a, const double* b, const double* c,
 }
 
 int fgb_k_component_dot(fgb_ctx* ctx, const double* a, const double* b, double* out, int mean_only) {
-    const unsigned grid = grid_for(ctx, npairs_of(ctx), 256);
+    const void* kp = (mean_only ? (ctx->dim == 3 ? (const void*)k_component_dot<3, 1> : ctx->dim == 6 ? (const void*)k_component_dot<6, 1> : (const void*)k_component_dot<9, 1>)
+                           : (ctx->dim == 3 ? (const void*)k_component_dot<3, 0> : ctx->dim == 6 ? (const void*)k_component_dot<6, 0> : (const void*)k_component_dot<9, 0>));
+    const unsigned grid = fgb_wave_grid(ctx, kp, 256, npairs_of(ctx), ctx->red_blocks);
     {
         ProfScope ps(ctx, "component_dot");
         if (mean_only) {
@@ -337,7 +357,8 @@ int fgb_k_component_dot(fgb_ctx* ctx, const double* a, const double* b, double* 
 }
 
 int fgb_k_cg_update(fgb_ctx* ctx, double* x, double* r, const double* p, const double* w, double a, double* delta) {
-    const unsigned grid = grid_for(ctx, npairs_of(ctx), 256);
+    const void* kp = ctx->dim == 3 ? (const void*)k_cg_update<3> : ctx->dim == 6 ? (const void*)k_cg_update<6> : (const void*)k_cg_update<9>;
+    const unsigned grid = fgb_wave_grid(ctx, kp, 256, npairs_of(ctx), ctx->red_blocks);
     {
         ProfScope ps(ctx, "cg_update");
         DISPATCH_D(ctx, (k_cg_update<3><<<grid, 256, 0, ctx->stream>>>(x, r, p, w, a, ctx->g, ctx->d_partials)),

@@ -611,9 +611,8 @@ static int eps_dot_launch(fgb_ctx* ctx, int mode, const double* u, double* eta, 
     Const9f E;
     for (int i = 0; i < 9; i++) E.v[i] = i < 6 ? Econst[i] : 0.0;
     const size_t nvox = (size_t)g.lnx * g.ny * g.nz;
-    size_t b = (nvox + 255) / 256;
-    if (b > (size_t)ctx->red_blocks) b = ctx->red_blocks;
-    const unsigned grid = (unsigned)b;
+    const void* kp = mode == 0 ? (const void*)k_eps_dot6<0> : mode == 1 ? (const void*)k_eps_dot6<1> : (const void*)k_eps_dot6<2>;
+    const unsigned grid = fgb_wave_grid(ctx, kp, 256, nvox, ctx->red_blocks);
     {
         ProfScope ps(ctx, mode == 2 ? "cg_update_implicit" : (mode == 1 ? "eps_dot_implicit" : "eps_dot"));
         const double* lo = (ctx->nranks > 1) ? ctx->halo : nullptr;
@@ -643,9 +642,7 @@ static int implicit_sweep(fgb_ctx* ctx, bool dot_only, const double* u, const do
     Const9f E;
     for (int i = 0; i < 9; i++) E.v[i] = i < 6 ? Econst[i] : 0.0;
     const size_t npairs = (size_t)g.lnx * g.ny * ((g.nz + 1) / 2);
-    size_t b = (npairs + 255) / 256;
-    if (b > (size_t)ctx->red_blocks) b = ctx->red_blocks;
-    const unsigned grid = (unsigned)b;
+    const unsigned grid = fgb_wave_grid(ctx, dot_only ? (const void*)k_cg_update_u6<1> : (const void*)k_cg_update_u6<0>, 256, npairs, ctx->red_blocks);
     {
         ProfScope ps(ctx, dot_only ? "eps_dot_implicit" : "cg_update_implicit");
         const double* lo = (ctx->nranks > 1) ? ctx->halo : nullptr;

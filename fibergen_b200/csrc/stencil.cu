@@ -126,13 +126,6 @@ __global__ void __launch_bounds__(256) k_eps(const double* __restrict__ u, doubl
     }
 }
 
-static unsigned grid_for(const fgb_ctx* ctx, size_t n, int block) {
-    size_t b = (n + block - 1) / block;
-    size_t cap = (size_t)ctx->sm_count * 16;
-    if (b > cap) b = cap;
-    if (b < 1) b = 1;
-    return (unsigned)b;
-}
 
 // halo layout is owned by comm.cu: ctx->halo = [3 lo slots][3 hi slots], each slot ctx->halo_slot doubles
 static void halo_ptrs(fgb_ctx* ctx, const double** lo, const double** hi) {
@@ -152,7 +145,8 @@ int fgb_k_div(fgb_ctx* ctx, const double* tau, double* u) {
     const double *lo, *hi;
     halo_ptrs(ctx, &lo, &hi);
     ProfScope ps(ctx, "div_staggered");
-    const unsigned grid = grid_for(ctx, nvox, 256);
+    const void* kp = ctx->dim == 3 ? (const void*)k_div<3> : ctx->dim == 6 ? (const void*)k_div<6> : (const void*)k_div<9>;
+    const unsigned grid = fgb_wave_grid(ctx, kp, 256, nvox, (size_t)ctx->sm_count * 16);
     if (ctx->dim == 3) k_div<3><<<grid, 256, 0, ctx->stream>>>(tau, u, g, lo, hi, ctx->halo_slot);
     else if (ctx->dim == 6) k_div<6><<<grid, 256, 0, ctx->stream>>>(tau, u, g, lo, hi, ctx->halo_slot);
     else k_div<9><<<grid, 256, 0, ctx->stream>>>(tau, u, g, lo, hi, ctx->halo_slot);
@@ -168,7 +162,8 @@ int fgb_k_eps(fgb_ctx* ctx, const double* u, double* eta, const double* Econst) 
     const double *lo, *hi;
     halo_ptrs(ctx, &lo, &hi);
     ProfScope ps(ctx, "eps_staggered");
-    const unsigned grid = grid_for(ctx, nvox, 256);
+    const void* kp = ctx->dim == 3 ? (const void*)k_eps<3> : ctx->dim == 6 ? (const void*)k_eps<6> : (const void*)k_eps<9>;
+    const unsigned grid = fgb_wave_grid(ctx, kp, 256, nvox, (size_t)ctx->sm_count * 16);
     if (ctx->dim == 3) k_eps<3><<<grid, 256, 0, ctx->stream>>>(u, eta, g, E, lo, hi, ctx->halo_slot);
     else if (ctx->dim == 6) k_eps<6><<<grid, 256, 0, ctx->stream>>>(u, eta, g, E, lo, hi, ctx->halo_slot);
     else k_eps<9><<<grid, 256, 0, ctx->stream>>>(u, eta, g, E, lo, hi, ctx->halo_slot);
