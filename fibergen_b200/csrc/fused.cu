@@ -523,7 +523,7 @@ int fgb_k_dir_stress_div_iso(fgb_ctx* ctx, const double* r, double cgbeta, const
 // The two sweeps of the implicit-operator-result form, two voxels (k, k+1) per thread so that x, r and p move as 16-byte accesses:
 //   eta = sym-grad_h u (same expressions as k_eps_dot6);  DOT_ONLY: sum p:(p - eta);  else: x += a p ; r -= a (p - eta) ; sum r:r
 template <int DOT_ONLY>
-__global__ void __launch_bounds__(256) k_cg_update_u6(const double* __restrict__ u, const double* __restrict__ p, double* __restrict__ x,
+__global__ void __launch_bounds__(256, 4) k_cg_update_u6(const double* __restrict__ u, const double* __restrict__ p, double* __restrict__ x,
                                                       double* __restrict__ r, double a, GridDev g, Const9f E, double* __restrict__ partials,
                                                       const double* __restrict__ halo_lo, const double* __restrict__ halo_hi, size_t hslot) {
     const unsigned nzh = (unsigned)(g.nz + 1) / 2;
