@@ -119,6 +119,101 @@ __global__ void __launch_bounds__(FFTZ_THREADS) k_fftz_p2(double* __restrict__ b
     }
 }
 
+// z pass, half-length form: ONE real row of length N = 2*N2 is the complex sequence z[m] = x[2m] + i x[2m+1] of length N2
+// (16-byte loads), transformed with the two-pass register FFT and split with the twiddle W_N^k:
+//   forward : X[k] = E[k] + W_N^k O[k],  E = (Z[k] + conj Z[N2-k])/2,  O = (Z[k] - conj Z[N2-k])/(2i),  X[N2] = Re Z[0] - Im Z[0]
+//   backward: Z[k] = (X[k] + conj X[N2-k]) + i conj(W_N^k) (X[k] - conj X[N2-k])   (c2r: Im X[0], Im X[N2] ignored)
+// Against the row-pair form above this halves the transform length (fewer flops, fewer registers) and needs no second row.
+// The partner Z[N2-k] of thread s lives in thread (R1-s)%R1 of the same warp: shuffles, __syncwarp only.
+template <int N2, int R1, int R2, int FWD>
+__global__ void __launch_bounds__(FFTZ_THREADS) k_fftz_h(double* __restrict__ base, long rows, long rowstride,
+                                                         const double2* __restrict__ tw, double scale) {
+    constexpr int TPP = Max<R1, R2>::v;
+    constexpr int PP = FFTZ_THREADS / TPP;         // rows per CTA
+    constexpr int XS = R2 + 1;
+    extern __shared__ double2 smem_zh[];
+    double2* tw2_s = smem_zh;                      // W_N2^j = tw[2j]
+    double2* twh_s = smem_zh + N2;                 // W_N^k, k < N2
+    const int tid = threadIdx.x;
+    for (int i = tid; i < N2; i += FFTZ_THREADS) { tw2_s[i] = tw[2 * i]; twh_s[i] = tw[i]; }
+    __syncthreads();
+    const int s = tid % TPP, pp = tid / TPP;
+    const long row = (long)blockIdx.x * PP + pp;
+    const bool valid = row < rows;
+    double2* r2 = reinterpret_cast<double2*>(base + (valid ? row : 0) * rowstride);
+    double2* x = smem_zh + 2 * N2 + (size_t)pp * (R1 * XS);
+    const int lane = threadIdx.x & 31;
+    const int partner = (lane - s) + ((R1 - s) % R1);
+
+    if (FWD) {
+        if (s < R2) {
+            double2 v[R1];
+#pragma unroll
+            for (int n1 = 0; n1 < R1; n1++) v[n1] = valid ? r2[R2 * n1 + s] : make_double2(0, 0);
+            p2::pass1<R1, R2, -1>(v, s, tw2_s);
+#pragma unroll
+            for (int k1 = 0; k1 < R1; k1++) x[k1 * XS + s] = v[k1];
+        }
+        __syncwarp();
+        double2 w[R2];
+        if (s < R1) {
+#pragma unroll
+            for (int n2 = 0; n2 < R2; n2++) w[n2] = x[s * XS + n2];
+            p2::RegFFT<R2, -1>::run(w);
+        } else {
+#pragma unroll
+            for (int n2 = 0; n2 < R2; n2++) w[n2] = make_double2(0, 0);
+        }
+        const double h = 0.5 * scale;
+#pragma unroll
+        for (int k2 = 0; k2 < R2; k2++) {
+            double2 zn;
+            zn.x = __shfl_sync(0xffffffffu, w[R2 - 1 - k2].x, partner);
+            zn.y = __shfl_sync(0xffffffffu, w[R2 - 1 - k2].y, partner);
+            if (s == 0) zn = w[(R2 - k2) % R2];
+            const int k = s + R1 * k2;
+            if (s < R1 && valid) {
+                const double2 a = w[k2];
+                const double ex = a.x + zn.x, ey = a.y - zn.y;          // 2E
+                const double ox = a.y + zn.y, oy = -(a.x - zn.x);       // 2O = -i (a - conj zn)
+                const double2 wk = twh_s[k];
+                r2[k] = make_double2(h * (ex + wk.x * ox - wk.y * oy), h * (ey + wk.x * oy + wk.y * ox));
+                if (k == 0) r2[N2] = make_double2(scale * (a.x - a.y), 0.0);
+            }
+        }
+    } else {
+        if (s < R2) {
+            double2 v[R1];
+#pragma unroll
+            for (int n1 = 0; n1 < R1; n1++) {
+                const int k = R2 * n1 + s;
+                double2 a = make_double2(0, 0), xn = make_double2(0, 0);
+                if (valid) { a = r2[k]; xn = r2[N2 - k]; }
+                if (k == 0) { a.y = 0.0; xn.y = 0.0; }                   // c2r ignores the imaginary parts of X[0] and X[N/2]
+                const double sx = a.x + xn.x, sy = a.y - xn.y;
+                const double dx = a.x - xn.x, dy = a.y + xn.y;
+                const double2 wk = twh_s[k];
+                const double tx = wk.x * dx + wk.y * dy, ty = wk.x * dy - wk.y * dx;     // conj(W_N^k) * D
+                v[n1] = make_double2(sx - ty, sy + tx);
+            }
+            p2::pass1<R1, R2, +1>(v, s, tw2_s);
+#pragma unroll
+            for (int k1 = 0; k1 < R1; k1++) x[k1 * XS + s] = v[k1];
+        }
+        __syncwarp();
+        if (s < R1) {
+            double2 w[R2];
+#pragma unroll
+            for (int n2 = 0; n2 < R2; n2++) w[n2] = x[s * XS + n2];
+            p2::RegFFT<R2, +1>::run(w);
+            if (valid) {
+#pragma unroll
+                for (int k2 = 0; k2 < R2; k2++) r2[s + R1 * k2] = w[k2];
+            }
+        }
+    }
+}
+
 // strided pass (y; x without Green): tile of T lanes, thread (t, s); exchange buffer X[(k1*R2+n2)*T + t].
 // Source and destination may differ and are addressed through PencilMaps, so the y pass of a slab-partitioned run
 // writes straight into (reads straight from) the all-to-all staging layout.
@@ -532,6 +627,20 @@ static void launch_z_p2(fgb_ctx* ctx, double* base, long rows, long rowstride, b
     }
 }
 
+template <int N2, int R1, int R2>
+static void launch_z_h(fgb_ctx* ctx, double* base, long rows, long rowstride, bool fwd, double scale) {
+    constexpr int PP = FFTZ_THREADS / Max<R1, R2>::v;
+    const unsigned grid = (unsigned)((rows + PP - 1) / PP);
+    const size_t smem = sizeof(double2) * (2 * N2 + (size_t)PP * R1 * (R2 + 1));
+    if (fwd) {
+        set_smem(k_fftz_h<N2, R1, R2, 1>, smem);
+        k_fftz_h<N2, R1, R2, 1><<<grid, FFTZ_THREADS, smem, ctx->stream>>>(base, rows, rowstride, ctx->plan[2].tw, scale);
+    } else {
+        set_smem(k_fftz_h<N2, R1, R2, 0>, smem);
+        k_fftz_h<N2, R1, R2, 0><<<grid, FFTZ_THREADS, smem, ctx->stream>>>(base, rows, rowstride, ctx->plan[2].tw, 1.0);
+    }
+}
+
 static int fft_z(fgb_ctx* ctx, double* base, int ncomp, const FftLayout& lay, bool fwd) {
     const GridDev& g = ctx->g;
     const long rows = (long)ncomp * g.lnx * g.ny;
@@ -539,6 +648,19 @@ static int fft_z(fgb_ctx* ctx, double* base, int ncomp, const FftLayout& lay, bo
     const long rowstride = 2L * lay.nzcs;
     const double scale = 1.0 / ((double)g.nx * g.ny * g.nz);
     ProfScope ps(ctx, fwd ? "fft_z_r2c" : "fft_z_c2r");
+    // nz = 512: the half-length form (256-point complex transform per row) beats the 512-point row-pair kernel on the c2r side
+    // (0.106 vs 0.134 ms on 128x128x512) and ties on r2c; at 256 and 1024 the row-pair kernel is faster (measured), FGB_ZH forces it
+    static const bool zh = getenv("FGB_ZH") != nullptr, no_zh = getenv("FGB_NO_ZH") != nullptr;
+    if (!no_zh && (g.nz == 512 || (zh && (g.nz == 128 || g.nz == 256 || g.nz == 1024)))) {
+        switch (g.nz) {
+            case 128: launch_z_h<64, 8, 8>(ctx, base, rows, rowstride, fwd, scale); break;
+            case 256: launch_z_h<128, 16, 8>(ctx, base, rows, rowstride, fwd, scale); break;
+            case 512: launch_z_h<256, 16, 16>(ctx, base, rows, rowstride, fwd, scale); break;
+            case 1024: launch_z_h<512, 32, 16>(ctx, base, rows, rowstride, fwd, scale); break;
+        }
+        FGB_CHECK_LAUNCH(ctx, "k_fftz_h");
+        return FGB_OK;
+    }
     if (is_fast_pow2(g.nz)) {
         switch (g.nz) {
             case 64: launch_z_p2<64, 8, 8>(ctx, base, rows, rowstride, fwd, scale); break;

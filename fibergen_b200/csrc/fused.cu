@@ -208,8 +208,8 @@ __device__ __forceinline__ void diag_from(const IsoPhases& M, const double* phi,
     if (gamma != 0) { t0 += gamma * tr; t1 += gamma * tr; t2 += gamma * tr; }
 }
 
-template <int UPDATE, int NP, int BJ, int HALO, int ZW>
-__global__ void __launch_bounds__(256, 2) k_dsd_march(const double* __restrict__ r, const double* __restrict__ p_old, double* __restrict__ p_new,
+template <int UPDATE, int NP, int BJ, int HALO, int ZW, int NT>
+__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_dsd_march(const double* __restrict__ r, const double* __restrict__ p_old, double* __restrict__ p_new,
                                                    double* __restrict__ u, GridDev g, IsoPhases M, double cgbeta, double beta, double gamma,
                                                    int SEG, const double* __restrict__ halo) {
     // halo != null (slab partition): planes i = -1 and i = lnx come from the neighbour ranks, layout
@@ -227,7 +227,8 @@ __global__ void __launch_bounds__(256, 2) k_dsd_march(const double* __restrict__
     const int kp = (kc + 1 == g.nz) ? 0 : kc + 1, km = (kc == 0) ? g.nz - 1 : kc - 1;
     // z neighbours travel through shared memory (double-buffered: one barrier per plane).  ZW: the CTA holds the whole z row, the
     // periodic wrap is a slot index; otherwise the two threads at the CTA's ends recompute their neighbour from memory.
-    __shared__ double zx[2][3 * BJ][256];
+    // NT = 512 (one CTA per SM) keeps a 257..512-voxel z row inside one CTA, so that no thread takes the slow edge path
+    extern __shared__ double zx[];          // [2][3 * BJ][NT]
     const int tid = threadIdx.x;
     const bool edge_hi = !ZW && ((tid == (int)blockDim.x - 1) || (kc + 1 >= g.nz));
     const bool edge_lo = !ZW && ((tid == 0) || (kc == 0));
@@ -311,20 +312,20 @@ __global__ void __launch_bounds__(256, 2) k_dsd_march(const double* __restrict__
             t5n[jr] = shear_from<NP>(M, phin[jr], e5, beta);
             t4n[jr] = shear_from<NP>(M, phin[jr], e4, beta);
         }
-        double(*zb)[256] = zx[(i - i0) & 1];
+        double* zb = zx + (size_t)((i - i0) & 1) * (3 * BJ * NT);
 #pragma unroll
         for (int jr = 0; jr < BJ; jr++) {
-            zb[3 * jr][tid] = tc[jr][4];
-            zb[3 * jr + 1][tid] = tc[jr][3];
-            zb[3 * jr + 2][tid] = tc[jr][2];
+            zb[(3 * jr) * NT + tid] = tc[jr][4];
+            zb[(3 * jr + 1) * NT + tid] = tc[jr][3];
+            zb[(3 * jr + 2) * NT + tid] = tc[jr][2];
         }
         __syncthreads();
 #pragma unroll
         for (int jr = 0; jr < BJ; jr++) {
             // z neighbours
-            double t4_kp = zb[3 * jr][nb_hi];
-            double t3_kp = zb[3 * jr + 1][nb_hi];
-            double t2_km = zb[3 * jr + 2][nb_lo];
+            double t4_kp = zb[(3 * jr) * NT + nb_hi];
+            double t3_kp = zb[(3 * jr + 1) * NT + nb_hi];
+            double t2_km = zb[(3 * jr + 2) * NT + nb_lo];
             if (edge_hi) {
                 double ph[NP];
                 const size_t o = ROW(i, j0 + jr) + kp;
@@ -366,9 +367,10 @@ struct MarchTile {
 static MarchTile march_tile(const fgb_ctx* ctx) {
     const GridDev& g = ctx->g;
     MarchTile t;
-    t.threads = 256;
+    t.threads = (g.nz > 256 && g.nz <= 512 && !getenv("FGB_MARCH_NT256")) ? 512 : 256;
     while (t.threads > 32 && t.threads / 2 >= g.nz) t.threads /= 2;
     t.kchunks = (g.nz + t.threads - 1) / t.threads;
+    const double resident = (t.threads > 256) ? 1.0 : 2.0;          // CTAs per SM (launch bounds of k_dsd_march)
     t.BJ = (g.ny % 4 == 0) ? 4 : (g.ny % 2 == 0) ? 2 : 1;
     t.SEG = 16;
     if (const char* e = getenv("FGB_MARCH_SEG")) t.SEG = atoi(e);
@@ -377,7 +379,7 @@ static MarchTile march_tile(const fgb_ctx* ctx) {
         for (int nseg = 1; nseg <= (g.lnx + 7) / 8; nseg++) {
             const int cand = (g.lnx + nseg - 1) / nseg;          // balanced segments
             const long ctas = (long)(g.ny / t.BJ) * ((g.lnx + cand - 1) / cand) * t.kchunks;
-            const double waves = (double)ctas / (2.0 * ctx->sm_count);
+            const double waves = (double)ctas / (resident * ctx->sm_count);
             const double score = waves / std::ceil(waves) * cand / (cand + 1.0);
             if (score > best * 1.005) { best = score; t.SEG = cand; }
         }
@@ -396,21 +398,32 @@ static int launch_march(fgb_ctx* ctx, const double* r, const double* p_old, doub
     const MarchTile mt = march_tile(ctx);
     const int threads = mt.threads, kchunks = mt.kchunks, SEG = mt.SEG;
     const int segs = mt.segs;
-#define LAUNCH_MARCH(BJ_)                                                                                                          \
-    do {                                                                                                                          \
-        dim3 grid(g.ny / BJ_, segs, kchunks);                                                                                     \
-        if (halo) {                                                                                                               \
-            if (kchunks == 1) k_dsd_march<UPDATE, NP, BJ_, 1, 1><<<grid, threads, 0, ctx->stream>>>(r, p_old, p_new, ctx->ubuf, g, M, cgbeta, beta, gamma, SEG, halo); \
-            else k_dsd_march<UPDATE, NP, BJ_, 1, 0><<<grid, threads, 0, ctx->stream>>>(r, p_old, p_new, ctx->ubuf, g, M, cgbeta, beta, gamma, SEG, halo);             \
-        } else {                                                                                                                  \
-            if (kchunks == 1) k_dsd_march<UPDATE, NP, BJ_, 0, 1><<<grid, threads, 0, ctx->stream>>>(r, p_old, p_new, ctx->ubuf, g, M, cgbeta, beta, gamma, SEG, halo); \
-            else k_dsd_march<UPDATE, NP, BJ_, 0, 0><<<grid, threads, 0, ctx->stream>>>(r, p_old, p_new, ctx->ubuf, g, M, cgbeta, beta, gamma, SEG, halo);             \
-        }                                                                                                                         \
+#define LAUNCH_MARCH5(BJ_, H_, Z_, NT_)                                                                              \
+    do {                                                                                                             \
+        const size_t smem = sizeof(double) * 2 * 3 * BJ_ * NT_;                                                     \
+        if (smem > 48 * 1024)                                                                                        \
+            FGB_CUDA(ctx, cudaFuncSetAttribute(k_dsd_march<UPDATE, NP, BJ_, H_, Z_, NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_dsd_march<UPDATE, NP, BJ_, H_, Z_, NT_><<<grid, threads, smem, ctx->stream>>>(r, p_old, p_new, ctx->ubuf, g, M, cgbeta, beta, gamma, SEG, halo); \
+    } while (0)
+#define LAUNCH_MARCH(BJ_)                                     \
+    do {                                                      \
+        dim3 grid(g.ny / BJ_, segs, kchunks);                 \
+        if (threads > 256) {                                  \
+            if (halo) LAUNCH_MARCH5(BJ_, 1, 1, 512);          \
+            else LAUNCH_MARCH5(BJ_, 0, 1, 512);               \
+        } else if (halo) {                                    \
+            if (kchunks == 1) LAUNCH_MARCH5(BJ_, 1, 1, 256);  \
+            else LAUNCH_MARCH5(BJ_, 1, 0, 256);               \
+        } else {                                              \
+            if (kchunks == 1) LAUNCH_MARCH5(BJ_, 0, 1, 256);  \
+            else LAUNCH_MARCH5(BJ_, 0, 0, 256);               \
+        }                                                     \
     } while (0)
     if (mt.BJ == 4) LAUNCH_MARCH(4);
     else if (mt.BJ == 2) LAUNCH_MARCH(2);
     else LAUNCH_MARCH(1);
 #undef LAUNCH_MARCH
+#undef LAUNCH_MARCH5
     FGB_CHECK_LAUNCH(ctx, "k_dsd_march");
     return FGB_OK;
 }

@@ -57,6 +57,8 @@ def main():
         ("elasticity cg staggered 64x64x32 (pow2 fast path)", (64, 64, 32), dict(mode="elasticity", method="cg", error_estimator="residual", tol=1e-8), "el"),
         ("elasticity cg staggered 512x16x16 / 16x512x16 (three-pass FFT + peer stores)", (512, 16, 16), dict(mode="elasticity", method="cg", error_estimator="residual", tol=1e-8), "el"),
         ("elasticity cg staggered 16x512x16", (16, 512, 16), dict(mode="elasticity", method="cg", error_estimator="residual", tol=1e-8), "el"),
+        ("elasticity cg staggered 16x8x300 (512-thread sweep with halo planes)", (16, 8, 300), dict(mode="elasticity", method="cg", error_estimator="residual", tol=1e-8), "el"),
+        ("elasticity cg staggered 16x8x512 (half-length z transform)", (16, 8, 512), dict(mode="elasticity", method="cg", error_estimator="residual", tol=1e-8), "el"),
         ("elasticity cg collocated 64x32x16 (6-component three-pass x pass)", (64, 32, 16), dict(mode="elasticity", method="cg", gamma_scheme="collocated", error_estimator="residual", tol=1e-8), "el"),
         ("elasticity basic collocated 24x16x10", (24, 16, 10), dict(mode="elasticity", method="basic", gamma_scheme="collocated", error_estimator="sigma", tol=1e-7), "el"),
         ("heat cg laminate 32x24x16", (32, 24, 16), dict(mode="heat", method="cg", mixing_rule="laminate", error_estimator="residual", tol=1e-8), "heat"),
