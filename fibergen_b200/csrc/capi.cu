@@ -659,7 +659,7 @@ extern "C" int fgb_basic_step(fgb_ctx* c, int src, int dst, const double* E, dou
     }
     if ((rc = fgb_k_calc_stress(c, c->fields[src], c->fields[dst], mu0, lambda0, 1.0))) return rc;            // calcStressDiff fg:18030
     if (c->mode == FGB_MODE_VISCOSITY) {
-        double* tmp;
+        double* tmp = nullptr;
         if ((rc = scratch_field(c, &tmp))) return rc;
         if ((rc = fgb_k_copy(c, c->fields[dst], tmp, c->dim))) return rc;
         return delta_impl(c, c->fields[dst], tmp, E, mu0, -1.0);
@@ -693,7 +693,7 @@ extern "C" int fgb_cg_apply(fgb_ctx* c, int F, int p, int w, double mu0, double 
         if (c->bc_relax != 1.0 && (rc = fgb_k_component_dot(c, c->fields[p], nullptr, c->F00, 1))) return rc;
         if ((rc = fgb_k_calc_stress(c, c->fields[p], c->fields[w], mu0, lambda0, 1.0))) return rc;
         if (c->mode == FGB_MODE_VISCOSITY) {
-            double* tmp;
+            double* tmp = nullptr;
             if ((rc = scratch_field(c, &tmp))) return rc;
             if ((rc = fgb_k_copy(c, c->fields[w], tmp, c->dim))) return rc;
             if ((rc = delta_impl(c, c->fields[w], tmp, zero, mu0, -1.0))) return rc;
