@@ -1248,6 +1248,73 @@ class LSSolver:
         eta[:, 0, 0, 0] = E
         return eta
 
+    def GammaOperatorFourierWillotR(self, E, mu_0, lambda_0, tau_hat, alpha=-1.0, beta=0.0):
+        """fg:19083-19298 (the "safe" branch, WILLOT_ALLOW_NONZERO_LAMBDA): Willot's rotated-scheme Green operator for linear
+        elasticity.  Discrete frequency vector k_a = (i/4) tan(q_a/2) (1+e^{i q_0})(1+e^{i q_1})(1+e^{i q_2}) / h_a with
+        q_a = 2 pi m_a / n_a, r = k/|k|; the Hermitian 6x6 matrix gamma(iv,jv) of fg:19237-19247 is applied with the Voigt
+        factor 2 on the shear columns (fg:19266-19273).  Needs lambda_0 != 0 (mu_0/lambda_0 appears explicitly), as in the
+        reference; eta_hat(0) = E."""
+        if self.dim != 6:
+            raise RuntimeError("Unknown gamma scheme 'willot' for mode '%s'" % self.mode)       # fg:20488-20531: elasticity only
+        small = np.finfo(float).tiny
+        with np.errstate(divide='ignore', invalid='ignore'):
+            mu_lambda_0 = np.float64(mu_0) / np.float64(lambda_0)
+        n = (self.nx, self.ny, self.nz)
+        L = (self.dx, self.dy, self.dz)
+        cnt = (None, None, self.nzc)
+        shape = [(-1, 1, 1), (1, -1, 1), (1, 1, -1)]
+        q, w = [], []
+        for a in range(3):
+            xi = (2 * math.pi / L[a]) * self._freq(n[a], cnt[a])
+            wa = L[a] / n[a]
+            q.append((xi * wa).reshape(shape[a]))
+            w.append(wa)
+        ex = [1.0 + (np.cos(qa) + 1j * np.sin(qa)) for qa in q]                               # 1 + polar(1, q) fg:19131
+        exp012 = ex[0] * ex[1] * ex[2]
+        k = [(1j * (0.25 * np.tan(0.5 * q[a]))) * exp012 / w[a] for a in range(3)]
+        k = [np.broadcast_to(ka, tau_hat.shape[1:]) for ka in k]
+        mag = np.sqrt(sum(ka.real ** 2 + ka.imag ** 2 for ka in k)) + small
+        r = [ka / mag for ka in k]
+        rc = [np.conj(ra) for ra in r]
+        rr = r[0] * r[0] + r[1] * r[1] + r[2] * r[2]
+        r2 = rr.real ** 2 + rr.imag ** 2
+        vi = (0, 1, 2, 1, 0, 0)
+        vj = (0, 1, 2, 2, 2, 1)
+        dl = np.eye(3)
+
+        def S(a, b, c):
+            # the s.. terms of fg:19178-19215: index a == b gives 4 Im(r_c conj r_a)^2, else -4 Im(r_a conj r_b) Im(r_a conj r_c)
+            if a == b:
+                t = (r[c] * rc[a]).imag
+                return 4.0 * t * t
+            return -4.0 * (r[a] * rc[b]).imag * (r[a] * rc[c]).imag
+
+        g = {}
+        with np.errstate(divide='ignore', invalid='ignore'):
+            for iv in range(6):
+                for jv in range(iv, 6):
+                    i, j, kk, l = vi[iv], vj[iv], vi[jv], vj[jv]
+                    sjk, sjl, sik, sil = S(kk, j, i), S(l, j, i), S(kk, i, j), S(l, i, j)
+                    num = ((1 + 2 * mu_lambda_0) * 0.25 * (r[i] * rc[l] * dl[j, kk] + r[j] * rc[l] * dl[i, kk]
+                                                           + r[i] * rc[kk] * dl[j, l] + r[j] * rc[kk] * dl[i, l])
+                           + (0.25 * (r[i] * rc[l] * sjk + r[j] * rc[l] * sik + r[i] * rc[kk] * sjl + r[j] * rc[kk] * sil)
+                              - (r[i] * rc[j]).real * (r[kk] * rc[l]).real)
+                           - mu_lambda_0 * r[i] * r[j] * rc[kk] * rc[l])
+                    g[iv, jv] = num / (mu_0 * (2 * (1 + mu_lambda_0) - r2))
+                    g[jv, iv] = np.conj(g[iv, jv])
+            ey = []
+            for iv in range(6):
+                c = 0
+                for j in range(3, 6):
+                    c = c + g[iv, j] * tau_hat[j]
+                c = c * 2
+                for j in range(3):
+                    c = c + g[iv, j] * tau_hat[j]
+                ey.append(c)
+            eta = alpha * np.stack(ey) + beta * tau_hat
+        eta[:, 0, 0, 0] = E
+        return eta
+
     def _gamma_colloc_el(self, X, norm2, mu_0, lambda_0, tau_hat, alpha, beta):
         c10 = alpha / (4 * mu_0)
         c20 = -alpha / (mu_0 * (1 + mu_0 / (lambda_0 + mu_0)))
@@ -1328,6 +1395,12 @@ class LSSolver:
             return self.ifft(eta_hat)
         if self.gamma_scheme == "staggered":                         # fg:20288-20300, 20342-20378
             return self._GammaOperatorStaggered(E, mu_0, lambda_0, tau, alpha)
+        if self.gamma_scheme == "willot" and self.mode == "elasticity":   # GammaOperatorWillotR fg:20322-20330
+            tau_hat = self.fft(tau)
+            self.F0 = tau_hat[:, 0, 0, 0].real.copy()
+            eta_hat = self.GammaOperatorFourierWillotR(E, mu_0, lambda_0, tau_hat, alpha, beta)
+            eta_hat[:, 0, 0, 0] += alpha * self.calcBCProjector()
+            return self.ifft(eta_hat)
         raise RuntimeError("Unknown gamma scheme '%s'" % self.gamma_scheme)
 
     def _GammaOperatorStaggered(self, E, mu_0, lambda_0, tau, alpha):

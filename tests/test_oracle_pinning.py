@@ -136,3 +136,19 @@ def test_hashin_coated_sphere_known_answer():
     assert np.allclose(sm[:3], 12.9152, rtol=1e-3)
     assert np.abs(sm[3:]).max() < 1e-3
     assert abs(sm[:3].mean() / 3 - 4.305343511446667) / 4.305343511446667 < 1e-3
+
+
+@pytest.mark.parametrize("n,L", GRIDS + [((8, 6, 4), (1., 2., 3.))])
+def test_willot_identity(n, L):
+    """'WillotR epsG0div identity' of fibergen --test (fg:24107-24126): Gamma C0 Gamma tau == Gamma tau for the rotated-scheme
+    Green operator (fg:19083-19298).  Oracle only so far: the device library still refuses gamma_scheme=willot."""
+    s = mk(n, L, "elasticity", "willot")
+    rng = np.random.default_rng(3)
+    tau = rng.random((6,) + n)
+    z = np.zeros(6)
+    tau = s.GammaOperator(z, s.mu_0, s.lambda_0, tau, 1.0)
+    org = tau.copy()
+    t = s.calcStressConst(s.mu_0, s.lambda_0, tau)
+    t = s.GammaOperator(z, s.mu_0, s.lambda_0, t, 1.0)
+    assert np.abs(org).max() > 1e-6
+    assert np.linalg.norm(np.abs(t - org).reshape(6, -1).max(axis=1)) <= TOL
