@@ -223,17 +223,6 @@ __global__ void k_reduce_finish(const double* __restrict__ partials, int nblocks
     if (threadIdx.x == 0) out[v] = sh[0];
 }
 
-int fgb_reduce_reserve(fgb_ctx* ctx, size_t nblocks) {
-    if (nblocks <= ctx->partials_cap) return FGB_OK;
-    FGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (ctx->d_partials) cudaFree(ctx->d_partials);
-    ctx->d_partials = nullptr;
-    ctx->partials_cap = 0;
-    FGB_CUDA(ctx, cudaMalloc(&ctx->d_partials, sizeof(double) * FGB_RED_MAXV * nblocks));
-    ctx->partials_cap = nblocks;
-    return FGB_OK;
-}
-
 int fgb_reduce_finish(fgb_ctx* ctx, int nblocks, int nvals, int op, double* host_out) {
     k_reduce_finish<<<nvals, 256, 0, ctx->stream>>>(ctx->d_partials, nblocks, nvals, op, ctx->d_result);
     FGB_CHECK_LAUNCH(ctx, "k_reduce_finish");

@@ -155,7 +155,6 @@ extern "C" int fgb_create(fgb_ctx** out, int nx, int ny, int nz, double Lx, doub
     c->stream = c->own_stream;
     c->red_blocks = c->sm_count * 8;
     CREATE_CUDA(cudaMalloc(&c->d_partials, sizeof(double) * 32 * (size_t)c->red_blocks));
-    c->partials_cap = (size_t)c->red_blocks;
     c->implicit_w_of = -1;
     CREATE_CUDA(cudaMalloc(&c->d_result, sizeof(double) * 64));
     CREATE_CUDA(cudaMallocHost(&c->h_result, sizeof(double) * 64));

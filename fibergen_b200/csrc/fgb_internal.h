@@ -61,7 +61,6 @@ struct fgb_ctx {
     int device;
     int rank, nranks;
     int sm_count;
-    size_t partials_cap;          // blocks d_partials has room for
     std::map<const void*, int> occupancy;      // resident CTAs per SM of a kernel at its launch block size (fgb_wave_grid)
     int implicit_w_of;            // field id p whose operator result w = sym-grad(u) is held implicitly in ubuf (-1: none)
     size_t smem_optin;
@@ -226,7 +225,6 @@ int fgb_k_component_dot(fgb_ctx* ctx, const double* a, const double* b, double* 
 int fgb_k_cg_update(fgb_ctx* ctx, double* x, double* r, const double* p, const double* w, double a, double* delta);
 // finish a block-partial reduction of `nvals` sums (or mins/maxs) and copy to host; op 0 sum, 1 min, 2 max
 int fgb_reduce_finish(fgb_ctx* ctx, int nblocks, int nvals, int op, double* host_out);
-int fgb_reduce_reserve(fgb_ctx* ctx, size_t nblocks);      // room for nblocks per-block partials (grows d_partials)
 // grid of a grid-stride kernel: enough blocks for n items, at most `cap` blocks, rounded down to whole waves of the kernel's resident
 // CTAs (148 SMs x occupancy) so that no partial last wave runs at reduced occupancy
 unsigned fgb_wave_grid(fgb_ctx* ctx, const void* kernel, int block, size_t n, size_t cap);
