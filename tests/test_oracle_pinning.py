@@ -152,3 +152,36 @@ def test_willot_identity(n, L):
     t = s.GammaOperator(z, s.mu_0, s.lambda_0, t, 1.0)
     assert np.abs(org).max() > 1e-6
     assert np.linalg.norm(np.abs(t - org).reshape(6, -1).max(axis=1)) <= TOL
+
+
+def test_effective_stiffness_between_reuss_and_voigt_bounds():
+    """known answer (5) of SURVEY 8c: the effective stiffness of calc_effective_properties (fg:26040-26088) lies between the
+    Reuss and Voigt bounds in the energy (Loewner) order, and is symmetric in the energy form."""
+    n = (12, 12, 12)
+    x = (np.arange(12) + 0.5) / 12 - 0.5
+    r2 = x[:, None, None] ** 2 + x[None, :, None] ** 2 + x[None, None, :] ** 2
+    phi = (r2 <= 0.3 ** 2).astype(float)
+    (l1, m1), (l2, m2) = lame(1.0, 0.3), lame(10.0, 0.25)
+    s = fo.LSSolver(*n, mode="elasticity", method="cg", gamma_scheme="staggered", error_estimator="residual", tol=1e-9)
+    s.add_phase("matrix", fo.LinearIsotropic(m1, l1), 1 - phi)
+    s.add_phase("sphere", fo.LinearIsotropic(m2, l2), phi)
+    Ceff, _ = s.calc_effective_properties()
+    W = np.diag([1.0, 1, 1, 2, 2, 2])
+
+    def iso(lam, mu):
+        C = np.zeros((6, 6))
+        C[:3, :3] = lam
+        C[np.arange(6), np.arange(6)] += 2 * mu
+        return C
+
+    f = phi.mean()
+    C1, C2 = iso(l1, m1), iso(l2, m2)
+    voigt = (1 - f) * C1 + f * C2
+    reuss = np.linalg.inv((1 - f) * np.linalg.inv(C1) + f * np.linalg.inv(C2))
+    K = W @ Ceff
+    assert np.abs(K - K.T).max() <= 1e-6 * np.abs(K).max()
+    K = 0.5 * (K + K.T)
+    assert np.linalg.eigvalsh(W @ voigt - K).min() >= -1e-8
+    assert np.linalg.eigvalsh(K - W @ reuss).min() >= -1e-8
+    # and strictly inside for a two-phase composite
+    assert np.linalg.eigvalsh(W @ voigt - K).max() > 1e-3 and np.linalg.eigvalsh(K - W @ reuss).max() > 1e-3
