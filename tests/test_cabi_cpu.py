@@ -68,3 +68,42 @@ def test_product_never_imports_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh")):
                 assert "oracle" not in open(os.path.join(dirpath, f)).read().replace("the CPU oracle", ""), f
+
+
+@pytest.mark.parametrize("header", ["fgb200.h", "fgb200_lssolver.h"])
+def test_headers_are_plain_c(header):
+    """the boundary is a C ABI: both headers must compile as C99 on their own (cgo / JNI / ctypes-generators consume them)"""
+    import subprocess
+    p = subprocess.run(["gcc", "-std=c99", "-Wall", "-pedantic", "-fsyntax-only", "-x", "c", "-I" + os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "include", header)], capture_output=True, text=True)
+    assert p.returncode == 0 and not p.stderr.strip(), p.stderr
+
+
+def test_c_host_links_and_fails_loudly_without_device(tmp_path):
+    """a host written in plain C against include/fgb200.h links with libfgb200.so; without an sm_100 device fgb_create returns
+    FGB_ENODEV with a message (no CPU path behind the ABI)"""
+    import subprocess
+    import torch
+    src = tmp_path / "host.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "fgb200.h"
+#include "fgb200_lssolver.h"
+int main(void) {
+    fgb_ctx* ctx = NULL;
+    int rc;
+    if (!strstr(fgb_version(), "sm_100a")) return 2;
+    rc = fgb_create(&ctx, 8, 8, 8, 1.0, 1.0, 1.0, FGB_MODE_ELASTICITY, FGB_GAMMA_STAGGERED, -1, 0, 1);
+    printf("rc=%d msg=%s\n", rc, fgb_last_error(ctx));
+    if (rc == FGB_OK) { fgb_destroy(ctx); return 0; }
+    return (rc == FGB_ENODEV && ctx == NULL && strlen(fgb_last_error(NULL)) > 0) ? 10 : 3;
+}
+''')
+    exe = tmp_path / "host"
+    libdir = os.path.dirname(L.LIB_PATH)
+    p = subprocess.run(["gcc", "-std=c99", "-Wall", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-L" + libdir,
+                        "-lfgb200", "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == (0 if torch.cuda.is_available() else 10), (r.returncode, r.stdout, r.stderr)
