@@ -360,3 +360,34 @@ int fgb_k_cg_update(fgb_ctx* ctx, double* x, double* r, const double* p, const d
     delta[0] /= (double)ctx->g.nx * ctx->g.ny * ctx->g.nz;
     return FGB_OK;
 }
+
+// extrapolateLoadstepPolynomial fg:21493-21512: p = Vinv * f, F = <tpowers, p>, in the reference's summation order
+struct ExtrapArgs {
+    int n;
+    const double* f[8];
+    double Vinv[64], tp[8];
+};
+__global__ void __launch_bounds__(256) k_extrapolate_poly(double* __restrict__ dst, ExtrapArgs A, size_t ntot) {
+    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < ntot; v += (size_t)gridDim.x * blockDim.x) {
+        double f[8];
+        for (int i = 0; i < A.n; i++) f[i] = A.f[i][v];
+        double acc = 0;
+        for (int i = 0; i < A.n; i++) {
+            double pi = 0;
+            for (int j = 0; j < A.n; j++) pi += A.Vinv[i * A.n + j] * f[j];
+            acc += A.tp[i] * pi;
+        }
+        dst[v] = acc;
+    }
+}
+
+int fgb_k_extrapolate_poly(fgb_ctx* ctx, int n, const double* const* fields, const double* Vinv, const double* tpowers, double* dst) {
+    ExtrapArgs A;
+    A.n = n;
+    for (int i = 0; i < n; i++) { A.f[i] = fields[i]; A.tp[i] = tpowers[i]; }
+    for (int i = 0; i < n * n; i++) A.Vinv[i] = Vinv[i];
+    const size_t ntot = ctx->g.plane * ctx->dim;
+    k_extrapolate_poly<<<grid_for(ctx, ntot, 256), 256, 0, ctx->stream>>>(dst, A, ntot);
+    FGB_CHECK_LAUNCH(ctx, "k_extrapolate_poly");
+    return FGB_OK;
+}

@@ -79,8 +79,10 @@ extern "C" int fgb_create(fgb_ctx** out, int nx, int ny, int nz, double Lx, doub
     if (nx < 1 || ny < 1 || nz < 1 || !(Lx > 0) || !(Ly > 0) || !(Lz > 0))
         return fgb_fail(nullptr, FGB_EINVAL, "invalid grid %dx%dx%d / box %g x %g x %g", nx, ny, nz, Lx, Ly, Lz);
     if (mode < FGB_MODE_ELASTICITY || mode > FGB_MODE_POROUS) return fgb_fail(nullptr, FGB_EINVAL, "unknown mode %d", mode);
-    if (gamma_scheme != FGB_GAMMA_COLLOCATED && gamma_scheme != FGB_GAMMA_STAGGERED)
-        return fgb_fail(nullptr, FGB_EUNSUPPORTED, "gamma scheme %d not supported (collocated and staggered only)", gamma_scheme);
+    if (gamma_scheme != FGB_GAMMA_COLLOCATED && gamma_scheme != FGB_GAMMA_STAGGERED && gamma_scheme != FGB_GAMMA_WILLOT)
+        return fgb_fail(nullptr, FGB_EUNSUPPORTED, "gamma scheme %d not supported (collocated, staggered and willot only)", gamma_scheme);
+    if (gamma_scheme == FGB_GAMMA_WILLOT && mode != FGB_MODE_ELASTICITY && mode != FGB_MODE_VISCOSITY)
+        return fgb_fail(nullptr, FGB_EINVAL, "Unknown gamma scheme 'willot' for this mode (fg:20488-20531: elasticity and viscosity only)");
     if (nranks < 1 || rank < 0 || rank >= nranks) return fgb_fail(nullptr, FGB_EINVAL, "bad rank %d of %d", rank, nranks);
     if (nranks > 1 && (nx % nranks || ny % nranks))
         return fgb_fail(nullptr, FGB_EUNSUPPORTED, "slab partition needs nx and ny divisible by the number of ranks");
@@ -130,9 +132,12 @@ extern "C" int fgb_create(fgb_ctx** out, int nx, int ny, int nz, double Lx, doub
     c->lam.alpha = 0.001; c->lam.beta = 0.1;
     c->lam.delta = 1 - 1024 * eps;
     c->lam.maxiter = 32; c->lam.backtrack = 1; c->lam.project_t = 1; c->lam.fixed_c1 = -1.0;
-    for (int a = 0; a < 3; a++) { c->tw_dev[a] = nullptr; c->kpm_dev[a] = nullptr; c->kp_dev[a] = nullptr; c->xi_dev[a] = nullptr; }
+    for (int a = 0; a < 3; a++) {
+        c->tw_dev[a] = nullptr; c->kpm_dev[a] = nullptr; c->kp_dev[a] = nullptr; c->xi_dev[a] = nullptr;
+        c->xi2pi_dev[a] = nullptr; c->wtan_dev[a] = nullptr; c->wex_dev[a] = nullptr; c->pois_dev[a] = nullptr;
+    }
     c->d_partials = nullptr; c->d_result = nullptr; c->h_result = nullptr; c->d_scalars = nullptr; c->d_flag = nullptr; c->h_flag = nullptr;
-    c->nccl_comm = nullptr; c->nccl_lib = nullptr; c->sbuf = nullptr; c->xbuf = nullptr; c->xbuf_comps = 0; c->xbuf_nzcs = 0;
+    c->nccl_comm = nullptr; c->nccl_lib = nullptr; c->sbuf = nullptr; c->xbuf = nullptr; c->xbuf_cap = 0;
     c->halo = nullptr; c->halo_slot = 0; c->d_gather = nullptr; c->visc_tmp = nullptr; c->p2p = false; c->iso_halo = nullptr; c->phi_halo_valid = false;
     c->halo_base = nullptr; c->iso_set = 0; c->halo_seq = c->iso_seq = 0;
     for (int q = 0; q < 8; q++) c->peer_halo[q] = nullptr;
@@ -376,6 +381,13 @@ extern "C" int fgb_adjust_residual(fgb_ctx* c, int r, const double* E, int z) {
     CHECK_CTX(c); CHECK_FIELD(c, r); CHECK_FIELD(c, z);
     return fgb_k_adjust_residual(c, c->fields[r], E, c->fields[z]);
 }
+extern "C" int fgb_extrapolate_polynomial(fgb_ctx* c, int n, const int* fields, const double* Vinv, const double* tpowers, int dst) {
+    CHECK_CTX(c); CHECK_FIELD(c, dst);
+    if (n < 1 || n > 8 || !fields || !Vinv || !tpowers) return fgb_fail(c, FGB_EINVAL, "polynomial extrapolation needs 1..8 fields");
+    const double* f[8];
+    for (int i = 0; i < n; i++) { CHECK_FIELD(c, fields[i]); f[i] = c->fields[fields[i]]; }
+    return fgb_k_extrapolate_poly(c, n, f, Vinv, tpowers, c->fields[dst]);
+}
 extern "C" int fgb_inner(fgb_ctx* c, int a, int b, int cc, double* out) {
     CHECK_CTX(c); CHECK_FIELD(c, a); CHECK_FIELD(c, b);
     if (cc >= 0) CHECK_FIELD(c, cc);
@@ -472,6 +484,8 @@ static int green_args(fgb_ctx* c, GreenArgs& ga, double mu0, double lambda0, dou
         if (c->dim == 3) { ga.kind = 2; ga.c10 = -alpha / (2 * mu0); }                                              // fg:19758-19763
         else if (c->dim == 6) { ga.kind = 1; ga.c10 = -alpha / mu0; ga.c20 = -alpha / (mu0 * (1 + mu0 / (lambda0 + mu0))); }   // fg:19749-19755
         else { ga.kind = 1; ga.c10 = -alpha / (2 * mu0); ga.c20 = -alpha / (2 * mu0 * (1 + 2 * mu0 / lambda0)); }  // fg:19768-19774
+    } else if (c->scheme == FGB_GAMMA_WILLOT) {
+        ga.kind = 8; ga.c10 = mu0; ga.c20 = mu0 / lambda0; ga.alpha = alpha;                                        // fg:19091
     } else {
         if (c->dim == 3) { ga.kind = 4; ga.c10 = alpha / (2 * mu0); }                                               // fg:19309
         else if (c->dim == 6) { ga.kind = 3; ga.c10 = alpha / (4 * mu0); ga.c20 = -alpha / (mu0 * (1 + mu0 / (lambda0 + mu0))); }  // fg:19387-19388
@@ -536,8 +550,10 @@ static int gamma_impl(fgb_ctx* c, double* field, const double* E, double mu0, do
 }
 
 // DeltaOperatorStaggered (fg:20422-20460): viscosity dual formulation.  `copy` holds tau (input), field is overwritten.
+static int delta_collocated(fgb_ctx* c, double* field, const double* E, double mu0, double alpha);
 static int delta_impl(fgb_ctx* c, double* field, const double* tau_copy, const double* E, double mu0, double alpha) {
-    if (c->scheme != FGB_GAMMA_STAGGERED) return fgb_fail(c, FGB_EUNSUPPORTED, "viscosity mode is implemented for the staggered scheme only");
+    if (c->scheme == FGB_GAMMA_COLLOCATED) return delta_collocated(c, field, E, mu0, alpha);
+    // DeltaOperatorStaggered fg:20422-20460 and DeltaOperatorWillotR fg:20380-20418 share this form
     const double m = 1 / (4 * mu0);
     double mean[9], adj[9];
     int rc = fgb_k_component_dot(c, tau_copy, nullptr, mean, 1);
@@ -545,6 +561,82 @@ static int delta_impl(fgb_ctx* c, double* field, const double* tau_copy, const d
     for (int i = 0; i < 6; i++) adj[i] = E[i] - 2 * alpha * m * mean[i];
     if ((rc = gamma_impl(c, field, adj, -1.0 / (4 * m), INFINITY, alpha, 0.0))) return rc;
     return fgb_k_xpay(c, field, field, 2 * alpha * m, tau_copy);
+}
+
+// DeltaOperatorCollocated fg:20462-20471: fftTensor(zero_trace) -> applyDeltaFourier fg:19075 -> fftInvTensor(zero_trace).
+// Component 0 is never transformed: tau^_0 := -(tau^_1 + tau^_2) in Fourier space (inside the fused x pass, kind 9) and
+// eta_0 := -(eta_1 + eta_2) in real space afterwards (mxpyTensor fg:20590).
+static int delta_collocated(fgb_ctx* c, double* field, const double* E, double mu0, double alpha) {
+    const double m = 1 / (4 * mu0);
+    int rc;
+    double R[9] = {0};
+    if (c->bc_active || c->bc_relax != 1.0) {
+        // initBCProjector(tau_hat) fg:20220 reads the zero frequency, whose component 0 is -(tau^_1 + tau^_2)
+        double F0[9] = {0}, a[9], b[9];
+        if (c->bc_active) {
+            if ((rc = fgb_k_component_dot(c, field, nullptr, F0, 1))) return rc;
+            F0[0] = -(F0[1] + F0[2]);
+        }
+        dyad4_mv(6, c->bc_MQ, F0, a);
+        dyad4_mv(6, c->bc_MQC0, c->F00, b);
+        for (int i = 0; i < 6; i++) R[i] = c->bc_relax * a[i] - (1 - c->bc_relax) * b[i];
+    }
+    GreenArgs ga;
+    green_args(c, ga, -1.0 / (4 * m), INFINITY, alpha, 2 * alpha * m, false);      // fg:19078
+    ga.kind = 9;
+    for (int i = 0; i < 6; i++) ga.dc[i] = E[i] + alpha * R[i];
+    const FftLayout lay = {c->g.nzc};
+    double* f1 = field + c->g.plane;
+    if ((rc = fgb_fft_z_forward(c, f1, 5, lay))) return rc;
+    if (c->nranks > 1) {
+        if ((rc = fgb_comm_fft_x(c, field, 6, lay, &ga))) return rc;               // (the y passes of component 0 act on scratch data)
+    } else {
+        if ((rc = fgb_fft_y(c, f1, 5, lay, -1))) return rc;
+        if ((rc = fgb_fft_x(c, field, 6, lay, 0, &ga))) return rc;
+        if ((rc = fgb_fft_y(c, f1, 5, lay, +1))) return rc;
+    }
+    if ((rc = fgb_fft_z_backward(c, f1, 5, lay))) return rc;
+    return fgb_k_mxpy(c, field, field + c->g.plane, field + 2 * c->g.plane);
+}
+
+// Fourier-space operator on all `dim` components of a field in the reference layout: forward transform, operator `kind` fused into
+// the x pass, inverse transform
+static int fourier_operator(fgb_ctx* c, double* field, const GreenArgs& ga) {
+    int rc;
+    const FftLayout lay = {c->g.nzc};
+    if ((rc = fgb_fft_z_forward(c, field, c->dim, lay))) return rc;
+    if (c->nranks > 1) {
+        if ((rc = fgb_comm_fft_x(c, field, c->dim, lay, &ga))) return rc;
+    } else {
+        if ((rc = fgb_fft_y(c, field, c->dim, lay, -1))) return rc;
+        if ((rc = fgb_fft_x(c, field, c->dim, lay, 0, &ga))) return rc;
+        if ((rc = fgb_fft_y(c, field, c->dim, lay, +1))) return rc;
+    }
+    return fgb_fft_z_backward(c, field, c->dim, lay);
+}
+
+// G0DivOperatorHyper fg:20281-20286 (fftTensor, G0DivOperatorFourierHyper fg:20155, fftInvVector): components 0..2 of the field
+// become u = alpha * G0 Div tau (collocated Fourier discretisation, xi = 2 pi m / L); components 3..8 are left undefined
+extern "C" int fgb_g0div_hyper(fgb_ctx* c, int f, double mu0, double lambda0, double alpha) {
+    CHECK_CTX(c); CHECK_FIELD(c, f);
+    if (c->dim != 9) return fgb_fail(c, FGB_EINVAL, "fgb_g0div_hyper needs the 9-component hyperelasticity layout");
+    GreenArgs ga;
+    memset(&ga, 0, sizeof(ga));
+    ga.kind = 6;
+    ga.c10 = -alpha / (2 * mu0);                                   // fg:20162-20163
+    ga.c20 = alpha / (2 * mu0 * (1 + 2 * mu0 / lambda0));
+    return fourier_operator(c, c->fields[f], ga);
+}
+
+// fftTensor, GradOperatorFourierHyper fg:22069-22116, fftInvTensor (the sequence of fg:24531-24533): components 0..2 of the field
+// hold a vector field q on entry, all 9 components hold grad q on return
+extern "C" int fgb_grad_hyper(fgb_ctx* c, int f) {
+    CHECK_CTX(c); CHECK_FIELD(c, f);
+    if (c->dim != 9) return fgb_fail(c, FGB_EINVAL, "fgb_grad_hyper needs the 9-component hyperelasticity layout");
+    GreenArgs ga;
+    memset(&ga, 0, sizeof(ga));
+    ga.kind = 7;
+    return fourier_operator(c, c->fields[f], ga);
 }
 
 extern "C" int fgb_gamma(fgb_ctx* c, int f, const double* E, double mu0, double lambda0, double alpha, double beta) {
@@ -576,7 +668,15 @@ extern "C" int fgb_calc_displacement(fgb_ctx* c, int eps, int tmp, double mu0, d
         if ((rc = fgb_k_calc_stress(c, c->fields[eps], c->fields[tmp], mu0, lambda0, 1.0))) return rc;      // calcStressDiff fg:18030
         m = 1 / (4 * mu0); l = INFINITY; a = 1 / (2 * mu0);                                                // fg:15535
     } else if (c->mode == FGB_MODE_HYPERELASTICITY) {
+        // fg:15524-15527: calcStressDiff, then G0DivOperatorHyper (collocated Fourier div and G0, not the staggered operators)
         if ((rc = fgb_k_calc_stress(c, c->fields[eps], c->fields[tmp], mu0, lambda0, 1.0))) return rc;
+        if ((rc = poll_flag(c))) return rc;
+        if ((rc = fgb_g0div_hyper(c, tmp, mu0, lambda0, 1.0))) return rc;
+        c->implicit_w_of = -1;
+        for (int d = 0; d < 3; d++)
+            FGB_CUDA(c, cudaMemcpy2DAsync(c->ubuf + (size_t)d * c->g.uplane, sizeof(double) * 2 * c->g.unzcs, c->fields[tmp] + (size_t)d * c->g.plane,
+                                          sizeof(double) * c->g.nzp, sizeof(double) * c->g.nzp, (size_t)c->g.lnx * c->g.ny, cudaMemcpyDeviceToDevice, c->stream));
+        return FGB_OK;
     } else {
         if ((rc = fgb_k_calc_stress_const(c, c->fields[eps], c->fields[tmp], mu0, lambda0))) return rc;    // fg:17973
     }
@@ -584,6 +684,39 @@ extern "C" int fgb_calc_displacement(fgb_ctx* c, int eps, int tmp, double mu0, d
     if (c->nranks > 1 && (rc = fgb_comm_halo_tau(c, c->fields[tmp]))) return rc;
     if ((rc = fgb_k_div(c, c->fields[tmp], c->ubuf))) return rc;
     return g0_staggered(c, m, l, a);
+}
+// get_raw_field("p") fg:15559-15573: pressure of the viscosity formulation.  calcStressDiff, divOperatorStaggered, divVector with
+// alpha = 1/(2 mu0) (fg:19983), poisson_solve (fg:23454).  tmp is a scratch field; the result is left in component 0 of the u buffer
+// (fgb_u_download with ncomp = 1).
+extern "C" int fgb_calc_pressure(fgb_ctx* c, int eps, int tmp, double mu0, double lambda0) {
+    CHECK_CTX(c); CHECK_FIELD(c, eps); CHECK_FIELD(c, tmp);
+    if (eps == tmp) return fgb_fail(c, FGB_EINVAL, "fgb_calc_pressure needs a scratch field different from the strain field");
+    if (c->dim < 6) return fgb_fail(c, FGB_EINVAL, "field 'p' needs a mode with at least 6 tensor components (fg:15564-15565)");
+    int rc = ensure_ubuf(c);
+    if (rc) return rc;
+    if ((rc = fgb_k_calc_stress(c, c->fields[eps], c->fields[tmp], mu0, lambda0, 1.0))) return rc;
+    if ((rc = poll_flag(c))) return rc;
+    if (c->nranks > 1 && (rc = fgb_comm_halo_tau(c, c->fields[tmp]))) return rc;
+    if ((rc = fgb_k_div(c, c->fields[tmp], c->ubuf))) return rc;
+    if (c->nranks > 1 && (rc = fgb_comm_halo_u(c))) return rc;
+    double* b = c->fields[tmp];                                    // one component in the u layout fits into the scratch field
+    if ((rc = fgb_k_div_vector(c, c->ubuf, b, 1 / (2 * mu0)))) return rc;
+    GreenArgs ga;
+    memset(&ga, 0, sizeof(ga));
+    ga.kind = 10;
+    const FftLayout lay = {c->g.unzcs};
+    if ((rc = fgb_fft_z_forward(c, b, 1, lay))) return rc;
+    if (c->nranks > 1) {
+        if ((rc = fgb_comm_fft_x(c, b, 1, lay, &ga))) return rc;
+    } else {
+        if ((rc = fgb_fft_y(c, b, 1, lay, -1))) return rc;
+        if ((rc = fgb_fft_x(c, b, 1, lay, 0, &ga))) return rc;
+        if ((rc = fgb_fft_y(c, b, 1, lay, +1))) return rc;
+    }
+    if ((rc = fgb_fft_z_backward(c, b, 1, lay))) return rc;
+    c->implicit_w_of = -1;
+    FGB_CUDA(c, cudaMemcpyAsync(c->ubuf, b, sizeof(double) * c->g.uplane, cudaMemcpyDeviceToDevice, c->stream));
+    return FGB_OK;
 }
 extern "C" int fgb_eps_staggered(fgb_ctx* c, int f, const double* E) {
     CHECK_CTX(c); CHECK_FIELD(c, f);
@@ -606,7 +739,7 @@ extern "C" int fgb_u_upload(fgb_ctx* c, const double* const* comps, int n) {
 extern "C" int fgb_u_download(fgb_ctx* c, double* const* comps, int n) {
     CHECK_CTX(c);
     if (int rcu = ensure_ubuf(c)) return rcu;
-    if (n != c->udim) return fgb_fail(c, FGB_EINVAL, "u buffer has %d components", c->udim);
+    if (n < 1 || n > c->udim) return fgb_fail(c, FGB_EINVAL, "u buffer has %d components", c->udim);
     for (int d = 0; d < n; d++)
         FGB_CUDA(c, cudaMemcpy2DAsync(comps[d], sizeof(double) * c->g.nzp, c->ubuf + (size_t)d * c->g.uplane, sizeof(double) * 2 * c->g.unzcs,
                                       sizeof(double) * c->g.nzp, (size_t)c->g.lnx * c->g.ny, cudaMemcpyDeviceToHost, c->stream));
@@ -659,8 +792,10 @@ extern "C" int fgb_basic_step(fgb_ctx* c, int src, int dst, const double* E, dou
     if ((rc = fgb_k_calc_stress(c, c->fields[src], c->fields[dst], mu0, lambda0, 1.0))) return rc;            // calcStressDiff fg:18030
     if (c->mode == FGB_MODE_VISCOSITY) {
         double* tmp = nullptr;
-        if ((rc = scratch_field(c, &tmp))) return rc;
-        if ((rc = fgb_k_copy(c, c->fields[dst], tmp, c->dim))) return rc;
+        if (c->scheme != FGB_GAMMA_COLLOCATED) {
+            if ((rc = scratch_field(c, &tmp))) return rc;
+            if ((rc = fgb_k_copy(c, c->fields[dst], tmp, c->dim))) return rc;
+        }
         return delta_impl(c, c->fields[dst], tmp, E, mu0, -1.0);
     }
     return gamma_impl(c, c->fields[dst], E, mu0, lambda0, -1.0, 0.0);
@@ -693,8 +828,10 @@ extern "C" int fgb_cg_apply(fgb_ctx* c, int F, int p, int w, double mu0, double 
         if ((rc = fgb_k_calc_stress(c, c->fields[p], c->fields[w], mu0, lambda0, 1.0))) return rc;
         if (c->mode == FGB_MODE_VISCOSITY) {
             double* tmp = nullptr;
-            if ((rc = scratch_field(c, &tmp))) return rc;
-            if ((rc = fgb_k_copy(c, c->fields[w], tmp, c->dim))) return rc;
+            if (c->scheme != FGB_GAMMA_COLLOCATED) {
+                if ((rc = scratch_field(c, &tmp))) return rc;
+                if ((rc = fgb_k_copy(c, c->fields[w], tmp, c->dim))) return rc;
+            }
             if ((rc = delta_impl(c, c->fields[w], tmp, zero, mu0, -1.0))) return rc;
         } else if ((rc = gamma_impl(c, c->fields[w], zero, mu0, lambda0, -1.0, 0.0))) return rc;
     }

@@ -67,19 +67,20 @@ static int need_comm(fgb_ctx* ctx) {
     return FGB_OK;
 }
 
-static int ensure_xbuf(fgb_ctx* ctx, int ncomp, int nzcs) {
-    if (ctx->xbuf && ctx->xbuf_comps >= ncomp && ctx->xbuf_nzcs >= nzcs) return FGB_OK;
+// The transposition buffers sbuf / xbuf hold `cap` doubles each.  Before the peers have mapped them they grow on demand; afterwards
+// their addresses are fixed (exported with CUDA IPC), and a larger request -- only the 9-component Fourier operators of the
+// hyperelastic post-processing on a staggered context -- gets a temporary pair and takes the NCCL all-to-all path.
+static int ensure_xbuf(fgb_ctx* ctx, size_t need) {
+    if (ctx->xbuf && ctx->xbuf_cap >= need) return FGB_OK;
     if (ctx->p2p) return fgb_fail(ctx, FGB_EINVAL, "transposition buffers are mapped by the peers and cannot grow");
     if (ctx->sbuf) cudaFree(ctx->sbuf);
     if (ctx->xbuf) cudaFree(ctx->xbuf);
     ctx->sbuf = ctx->xbuf = nullptr;
-    const GridDev& g = ctx->g;
-    const size_t bytes = sizeof(double) * 2 * (size_t)ncomp * g.lnx * g.ny * nzcs;
-    cudaError_t e = cudaMalloc(&ctx->sbuf, bytes);
-    if (e == cudaSuccess) e = cudaMalloc(&ctx->xbuf, bytes);
-    if (e != cudaSuccess) return fgb_fail(ctx, FGB_ENOMEM, "cannot allocate the transpose buffers (%zu bytes each): %s", bytes, cudaGetErrorString(e));
-    ctx->xbuf_comps = ncomp;
-    ctx->xbuf_nzcs = nzcs;
+    ctx->xbuf_cap = 0;
+    cudaError_t e = cudaMalloc(&ctx->sbuf, sizeof(double) * need);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->xbuf, sizeof(double) * need);
+    if (e != cudaSuccess) return fgb_fail(ctx, FGB_ENOMEM, "cannot allocate the transpose buffers (%zu bytes each): %s", sizeof(double) * need, cudaGetErrorString(e));
+    ctx->xbuf_cap = need;
     return FGB_OK;
 }
 
@@ -177,8 +178,12 @@ extern "C" int fgb_comm_init(fgb_ctx* ctx, const void* id128) {
     ctx->phi_halo_valid = false;
     FGB_CUDA(ctx, cudaMalloc(&ctx->d_gather, sizeof(double) * 64 * ctx->nranks));
     // transposition buffers are allocated once (their addresses are exported to the peers)
+    // sized for the scheme's own operator and for the staggered-grid operators that get_raw_field("u") applies on every context
+    // (fg:15517-15557): max(dim*nzc, udim*unzcs) complex numbers per row of the slab
     const bool stag = ctx->scheme == FGB_GAMMA_STAGGERED;
-    if ((rc = ensure_xbuf(ctx, stag ? ctx->udim : ctx->dim, stag ? g.unzcs : g.nzc))) return rc;
+    size_t per_row = (size_t)ctx->udim * g.unzcs;
+    if (!stag && (size_t)ctx->dim * g.nzc > per_row) per_row = (size_t)ctx->dim * g.nzc;
+    if ((rc = ensure_xbuf(ctx, 2 * per_row * g.lnx * g.ny))) return rc;
     return map_peers(ctx);
 }
 
@@ -229,11 +234,25 @@ int fgb_comm_fft_x(fgb_ctx* ctx, double* base, int ncomp, const FftLayout& lay, 
     if (rc) return rc;
     const GridDev& g = ctx->g;
     const int P = ctx->nranks, lny = g.ny / P, nzcs = lay.nzcs;
-    if ((rc = ensure_xbuf(ctx, ncomp, nzcs))) return rc;
+    const size_t need = 2 * (size_t)ncomp * g.lnx * g.ny * nzcs;
+    struct TmpPair {
+        double *s = nullptr, *x = nullptr;
+        ~TmpPair() { if (s) cudaFree(s); if (x) cudaFree(x); }
+    } tmp;
+    double *sbuf = ctx->sbuf, *xbuf = ctx->xbuf;
+    bool p2p = ctx->p2p;
+    if (ctx->p2p && need > ctx->xbuf_cap) {
+        if (cudaMalloc(&tmp.s, sizeof(double) * need) != cudaSuccess || cudaMalloc(&tmp.x, sizeof(double) * need) != cudaSuccess)
+            return fgb_fail(ctx, FGB_ENOMEM, "cannot allocate temporary transpose buffers (%zu bytes each)", sizeof(double) * need);
+        sbuf = tmp.s; xbuf = tmp.x; p2p = false;
+    } else {
+        if ((rc = ensure_xbuf(ctx, need))) return rc;
+        sbuf = ctx->sbuf; xbuf = ctx->xbuf;
+    }
     const size_t chunk = (size_t)g.lnx * lny * nzcs;                 // complex numbers per (component, peer)
     const PencilMap nat = {nzcs, g.ny, 0, (long)g.ny * nzcs, (long)g.lnx * g.ny * nzcs};
     const PencilMap stg = {nzcs, lny, (long)chunk, (long)lny * nzcs, (long)P * (long)chunk};
-    if (ctx->p2p && nzcs == ctx->xbuf_nzcs) {
+    if (p2p) {
         // fused compute + transfer: the forward y pass stores segment q of every pencil into R of rank q over NVLink,
         // the fused x pass stores segment q of its output into the staging buffer of rank q; two stream-ordered barriers.
         const int me = ctx->rank;
@@ -274,22 +293,23 @@ int fgb_comm_fft_x(fgb_ctx* ctx, double* base, int ncomp, const FftLayout& lay, 
     }
     {
         ProfScope ps(ctx, "fft_y_fwd");
-        if ((rc = fgb_fft_strided(ctx, 1, base, ctx->sbuf, nat, stg, g.nzc, g.lnx, ncomp, -1))) return rc;
+        if ((rc = fgb_fft_strided(ctx, 1, base, sbuf, nat, stg, g.nzc, g.lnx, ncomp, -1))) return rc;
     }
     {
         ProfScope ps(ctx, "alltoall_fwd");
-        if ((rc = alltoall(ctx, ctx->sbuf, ctx->xbuf, ncomp, chunk))) return rc;
+        if ((rc = alltoall(ctx, sbuf, xbuf, ncomp, chunk))) return rc;
     }
     // y-slab layout R[c][ii][jl][k]: x pencils have stride lny*nzcs, the outer index is jl, jj = rank*lny + jl
-    if ((rc = fgb_fft_x_green_layout(ctx, ctx->xbuf, ga, (long)lny * nzcs, g.nzc, lny, nzcs, (long)g.nx * lny * nzcs, ctx->rank * lny))) return rc;
+    if ((rc = fgb_fft_x_green_layout(ctx, xbuf, ga, (long)lny * nzcs, g.nzc, lny, nzcs, (long)g.nx * lny * nzcs, ctx->rank * lny))) return rc;
     {
         ProfScope ps(ctx, "alltoall_bwd");
-        if ((rc = alltoall(ctx, ctx->xbuf, ctx->sbuf, ncomp, chunk))) return rc;
+        if ((rc = alltoall(ctx, xbuf, sbuf, ncomp, chunk))) return rc;
     }
     {
         ProfScope ps(ctx, "fft_y_bwd");
-        if ((rc = fgb_fft_strided(ctx, 1, ctx->sbuf, base, stg, nat, g.nzc, g.lnx, ncomp, +1))) return rc;
+        if ((rc = fgb_fft_strided(ctx, 1, sbuf, base, stg, nat, g.nzc, g.lnx, ncomp, +1))) return rc;
     }
+    if (tmp.s) FGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // the temporary pair is freed on return
     return FGB_OK;
 }
 

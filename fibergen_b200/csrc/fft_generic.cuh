@@ -207,13 +207,18 @@ __global__ void __launch_bounds__(256) k_fft_strided(const double2* __restrict__
 // ------------------------------------------------------------------------------------------------
 struct GreenDev {
     int kind;
-    double c10, c20, beta;
+    double c10, c20, beta, alpha;
     double dc[9];
     int freq_hack;
     int nx, ny, nz;
     const double* kpm[3];
     const double2* kp[3];
     const double* xi[3];
+    const double* xi2pi[3];      // 2 pi m / L per index (fg:20159, fg:22073, fg:19089)
+    const double2* wex[3];       // Willot-R: 1 + exp(i q), q = xi2pi * L/n (fg:19132)
+    const double* wtan[3];       // Willot-R: 0.25 tan(q/2)               (fg:19153)
+    double wvox[3];              // Willot-R: voxel size L/n              (fg:19115-19117)
+    const double* pois[3];       // poisson_solve fg:23454: (n/L)^2 (cos(2 pi i / n) - 1) per index
 };
 
 // G0OperatorFourierStaggeredGeneral, fg:19834-19927
@@ -353,6 +358,121 @@ __device__ __forceinline__ void green_colloc_hyper(const GreenDev& G, int ii, in
     for (int i = 0; i < 9; i++) f[i] = cadd(ey[i], cscale(G.beta, f[i]));
 }
 
+// G0DivOperatorFourierHyper, fg:20155-20218: u^ = G0^ (i xi . tau^) with xi = 2 pi m / L, 9 -> 3 components (the remaining six are
+// left untouched: the caller only transforms components 0..2 back)
+__device__ __forceinline__ void green_g0div_hyper(const GreenDev& G, int ii, int jj, int kk, double2* f) {
+    const double x0 = __ldg(G.xi2pi[0] + ii), x1 = __ldg(G.xi2pi[1] + jj), x2 = __ldg(G.xi2pi[2] + kk);
+    const double norm = x0 * x0 + x1 * x1 + x2 * x2;
+    const double c1 = G.c10 / norm;
+    const double c2 = G.c20 / (norm * norm);
+    // imag * (xi0*a + xi1*b + xi2*c)
+    const double2 s1 = cadd(cadd(cscale(x0, f[0]), cscale(x1, f[5])), cscale(x2, f[4]));
+    const double2 s2 = cadd(cadd(cscale(x0, f[8]), cscale(x1, f[1])), cscale(x2, f[3]));
+    const double2 s3 = cadd(cadd(cscale(x0, f[7]), cscale(x1, f[6])), cscale(x2, f[2]));
+    const double2 f1 = make_double2(-s1.y, s1.x), f2 = make_double2(-s2.y, s2.x), f3 = make_double2(-s3.y, s3.x);
+    f[0] = cadd(cscale(c1, f1), cscale(c2, cadd(cadd(cscale(x0 * x0, f1), cscale(x0 * x1, f2)), cscale(x0 * x2, f3))));
+    f[1] = cadd(cscale(c1, f2), cscale(c2, cadd(cadd(cscale(x1 * x0, f1), cscale(x1 * x1, f2)), cscale(x1 * x2, f3))));
+    f[2] = cadd(cscale(c1, f3), cscale(c2, cadd(cadd(cscale(x2 * x0, f1), cscale(x2 * x1, f2)), cscale(x2 * x2, f3))));
+}
+
+// GradOperatorFourierHyper, fg:22069-22116: W^ = i xi (x) q^, 3 -> 9 components
+__device__ __forceinline__ void green_grad_hyper(const GreenDev& G, int ii, int jj, int kk, double2* f) {
+    const double x0 = __ldg(G.xi2pi[0] + ii), x1 = __ldg(G.xi2pi[1] + jj), x2 = __ldg(G.xi2pi[2] + kk);
+    const double2 q0 = f[0], q1 = f[1], q2 = f[2];
+#define IXQ(xv, q) make_double2(-(xv) * (q).y, (xv) * (q).x)
+    f[0] = IXQ(x0, q0); f[1] = IXQ(x1, q1); f[2] = IXQ(x2, q2);
+    f[3] = IXQ(x2, q1); f[4] = IXQ(x2, q0); f[5] = IXQ(x1, q0);
+    f[6] = IXQ(x1, q2); f[7] = IXQ(x0, q2); f[8] = IXQ(x0, q1);
+#undef IXQ
+}
+
+// GammaOperatorFourierWillotR, fg:19083-19299 (the branch compiled in the reference: WILLOT_ALLOW_NONZERO_LAMBDA, "defined for
+// lambda_0 -> infinity").  G.c10 = mu_0, G.c20 = mu_0/lambda_0.
+__device__ __forceinline__ double2 cconj(double2 a) { return make_double2(a.x, -a.y); }
+__device__ __forceinline__ double wr_s(const double2* r, int a, int b, int c) {
+    // the s.. terms (fg:19178-19215): a == b -> 4 Im(r_c conj r_a)^2, else -4 Im(r_a conj r_b) Im(r_a conj r_c)
+    if (a == b) {
+        const double t = cmul(r[c], cconj(r[a])).y;
+        return 4.0 * t * t;
+    }
+    return -4.0 * cmul(r[a], cconj(r[b])).y * cmul(r[a], cconj(r[c])).y;
+}
+static __device__ __noinline__ void green_willot(const GreenDev& G, int ii, int jj, int kk, double2* f) {
+    const int vi[6] = {0, 1, 2, 1, 0, 0};
+    const int vj[6] = {0, 1, 2, 2, 2, 1};
+    const double2 e0 = __ldg(G.wex[0] + ii), e1 = __ldg(G.wex[1] + jj), e2 = __ldg(G.wex[2] + kk);
+    const double2 e012 = cmul(cmul(e0, e1), e2);
+    const double t[3] = {__ldg(G.wtan[0] + ii), __ldg(G.wtan[1] + jj), __ldg(G.wtan[2] + kk)};
+    double2 r[3], rc[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const double2 k = cmul(make_double2(0.0, t[a]), e012);
+        r[a] = make_double2(k.x / G.wvox[a], k.y / G.wvox[a]);
+    }
+    const double n2 = (r[0].x * r[0].x + r[0].y * r[0].y) + (r[1].x * r[1].x + r[1].y * r[1].y) + (r[2].x * r[2].x + r[2].y * r[2].y);
+    const double mag = sqrt(n2) + 2.2250738585072014e-308;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        r[a] = make_double2(r[a].x / mag, r[a].y / mag);
+        rc[a] = cconj(r[a]);
+    }
+    const double2 rr = cadd(cadd(cmul(r[0], r[0]), cmul(r[1], r[1])), cmul(r[2], r[2]));
+    const double r2 = rr.x * rr.x + rr.y * rr.y;
+    const double mu_0 = G.c10, ml = G.c20;
+    const double den = mu_0 * (2 * (1 + ml) - r2);
+    double2 g[6][6];
+    for (int iv = 0; iv < 6; iv++)
+        for (int jv = iv; jv < 6; jv++) {
+            const int i = vi[iv], j = vj[iv], k = vi[jv], l = vj[jv];
+            const double sjk = wr_s(r, k, j, i), sjl = wr_s(r, l, j, i), sik = wr_s(r, k, i, j), sil = wr_s(r, l, i, j);
+            const double djk = (j == k), dik = (i == k), djl = (j == l), dil = (i == l);
+            const double2 ril = cmul(r[i], rc[l]), rjl = cmul(r[j], rc[l]), rik = cmul(r[i], rc[k]), rjk = cmul(r[j], rc[k]);
+            const double2 a1 = cadd(cadd(cadd(cscale(djk, ril), cscale(dik, rjl)), cscale(djl, rik)), cscale(dil, rjk));
+            const double2 a2 = cadd(cadd(cadd(cscale(sjk, ril), cscale(sik, rjl)), cscale(sjl, rik)), cscale(sil, rjk));
+            const double re = cmul(r[i], rc[j]).x * cmul(r[k], rc[l]).x;
+            const double2 a3 = cmul(cmul(cmul(cscale(ml, r[i]), r[j]), rc[k]), rc[l]);
+            double2 num = cscale((1 + 2 * ml) * 0.25, a1);
+            num = cadd(num, make_double2(0.25 * a2.x - re, 0.25 * a2.y));
+            num = csub(num, a3);
+            g[iv][jv] = make_double2(num.x / den, num.y / den);
+            g[jv][iv] = cconj(g[iv][jv]);
+        }
+    double2 ey[6];
+    for (int iv = 0; iv < 6; iv++) {
+        double2 c = make_double2(0, 0);
+        for (int j = 3; j < 6; j++) c = cadd(c, cmul(g[iv][j], f[j]));
+        c = cscale(2.0, c);
+        for (int j = 0; j < 3; j++) c = cadd(c, cmul(g[iv][j], f[j]));
+        ey[iv] = c;
+    }
+#pragma unroll
+    for (int j = 0; j < 6; j++) f[j] = cadd(cscale(G.alpha, ey[j]), cscale(G.beta, f[j]));
+}
+
+// operator kinds of the fused x pass (GreenArgs::kind)
+template <int KIND>
+__device__ __forceinline__ void green_apply(const GreenDev& G, int ii, int jj, int kk, double2* f) {
+    if (KIND == 1) green_staggered(G, ii, jj, kk, f);
+    if (KIND == 2) green_staggered_heat(G, ii, jj, kk, f);
+    if (KIND == 3) green_colloc_el(G, ii, jj, kk, f);
+    if (KIND == 4) green_colloc_heat(G, ii, jj, kk, f);
+    if (KIND == 5) green_colloc_hyper(G, ii, jj, kk, f);
+    if (KIND == 6) green_g0div_hyper(G, ii, jj, kk, f);
+    if (KIND == 7) green_grad_hyper(G, ii, jj, kk, f);
+    if (KIND == 8) green_willot(G, ii, jj, kk, f);
+    if (KIND == 10) {
+        // poisson_solve fg:23454-23493: u^ = f^ / (2 sum_a (n_a/L_a)^2 (cos(2 pi i_a/n_a) - 1)); the reference folds the 1/nxyz of its
+        // unscaled forward transform into the same divisor, here the forward pass has already applied it
+        const double d = 2 * (__ldg(G.pois[0] + ii) + __ldg(G.pois[1] + jj) + __ldg(G.pois[2] + kk));
+        f[0] = make_double2(f[0].x / d, f[0].y / d);
+    }
+    if (KIND == 9) {
+        // viscosity, fftTensor(..., zero_trace) fg:18557-18559: component 0 is not transformed, tau^_0 = -(tau^_1 + tau^_2)
+        f[0] = make_double2(-(f[1].x + f[2].x), -(f[1].y + f[2].y));
+        green_colloc_el(G, ii, jj, kk, f);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // x pass fused with the Green operator: forward x, operator, inverse x -- one HBM round trip
 // layout seen by this kernel: element (ii, jj, kk) of component c at base[c*cstride + (jj-jbase)*ostride + ii*estride + kk]
@@ -399,11 +519,7 @@ __global__ void __launch_bounds__(256) k_fft_x_green(double2* __restrict__ base,
 #pragma unroll
             for (int c = 0; c < NC; c++) f[c] = make_double2(G.dc[c], 0.0);
         } else {
-            if (KIND == 1) green_staggered(G, ii, jj, kk, f);
-            if (KIND == 2) green_staggered_heat(G, ii, jj, kk, f);
-            if (KIND == 3) green_colloc_el(G, ii, jj, kk, f);
-            if (KIND == 4) green_colloc_heat(G, ii, jj, kk, f);
-            if (KIND == 5) green_colloc_hyper(G, ii, jj, kk, f);
+            green_apply<KIND>(G, ii, jj, kk, f);
         }
 #pragma unroll
         for (int c = 0; c < NC; c++) ptr[c][idx] = f[c];

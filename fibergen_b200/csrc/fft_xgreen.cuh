@@ -1,0 +1,305 @@
+// Fused x pass (forward x, Green operator, inverse x: one HBM round trip) for power-of-two nx, and the launcher that picks a
+// kernel for (components, operator kind, nx).  Included by the per-operator translation units fft_xg*.cu so that the
+// instantiations compile in parallel.
+#pragma once
+#include "fft_generic.cuh"
+#include "fft_pow2.cuh"
+#include "fft_pow2_3.cuh"
+#include "fft_launch.cuh"
+#include <cstdlib>
+
+using p2::Max;
+
+// x pass fused with the Green operator (power-of-two nx).  One shared-memory exchange per direction:
+//   forward : threads n2: R1-point FFT over n1, twiddle W_N^(n2 k1) | exchange | threads k1: R2-point FFT over n2 -> X[k1 + R1 k2]
+//   operator: every thread owns all NC components at its R2 frequencies (registers)
+//   inverse : threads k1: R2-point inverse FFT over k2, twiddle conj W_N^(k1 na) | exchange | threads na: R1-point inverse FFT over k1
+//             -> x[na + R2 nb], the same distribution the forward pass loaded, stored straight back to HBM.
+template <int N, int R1, int R2, int NC, int KIND, int T, int ASYNC>
+__global__ void __launch_bounds__(Max<R1, R2>::v* T) k_fftx_green_p2(double2* __restrict__ base, const double2* __restrict__ tw, GreenDev G,
+                                                                     long estride, int ninner, long ostride, long cstride, int jbase,
+                                                                     PencilMap xo, PeerTable pt) {
+    constexpr int TPP = Max<R1, R2>::v;
+    constexpr int NT = TPP * T;
+    extern __shared__ double2 smem[];
+    double2* tw_s = smem;                 // N
+    double2* S = smem + N;                // NC * N * T exchange space, component c at S + c*N*T
+    const int tid = threadIdx.x;
+    for (int i = tid; i < N; i += NT) tw_s[i] = tw[i];
+    const int t = tid % T, s = tid / T;
+    const int inner = blockIdx.x * T + t;
+    const bool valid = inner < ninner;
+    double2* g = base + (long)blockIdx.y * ostride + inner;
+    __syncthreads();
+
+    // ---- forward pass 1 (per component; one component in registers at a time).  All NC*R1 loads of a thread are issued up front
+    // as 16-byte asynchronous copies into the exchange buffer (element x of component c at Sc[x*T + t], exactly where the
+    // thread stores its pass-1 result for k1 = x / R2), one commit group per component, so the whole tile is in flight while
+    // the first component is being transformed.
+    if (s < R2) {
+        if (ASYNC) {
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                double2* Sc = S + (size_t)c * N * T;
+#pragma unroll
+                for (int n1 = 0; n1 < R1; n1++) {
+                    double2* d = Sc + ((R2 * n1 + s) * T + t);
+                    if (valid) {
+                        const unsigned sa = (unsigned)__cvta_generic_to_shared(d);
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(g + c * cstride + (long)(R2 * n1 + s) * estride) : "memory");
+                    } else {
+                        *d = make_double2(0, 0);
+                    }
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            }
+        }
+#pragma unroll(ASYNC == 2 ? 1 : NC)
+        for (int c = 0; c < NC; c++) {
+            double2* Sc = S + (size_t)c * N * T;
+            double2 v[R1];
+            if (ASYNC) {
+                if (c == 0) asm volatile("cp.async.wait_group %0;" ::"n"(NC - 1) : "memory");
+                else if (c == 1) asm volatile("cp.async.wait_group %0;" ::"n"(NC > 2 ? NC - 2 : 0) : "memory");
+                else asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+                for (int n1 = 0; n1 < R1; n1++) v[n1] = Sc[(R2 * n1 + s) * T + t];
+            } else {
+#pragma unroll
+                for (int n1 = 0; n1 < R1; n1++) v[n1] = valid ? g[c * cstride + (long)(R2 * n1 + s) * estride] : make_double2(0, 0);
+            }
+            p2::pass1<R1, R2, -1>(v, s, tw_s);
+#pragma unroll
+            for (int k1 = 0; k1 < R1; k1++) Sc[(k1 * R2 + s) * T + t] = v[k1];
+        }
+    }
+    __syncthreads();
+    // ---- forward pass 2, Green operator and inverse pass 1 on registers
+    double2 w[NC][R2];
+    if (s < R1) {
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            const double2* Sc = S + (size_t)c * N * T;
+#pragma unroll
+            for (int n2 = 0; n2 < R2; n2++) w[c][n2] = Sc[(s * R2 + n2) * T + t];
+            p2::RegFFT<R2, -1>::run(w[c]);
+        }
+        const int jj = jbase + blockIdx.y;
+        const int kk = inner;
+        if (valid) {
+#pragma unroll
+            for (int k2 = 0; k2 < R2; k2++) {
+                const int ii = s + R1 * k2;
+                double2 f[NC];
+#pragma unroll
+                for (int c = 0; c < NC; c++) f[c] = w[c][k2];
+                if (ii == 0 && jj == 0 && kk == 0) {
+#pragma unroll
+                    for (int c = 0; c < NC; c++) f[c] = make_double2(G.dc[c], 0.0);
+                } else {
+                    green_apply<KIND>(G, ii, jj, kk, f);
+                }
+#pragma unroll
+                for (int c = 0; c < NC; c++) w[c][k2] = f[c];
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            p2::RegFFT<R2, +1>::run(w[c]);          // inverse over k2 -> Y[k1][na], na = 0..R2-1
+#pragma unroll
+            for (int na = 1; na < R2; na++) {
+                double2 tws = tw_s[s * na];
+                tws.y = -tws.y;
+                w[c][na] = p2::pmul(w[c][na], tws);
+            }
+        }
+    }
+    __syncthreads();          // all exchange reads done before S is overwritten
+    if (s < R1) {
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            double2* Sc = S + (size_t)c * N * T;
+#pragma unroll
+            for (int na = 0; na < R2; na++) Sc[(na * R1 + s) * T + t] = w[c][na];
+        }
+    }
+    __syncthreads();
+    // ---- inverse pass 2: thread na gathers Y[k1][na] over k1, R1-point inverse FFT, output x[na + R2*nb]
+    if (s < R2) {
+#pragma unroll(ASYNC == 2 ? 1 : NC)
+        for (int c = 0; c < NC; c++) {
+            const double2* Sc = S + (size_t)c * N * T;
+            double2 v[R1];
+#pragma unroll
+            for (int k1 = 0; k1 < R1; k1++) v[k1] = Sc[(s * R1 + k1) * T + t];
+            p2::RegFFT<R1, +1>::run(v);
+            if (valid) {
+#pragma unroll
+                for (int nb = 0; nb < R1; nb++) {
+                    const int e = s + R2 * nb;
+                    double2* b = pt.n ? pt.p[e / xo.seglen] : base;
+                    b[c * xo.cstride + (long)blockIdx.y * xo.ostride + inner + xo.at(e)] = v[nb];
+                }
+            }
+        }
+    }
+}
+
+// fused x pass: forward (three passes, one component at a time through the two exchange buffers), Green operator on the
+// NC*R3 register values of a thread, mirrored inverse back to the distribution that was loaded.
+template <int R1, int R2, int R3, int NC, int KIND, int T, int MINB>
+__global__ void __launch_bounds__(p3::Plan<R1, R2, R3, T>::TPP* T, MINB)
+    k_fftx_green_p3(double2* __restrict__ base, const double2* __restrict__ tw, GreenDev G, long estride, int ninner, long ostride,
+                    long cstride, int jbase, PencilMap xo, PeerTable pt) {
+    using P = p3::Plan<R1, R2, R3, T>;
+    constexpr int N = P::N, M = P::M;
+    extern __shared__ double2 smem_x3[];
+    double2* tw_s = smem_x3;
+    double2* B1 = smem_x3 + N;
+    double2* B2 = B1 + P::BUF1;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < N; i += P::TPP * T) tw_s[i] = tw[i];
+    const int t = tid % T, s = tid / T;
+    const int inner = blockIdx.x * T + t;
+    const bool valid = inner < ninner;
+    double2* g = base + (long)blockIdx.y * ostride + inner;
+    __syncthreads();
+
+    double2 w[NC][R3];
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        double2 v[R1];
+        if (s < M) {
+#pragma unroll
+            for (int n1 = 0; n1 < R1; n1++) v[n1] = valid ? g[c * cstride + (long)(M * n1 + s) * estride] : make_double2(0, 0);
+        }
+        P::template forward<-1>(v, w[c], s, t, B1, B2, tw_s);
+    }
+    if (s < R1 * R2 && valid) {
+        const int jj = jbase + blockIdx.y;
+        const int kk = inner;
+#pragma unroll
+        for (int k3 = 0; k3 < R3; k3++) {
+            const int ii = s + R1 * R2 * k3;
+            double2 f[NC];
+#pragma unroll
+            for (int c = 0; c < NC; c++) f[c] = w[c][k3];
+            if (ii == 0 && jj == 0 && kk == 0) {
+#pragma unroll
+                for (int c = 0; c < NC; c++) f[c] = make_double2(G.dc[c], 0.0);
+            } else {
+                green_apply<KIND>(G, ii, jj, kk, f);
+            }
+#pragma unroll
+            for (int c = 0; c < NC; c++) w[c][k3] = f[c];
+        }
+    }
+    __syncthreads();          // forward pass-3 reads of B2 are done before the inverse overwrites it
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        double2 o[R1];
+        P::inverse(w[c], o, s, t, B1, B2, tw_s);
+        if (s < M && valid) {
+#pragma unroll
+            for (int na = 0; na < R1; na++) {
+                const int e = s + M * na;
+                double2* b = pt.n ? pt.p[e / xo.seglen] : base;
+                b[c * xo.cstride + (long)blockIdx.y * xo.ostride + inner + xo.at(e)] = o[na];
+            }
+        }
+    }
+}
+
+// ---- x with Green operator ---------------------------------------------------------------------------------
+template <int N, int R1, int R2, int NC, int KIND, int T>
+static int launch_xg_p2(fgb_ctx* ctx, double2* base, const GreenDev& G, long estride, int ninner, int nouter, long ostride, long cstride,
+                        int jbase, const PencilMap& xo, const PeerTable& pt) {
+    constexpr int NT = Max<R1, R2>::v * T;
+    const size_t smem = (size_t)(N + (size_t)NC * N * T) * sizeof(double2);
+    if (smem > ctx->smem_optin) return -1;
+    dim3 grid((ninner + T - 1) / T, nouter, 1);
+    // default: asynchronous tile prefetch, component loops of the first and last pass not unrolled (smaller code, fewer
+    // instruction-cache misses); FGB_XG_UNROLLED / FGB_XG_NOASYNC select the older variants for comparison
+    static const bool no_async = getenv("FGB_XG_NOASYNC") != nullptr;
+    static const bool rolled = getenv("FGB_XG_UNROLLED") == nullptr && !no_async;
+    if (rolled) {
+        FGB_CUDA(ctx, set_smem(k_fftx_green_p2<N, R1, R2, NC, KIND, T, 2>, smem));
+        k_fftx_green_p2<N, R1, R2, NC, KIND, T, 2><<<grid, NT, smem, ctx->stream>>>(base, ctx->plan[0].tw, G, estride, ninner, ostride, cstride, jbase, xo, pt);
+    } else if (no_async) {
+        FGB_CUDA(ctx, set_smem(k_fftx_green_p2<N, R1, R2, NC, KIND, T, 0>, smem));
+        k_fftx_green_p2<N, R1, R2, NC, KIND, T, 0><<<grid, NT, smem, ctx->stream>>>(base, ctx->plan[0].tw, G, estride, ninner, ostride, cstride, jbase, xo, pt);
+    } else {
+        FGB_CUDA(ctx, set_smem(k_fftx_green_p2<N, R1, R2, NC, KIND, T, 1>, smem));
+        k_fftx_green_p2<N, R1, R2, NC, KIND, T, 1><<<grid, NT, smem, ctx->stream>>>(base, ctx->plan[0].tw, G, estride, ninner, ostride, cstride, jbase, xo, pt);
+    }
+    FGB_CHECK_LAUNCH(ctx, "k_fftx_green_p2");
+    return FGB_OK;
+}
+
+template <int R1, int R2, int R3, int NC, int KIND, int T, int MINB>
+static int launch_xg_p3(fgb_ctx* ctx, double2* base, const GreenDev& G, long estride, int ninner, int nouter, long ostride, long cstride,
+                        int jbase, const PencilMap& xo, const PeerTable& pt) {
+    using P = p3::Plan<R1, R2, R3, T>;
+    constexpr int NT = P::TPP * T;
+    const size_t smem = (size_t)(P::N + P::SMEM_ELEMS) * sizeof(double2);
+    if (smem > ctx->smem_optin) return -1;
+    dim3 grid((ninner + T - 1) / T, nouter, 1);
+    FGB_CUDA(ctx, set_smem(k_fftx_green_p3<R1, R2, R3, NC, KIND, T, MINB>, smem));
+    k_fftx_green_p3<R1, R2, R3, NC, KIND, T, MINB><<<grid, NT, smem, ctx->stream>>>(base, ctx->plan[0].tw, G, estride, ninner, ostride, cstride,
+                                                                                   jbase, xo, pt);
+    FGB_CHECK_LAUNCH(ctx, "k_fftx_green_p3");
+    return FGB_OK;
+}
+
+template <int NC, int KIND>
+static int launch_x_green(fgb_ctx* ctx, double2* base, const GreenDev& G, long estride, int ninner, int nouter, long ostride, long cstride,
+                          int jbase, const PencilMap& xo, const PeerTable& pt) {
+    const int nx = ctx->g.nx;
+    int rc = -1;
+    // register budget: NC*R2 complex per thread -> the fast path covers NC <= 3 (staggered / heat); larger tensors use the generic kernel
+    // three-pass kernels: NC*R3 complex values per thread, so every tensor rank stays in registers.  They carry nx = 512 / 1024 for
+    // all operators and the 6- and 9-component (collocated) operators at every power of two; the 1- and 3-component operators at
+    // nx <= 256 are faster with the two-pass kernel below.
+    static const bool no_p3 = getenv("FGB_NO_P3") != nullptr;
+    static const bool xg_p3 = getenv("FGB_XG_P3") != nullptr;
+    constexpr int MB = (NC <= 3 ? 2 : 1);
+    if (!no_p3) {
+#define XG3(R1, R2, R3, T) rc = launch_xg_p3<R1, R2, R3, NC, KIND, T, MB>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt)
+        // FGB_XG_P3_T8 (not validated on hardware yet, off by default): 8-lane tiles = 128-byte segments for the nx = 512 pass
+        // when it stores to peer memory; the 4-lane tile's 64-byte stores reach only ~430 GB/s over NVLink at 8 GPUs
+        static const bool t8_peer = getenv("FGB_XG_P3_T8") != nullptr;
+        if constexpr (NC <= 3) {
+            if (nx == 512 && t8_peer && pt.n > 0)
+                rc = launch_xg_p3<8, 8, 8, NC, KIND, 8, 1>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt);
+        }
+        if (rc != -1) return rc;
+        if (nx == 512) XG3(8, 8, 8, 4);
+        else if (nx == 1024) XG3(16, 8, 8, 2);
+        else if (NC > 3 || xg_p3) {
+            if (nx == 64) XG3(4, 4, 4, 8);
+            else if (nx == 128) XG3(8, 4, 4, 8);
+            else if (nx == 256) XG3(8, 8, 4, 4);
+        }
+#undef XG3
+        if (rc != -1) return rc;
+    }
+    if constexpr (NC <= 3) {
+        switch (nx) {
+            case 64: rc = launch_xg_p2<64, 8, 8, NC, KIND, 8>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt); break;
+            case 128: rc = launch_xg_p2<128, 16, 8, NC, KIND, 8>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt); break;
+            case 256: rc = launch_xg_p2<256, 16, 16, NC, KIND, 8>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt); break;
+            case 512: rc = launch_xg_p2<512, 32, 16, NC, KIND, 4>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt); break;
+            case 1024: if constexpr (NC == 1) rc = launch_xg_p2<1024, 32, 32, NC, KIND, 2>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt); break;
+        }
+        if (rc != -1) return rc;
+    }
+    int T = pick_T(ctx, nx, NC + 1, 0, 8);
+    if (!T) return fgb_fail(ctx, FGB_EUNSUPPORTED, "nx=%d with %d components does not fit shared memory", nx, NC);
+    const size_t smem = (size_t)(NC + 1) * nx * T * sizeof(double2);
+    dim3 grid((ninner + T - 1) / T, nouter, 1);
+    FGB_CUDA(ctx, set_smem(k_fft_x_green<NC, KIND>, smem));
+    k_fft_x_green<NC, KIND><<<grid, 256, smem, ctx->stream>>>(base, ctx->plan[0], G, estride, ninner, ostride, cstride, T, jbase, xo, pt);
+    FGB_CHECK_LAUNCH(ctx, "k_fft_x_green");
+    return FGB_OK;
+}
+

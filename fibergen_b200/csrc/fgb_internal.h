@@ -84,6 +84,10 @@ struct fgb_ctx {
     double* kpm_dev[3];         // staggered: sin(xi)/h per index     (fg:19856-19876)
     double2* kp_dev[3];         // staggered: kpm*exp(i xi)
     double* xi_dev[3];          // collocated: m/L per index           (fg:19393-19406)
+    double* xi2pi_dev[3];       // 2 pi m/L per index (G0Div/Grad hyper fg:20159, Willot-R fg:19089)
+    double* wtan_dev[3];        // Willot-R: 0.25 tan(q/2), q = 2 pi m/n (fg:19153)
+    double2* wex_dev[3];        // Willot-R: 1 + exp(i q)                (fg:19132)
+    double* pois_dev[3];        // poisson_solve: (n/L)^2 (cos(2 pi i/n) - 1) (fg:23462-23486)
 
     // reductions
     double* d_partials;         // [nblocks][32]
@@ -99,8 +103,7 @@ struct fgb_ctx {
     void* nccl_lib;             // dlopen handle of libnccl.so.2
     double* sbuf;               // all-to-all staging, [c][q][il][jl][k] complex (same size as the transformed buffer)
     double* xbuf;               // y-slab layout [c][ii][jl][k] complex: the fused x pass runs in place on it
-    int xbuf_comps;             // components sbuf/xbuf are sized for
-    int xbuf_nzcs;
+    size_t xbuf_cap;            // doubles sbuf / xbuf can hold (each)
     double* halo;               // [3 lo slots][3 hi slots] of halo_slot doubles (neighbour x planes for the stencils)
     size_t halo_slot;
     double* d_gather;           // rank-ordered reduction staging
@@ -188,9 +191,11 @@ int fgb_fft_strided(fgb_ctx* ctx, int axis, const double* src, double* dst, cons
                     int nouter, int ncomp, int dir, const PeerTable* peers = nullptr);
 // x pass; green_kind: 0 none (plain forward or backward per dir), otherwise fused fwd-x, Green, inv-x
 struct GreenArgs {
-    int kind;             // 0 none, 1 staggered elasticity/hyper (general), 2 staggered heat, 3 colloc elasticity, 4 colloc heat, 5 colloc hyper
-    double c10, c20;      // staggered coefficients / collocated c10, c20
+    int kind;             // 0 none, 1 staggered elasticity/hyper (general), 2 staggered heat, 3 colloc elasticity, 4 colloc heat, 5 colloc hyper,
+                          // 6 G0-div hyper (9 -> 3), 7 grad hyper (3 -> 9), 8 Willot-R, 9 colloc elasticity on the zero-trace representation, 10 Poisson
+    double c10, c20;      // staggered coefficients / collocated c10, c20 (Willot-R: mu_0 and mu_0/lambda_0)
     double beta;          // collocated beta
+    double alpha;         // Willot-R only (the other kinds fold alpha into c10, c20)
     double dc[9];         // value of the zero frequency
     int freq_hack;
 };
@@ -201,6 +206,8 @@ int fgb_fft_x_green_layout(fgb_ctx* ctx, double* base, const GreenArgs* ga, long
 // stencil.cu ---------------------------------------------------------------------------------
 int fgb_k_div(fgb_ctx* ctx, const double* tau, double* u);
 int fgb_k_eps(fgb_ctx* ctx, const double* u, double* eta, const double* Econst /*dim, host*/);
+int fgb_k_div_vector(fgb_ctx* ctx, const double* u, double* b, double alpha);   // divVector fg:19983: 3-component u buffer -> one component (u layout)
+int fgb_k_mxpy(fgb_ctx* ctx, double* r, const double* x, const double* y);        // mxpyTensor fg:20590 on one component plane
 
 // material.cu --------------------------------------------------------------------------------
 MaterialDev fgb_material_dev(fgb_ctx* ctx);
@@ -223,6 +230,7 @@ int fgb_k_calc_stress_const(fgb_ctx* ctx, const double* src, double* dst, double
 int fgb_k_inner(fgb_ctx* ctx, const double* a, const double* b, const double* c, double* out);
 int fgb_k_component_dot(fgb_ctx* ctx, const double* a, const double* b, double* out, int mean_only);
 int fgb_k_cg_update(fgb_ctx* ctx, double* x, double* r, const double* p, const double* w, double a, double* delta);
+int fgb_k_extrapolate_poly(fgb_ctx* ctx, int n, const double* const* fields, const double* Vinv, const double* tpowers, double* dst);
 // finish a block-partial reduction of `nvals` sums (or mins/maxs) and copy to host; op 0 sum, 1 min, 2 max
 int fgb_reduce_finish(fgb_ctx* ctx, int nblocks, int nvals, int op, double* host_out);
 // grid of a grid-stride kernel: enough blocks for n items, at most `cap` blocks, rounded down to whole waves of the kernel's resident

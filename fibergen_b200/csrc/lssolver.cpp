@@ -199,6 +199,17 @@ LSSolver::LSSolver(int nx, int ny, int nz, double dx, double dy, double dz, int 
     _mixing_rule = "voigt";
     _G0_solver = "fft";
     _loadsteps = {0.0, 1.0};
+    _loadstep_extrapolation_order = 0;                                                       // fg:14830-14831
+    _loadstep_extrapolation_method = "polynomial";
+    _first_loadstep = -1;
+    // the reference sizes the prescribed loads in its constructor (mode is known there); here the mode may still change until
+    // init(), so loads set earlier are kept as given and expanded to the tensor dimension by init()
+    _E.assign(_dim, 0.0);
+    _S.assign(_dim, 0.0);
+    _current_E.assign(_dim, 0.0);
+    _current_S.assign(_dim, 0.0);
+    _Id.assign(_dim, 0.0);
+    _Id[0] = _Id[1] = _Id[2] = 1;
     _mu_0 = _lambda_0 = 0;
     _reference_set = false;
     _epsilon = _f1 = _f2 = _f3 = _f4 = _f5 = -1;
@@ -222,14 +233,42 @@ void LSSolver::check(int rc) const {
     fail(std::string(fgb_last_error(_ctx)));
 }
 
-static double to_double(const std::string& v) { return std::strtod(v.c_str(), nullptr); }
-static bool to_bool(const std::string& v) { return v == "1" || v == "true" || v == "True" || v == "yes"; }
+// the reference's pt_get throws on malformed values (fg:889-946): no silent 0
+static double to_double(const std::string& v) {
+    char* end = nullptr;
+    const double x = std::strtod(v.c_str(), &end);
+    while (end && (*end == ' ' || *end == '\t')) end++;
+    if (v.empty() || end == v.c_str() || (end && *end != 0)) throw std::runtime_error("Invalid numeric value '" + v + "'");
+    return x;
+}
+static size_t to_size(const std::string& v) {
+    char* end = nullptr;
+    const long long x = std::strtoll(v.c_str(), &end, 10);
+    while (end && (*end == ' ' || *end == '\t')) end++;
+    if (v.empty() || end == v.c_str() || (end && *end != 0) || x < 0) throw std::runtime_error("Invalid non-negative integer value '" + v + "'");
+    return (size_t)x;
+}
+static bool to_bool(const std::string& v) {
+    if (v == "1" || v == "true" || v == "True" || v == "yes") return true;
+    if (v == "0" || v == "false" || v == "False" || v == "no") return false;
+    throw std::runtime_error("Invalid boolean value '" + v + "'");
+}
 
 void LSSolver::set(const std::string& key, const std::string& value) {
+    try {
+        set_impl(key, value);
+    } catch (const std::exception& e) {
+        const std::string msg = e.what();
+        if (msg.rfind("Invalid ", 0) == 0) fail("solver setting '" + key + "': " + msg);
+        throw;
+    }
+}
+
+void LSSolver::set_impl(const std::string& key, const std::string& value) {
     if (key == "tol") _tol = to_double(value);
     else if (key == "abs_tol") _abs_tol = to_double(value);
     else if (key == "bc_tol") _bc_tol = to_double(value);
-    else if (key == "maxiter") _maxiter = (size_t)std::strtoull(value.c_str(), nullptr, 10);
+    else if (key == "maxiter") _maxiter = to_size(value);
     else if (key == "update_ref") _update_ref = value;
     else if (key == "ref_scale") _ref_scale = to_double(value);
     else if (key == "newton_relax") _newton_relax = to_double(value);
@@ -237,9 +276,18 @@ void LSSolver::set(const std::string& key, const std::string& value) {
     else if (key == "outer_error_estimator") _outer_error_estimator = value;
     else if (key == "method") _method = value;
     else if (key == "cg_inner_product") _cg_inner_product = value;
-    else if (key == "cg_reinit") _cg_reinit = (size_t)std::strtoull(value.c_str(), nullptr, 10);
+    else if (key == "cg_reinit") _cg_reinit = to_size(value);
+    else if (key == "loadstep_extrapolation_order") _loadstep_extrapolation_order = to_size(value);          // fg:15090
+    else if (key == "loadstep_extrapolation_method") _loadstep_extrapolation_method = value;                 // fg:15091
+    else if (key == "first_loadstep") {
+        _first_loadstep = (value.size() && value[0] == '-') ? -1 : (long)to_size(value);
+    }
     else if (key == "gamma_scheme") _gamma_scheme = value;
-    else if (key == "mode") _mode = value;
+    else if (key == "mode") {
+        _mode = value;
+        // the tensor dimension follows the mode (fg:14980-14997) so that loads given before init() are sized correctly
+        if (!_ctx) _dim = (value == "hyperelasticity") ? 9 : ((value == "heat" || value == "porous") ? 3 : 6);
+    }
     else if (key == "bc_relax") _bc_relax = to_double(value);
     else if (key == "freq_hack") _freq_hack = to_bool(value);
     else if (key == "G0_solver") _G0_solver = value;
@@ -248,7 +296,8 @@ void LSSolver::set(const std::string& key, const std::string& value) {
         // uniform_loadsteps(n) (fg:15033) or an explicit comma separated parameter list
         _loadsteps.clear();
         if (value.find(',') == std::string::npos) {
-            const size_t n = (size_t)std::strtoull(value.c_str(), nullptr, 10);
+            const size_t n = to_size(value);
+            if (n < 1) fail("loadsteps must be at least 1");
             for (size_t i = 0; i <= n; i++) _loadsteps.push_back(i / (double)n);
         } else {
             std::stringstream ss(value);
@@ -320,7 +369,10 @@ void LSSolver::init() {
     int scheme;
     if (_gamma_scheme == "collocated") scheme = FGB_GAMMA_COLLOCATED;
     else if (_gamma_scheme == "staggered") scheme = FGB_GAMMA_STAGGERED;
-    else { fail("Unknown gamma scheme '" + _gamma_scheme + "' (this build provides collocated and staggered)"); return; }
+    else if (_gamma_scheme == "willot") scheme = FGB_GAMMA_WILLOT;
+    else { fail("Unknown gamma scheme '" + _gamma_scheme + "' (this build provides collocated, staggered and willot)"); return; }
+    if (_loadstep_extrapolation_method != "polynomial")
+        fail("Unknown loadstep extrapolation method '" + _loadstep_extrapolation_method + "' (this build provides polynomial)");
     if (_G0_solver != "fft") fail("Unknown G0-solver '" + _G0_solver + "' (multigrid is not provided)");
     if (_method != "basic" && _method != "cg" && _method != "polarization") fail("Unknown solver method '" + _method + "'");
     if (_cg_inner_product != "l2") fail("Unknown inner product '" + _cg_inner_product + "'");   // "energy" throws in the reference too (fg:20792)
@@ -361,12 +413,13 @@ void LSSolver::init() {
 
     _epsilon = fgb_field_alloc(_ctx);
     check(_epsilon);
-    _E.assign(_dim, 0.0);
-    _S.assign(_dim, 0.0);
     _current_E.assign(_dim, 0.0);
     _current_S.assign(_dim, 0.0);
     _Id.assign(_dim, 0.0);
     _Id[0] = _Id[1] = _Id[2] = 1;
+    // loads given before init() (or before a re-init) stay in force
+    _E = _E_raw.empty() ? Vec(_dim, 0.0) : expandLoad(_E_raw, "strain");
+    _S = _S_raw.empty() ? Vec(_dim, 0.0) : expandLoad(_S_raw, "stress");
     if (!_reference_set) {
         _mu_0 = std::numeric_limits<double>::quiet_NaN();                                  // fg:15340
         _lambda_0 = 0.0;
@@ -381,23 +434,28 @@ void LSSolver::setPhase(int m, const double* phi) { check(fgb_set_phase(_ctx, m,
 void LSSolver::setNormals(const double* const* c) { check(fgb_set_normals(_ctx, c)); }
 void LSSolver::setOrientation(const double* const* c) { check(fgb_set_orientation(_ctx, c)); }
 
-void LSSolver::setStrain(const Vec& e) {
-    // fg:20691-20712
-    if (e.size() == 3 && _dim == 3) _E = e;
+Vec LSSolver::expandLoad(const Vec& e, const char* what) const {
+    // fg:20691-20712 (setStrain) / fg:20667-20689 (setStress): 3-, 6- or 9-vectors, shear entries duplicated for dim 9
+    Vec r(_dim, 0.0);
+    if (e.size() == 3 && _dim == 3) r = e;
     else if (e.size() == 6 && _dim >= 6) {
-        for (int i = 0; i < 6; i++) _E[i] = e[i];
-        if (_dim == 9) { _E[6] = e[3]; _E[7] = e[4]; _E[8] = e[5]; }
-    } else if (e.size() == 9 && _dim == 9) _E = e;
-    else fail("Invalid size of strain vector");
+        for (int i = 0; i < 6; i++) r[i] = e[i];
+        if (_dim == 9) { r[6] = e[3]; r[7] = e[4]; r[8] = e[5]; }
+    } else if (e.size() == 9 && _dim == 9) r = e;
+    else fail(std::string("Invalid size of ") + what + " vector");
+    return r;
+}
+
+void LSSolver::setStrain(const Vec& e) {
+    if (e.size() != 3 && e.size() != 6 && e.size() != 9) fail("Invalid size of strain vector");
+    _E_raw = e;
+    if (_ctx) _E = expandLoad(e, "strain");
 }
 
 void LSSolver::setStress(const Vec& e) {
-    if (e.size() == 3 && _dim == 3) _S = e;
-    else if (e.size() == 6 && _dim >= 6) {
-        for (int i = 0; i < 6; i++) _S[i] = e[i];
-        if (_dim == 9) { _S[6] = e[3]; _S[7] = e[4]; _S[8] = e[5]; }
-    } else if (e.size() == 9 && _dim == 9) _S = e;
-    else fail("Invalid size of stress vector");
+    if (e.size() != 3 && e.size() != 6 && e.size() != 9) fail("Invalid size of stress vector");
+    _S_raw = e;
+    if (_ctx) _S = expandLoad(e, "stress");
 }
 
 void LSSolver::setBCProjector(const Mat& P) {
@@ -601,14 +659,72 @@ bool LSSolver::run() {
     }
 }
 
+// LU with partial pivoting (what lapack::gesv does, fg:21486): X = A^-1, A is n x n row-major
+static bool invert_gesv(Mat A, int n, Mat& X) {
+    X.assign(n * n, 0.0);
+    for (int i = 0; i < n; i++) X[i * n + i] = 1.0;
+    for (int k = 0; k < n; k++) {
+        int piv = k;
+        for (int i = k + 1; i < n; i++)
+            if (std::fabs(A[i * n + k]) > std::fabs(A[piv * n + k])) piv = i;
+        if (A[piv * n + k] == 0.0) return false;
+        if (piv != k)
+            for (int j = 0; j < n; j++) { std::swap(A[k * n + j], A[piv * n + j]); std::swap(X[k * n + j], X[piv * n + j]); }
+        for (int i = k + 1; i < n; i++) {
+            const double l = A[i * n + k] / A[k * n + k];
+            for (int j = k; j < n; j++) A[i * n + j] -= l * A[k * n + j];
+            for (int j = 0; j < n; j++) X[i * n + j] -= l * X[k * n + j];
+        }
+    }
+    for (int k = n - 1; k >= 0; k--)
+        for (int j = 0; j < n; j++) {
+            double v = X[k * n + j];
+            for (int i = k + 1; i < n; i++) v -= A[k * n + i] * X[i * n + j];
+            X[k * n + j] = v / A[k * n + k];
+        }
+    return true;
+}
+
+void LSSolver::extrapolateLoadstep(const std::vector<std::pair<double, int>>& last, double t) {
+    // extrapolateLoadstepPolynomial fg:21468-21513: Vandermonde system through the stored load steps, evaluated at t
+    const int n = (int)last.size();
+    Mat V(n * n), Vinv;
+    Vec tpowers(n);
+    for (int i = 0; i < n; i++) {
+        for (int j = 0; j < n; j++) V[i * n + j] = std::pow(last[i].first, j);
+        tpowers[i] = std::pow(t, i);
+    }
+    if (!invert_gesv(V, n, Vinv)) fail("Error inverting Vandermonde matrix");
+    std::vector<int> ids(n);
+    for (int i = 0; i < n; i++) ids[i] = last[i].second;
+    check(fgb_extrapolate_polynomial(_ctx, n, ids.data(), Vinv.data(), tpowers.data(), _epsilon));
+}
+
 bool LSSolver::runLoadsteppingSolver(const Vec& Emax, const Vec& Smax) {
-    // fg:21584-21686 (first_loadstep default: skip step 0 unless more than one step is given)
-    const size_t first = (_loadsteps.size() > 2) ? 0 : 1;
+    // fg:21584-21686
+    const size_t first = (_first_loadstep >= 0) ? (size_t)_first_loadstep : ((_loadsteps.size() > 2) ? 0 : 1);
+    std::vector<std::pair<double, int>> last;          // (load parameter, field holding that step's solution)
+    struct Release {
+        LSSolver* s;
+        std::vector<std::pair<double, int>>* l;
+        ~Release() { for (auto& e : *l) fgb_field_free(s->_ctx, e.second); }
+    } release{this, &last};
     for (size_t istep = first; istep < _loadsteps.size(); istep++) {
         const double t = _loadsteps[istep];
         Vec E = t * Emax;
         Vec S = t * Smax;
         if (_mode == "hyperelasticity") E = E + (1 - t) * dyad4(_BC_P, _Id);
+        if (_loadstep_extrapolation_order > 0 && istep > first) {                          // fg:21634-21650
+            while (last.size() > _loadstep_extrapolation_order) {
+                check(fgb_field_free(_ctx, last.front().second));
+                last.erase(last.begin());
+            }
+            const int keep = fgb_field_alloc(_ctx);
+            check(keep);
+            check(fgb_copy(_ctx, _epsilon, keep));
+            last.push_back(std::make_pair(_loadsteps[istep - 1], keep));
+            if (last.size() >= 2) extrapolateLoadstep(last, t);
+        }
         runSolver(E, S);
     }
     return false;
@@ -788,6 +904,7 @@ Mat LSSolver::calcEffectiveProperties() {
 int LSSolver::fieldComponents(const std::string& name) const {
     if (name == "epsilon" || name == "sigma") return _dim;
     if (name == "u") return _dim == 3 ? 1 : 3;
+    if (name == "p") return _dim >= 6 ? 1 : -1;
     return -1;
 }
 
@@ -801,6 +918,9 @@ void LSSolver::getField(const std::string& name, double* const* comps) {
     } else if (name == "u") {                                                               // fg:15517-15557
         check(fgb_calc_displacement(_ctx, _epsilon, field(_f5), _mu_0, _lambda_0));
         check(fgb_u_download(_ctx, comps, fieldComponents(name)));
+    } else if (name == "p" && _dim >= 6) {                                                  // fg:15559-15573
+        check(fgb_calc_pressure(_ctx, _epsilon, field(_f5), _mu_0, _lambda_0));
+        check(fgb_u_download(_ctx, comps, 1));
     } else fail("Unknown field '" + name + "'");
 }
 

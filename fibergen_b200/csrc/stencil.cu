@@ -170,3 +170,51 @@ int fgb_k_eps(fgb_ctx* ctx, const double* u, double* eta, const double* Econst) 
     FGB_CHECK_LAUNCH(ctx, "k_eps");
     return FGB_OK;
 }
+
+// divVector fg:19983-20003: b = alpha * sum_a (f_a(x) - f_a(x + e_a)) / h_a of the 3-component buffer u (forward differences with the
+// sign of the reference), written as one component in the u layout.  halo_hi: [u0 at i = lnx].
+__global__ void __launch_bounds__(256) k_div_vector(const double* __restrict__ u, double* __restrict__ b, GridDev g, double alpha,
+                                                    const double* __restrict__ halo_hi) {
+    const unsigned nvox = (unsigned)g.lnx * (unsigned)g.ny * (unsigned)g.nz;
+    const size_t us = 2 * (size_t)g.unzcs;
+    const double chx = alpha * g.hx, chy = alpha * g.hy, chz = alpha * g.hz;
+    for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += gridDim.x * blockDim.x) {
+        const unsigned row_ = v / (unsigned)g.nz;
+        const int k = (int)(v - row_ * (unsigned)g.nz);
+        const int i = (int)(row_ / (unsigned)g.ny);
+        const int j = (int)(row_ - (unsigned)i * (unsigned)g.ny);
+        const int jp = (j + 1 == g.ny) ? 0 : j + 1;
+        const int kp = (k + 1 == g.nz) ? 0 : k + 1;
+        const size_t o = ((size_t)i * g.ny + j) * us + k;
+        const double* u0 = u;
+        const double* u1 = u + g.uplane;
+        const double* u2 = u + 2 * g.uplane;
+        const double u0_xp = at_x(u0, g, i, j, k, +1, halo_hi, halo_hi, us);
+        b[o] = (u0[o] - u0_xp) * chx + (u1[o] - u1[((size_t)i * g.ny + jp) * us + k]) * chy + (u2[o] - u2[((size_t)i * g.ny + j) * us + kp]) * chz;
+    }
+}
+
+int fgb_k_div_vector(fgb_ctx* ctx, const double* u, double* b, double alpha) {
+    const GridDev& g = ctx->g;
+    const size_t nvox = (size_t)g.lnx * g.ny * g.nz;
+    const double *lo, *hi;
+    halo_ptrs(ctx, &lo, &hi);
+    ProfScope ps(ctx, "div_vector");
+    const unsigned grid = fgb_wave_grid(ctx, (const void*)k_div_vector, 256, nvox, (size_t)ctx->sm_count * 16);
+    k_div_vector<<<grid, 256, 0, ctx->stream>>>(u, b, g, alpha, hi);
+    FGB_CHECK_LAUNCH(ctx, "k_div_vector");
+    return FGB_OK;
+}
+
+// mxpyTensor fg:20590-20596: r = -(x + y) over a whole component plane (padding included, as in the reference)
+__global__ void __launch_bounds__(256) k_mxpy(double* __restrict__ r, const double* __restrict__ x, const double* __restrict__ y, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) r[i] = -(x[i] + y[i]);
+}
+
+int fgb_k_mxpy(fgb_ctx* ctx, double* r, const double* x, const double* y) {
+    const size_t n = ctx->g.plane;
+    const unsigned grid = fgb_wave_grid(ctx, (const void*)k_mxpy, 256, n, (size_t)ctx->sm_count * 16);
+    k_mxpy<<<grid, 256, 0, ctx->stream>>>(r, x, y, n);
+    FGB_CHECK_LAUNCH(ctx, "k_mxpy");
+    return FGB_OK;
+}

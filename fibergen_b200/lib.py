@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libfgb200.so")
 # error codes (fgb200.h)
 FGB_OK, FGB_EINVAL, FGB_ENODEV, FGB_ENOMEM, FGB_ECUDA, FGB_EUNSUPPORTED, FGB_ENUMERIC, FGB_ECOMM = 0, -1, -2, -3, -4, -5, -6, -7
 MODES = {"elasticity": 0, "hyperelasticity": 1, "viscosity": 2, "heat": 3, "porous": 4}
-SCHEMES = {"collocated": 0, "staggered": 1}
+SCHEMES = {"collocated": 0, "staggered": 1, "willot": 2}
 LAWS = {"iso": 0, "general": 1, "tiso": 2, "scalar": 3, "aniso3": 4, "svk": 5, "nh": 6, "nh2": 7}
 MIXING = {"voigt": 0, "reuss": 1, "laminate": 2}
 
@@ -65,6 +65,10 @@ PROTOTYPES = {
     "fgb_min_detF": (C.c_int, [C.c_void_p, C.c_int, c_dp]),
     "fgb_mean_cauchy": (C.c_int, [C.c_void_p, C.c_int, C.c_double, c_dp]),
     "fgb_calc_displacement": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double]),
+    "fgb_g0div_hyper": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double]),
+    "fgb_grad_hyper": (C.c_int, [C.c_void_p, C.c_int]),
+    "fgb_calc_pressure": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double]),
+    "fgb_extrapolate_polynomial": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), c_dp, c_dp, C.c_int]),
     "fgb_ref_material": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_dp, c_dp]),
     "fgb_calc_stress": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]),
     "fgb_calc_stress_deriv": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]),

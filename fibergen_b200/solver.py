@@ -231,6 +231,8 @@ class LSSolver:
             value = "1" if value else "0"
         elif isinstance(value, float):
             value = repr(value)
+        elif isinstance(value, (list, tuple, np.ndarray)):
+            value = ",".join(repr(float(x)) for x in value)
         self.chk(self.lib.fgls_set(self.h, key.encode(), str(value).encode()))
 
     def add_material(self, name, law, *params):

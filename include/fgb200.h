@@ -47,9 +47,10 @@ typedef struct fgb_ctx fgb_ctx;
 #define FGB_MODE_HEAT            3
 #define FGB_MODE_POROUS          4
 
-/* LSSolver::_gamma_scheme (fg:14697); others -> FGB_EUNSUPPORTED */
+/* LSSolver::_gamma_scheme (fg:14697); half_staggered / full_staggered are handled above this layer (dfg transfer, fgb_dfg_*) */
 #define FGB_GAMMA_COLLOCATED 0
 #define FGB_GAMMA_STAGGERED  1
+#define FGB_GAMMA_WILLOT     2   /* GammaOperatorWillotR fg:20322 (elasticity, viscosity); needs a reference material with lambda_0 != 0 */
 
 /* material laws (fg:15211-15294) with their parameter vectors */
 #define FGB_LAW_ISO      0  /* LinearIsotropicMaterialLaw fg:11354           params: mu, lambda            */
@@ -130,6 +131,9 @@ int  fgb_copy(fgb_ctx* ctx, int src, int dst);                                  
 int  fgb_xpay(fgb_ctx* ctx, int r, int x, double a, int y);                      /* r = x + a*y      fg:9819 */
 int  fgb_xpaymz(fgb_ctx* ctx, int r, int x, double a, int y, int z);             /* r = x + a*(y-z)  fg:9993 */
 int  fgb_adjust_residual(fgb_ctx* ctx, int r, const double* E, int z);           /* r += E - z       fg:10012 */
+/* extrapolateLoadstepPolynomial fg:21468-21513: per voxel and component p = Vinv * (f_0 .. f_{n-1}), dst = tpowers . p with
+ * f_i the value of fields[i]; Vinv is n x n row-major, n <= 8.  dst may be one of the fields. */
+int  fgb_extrapolate_polynomial(fgb_ctx* ctx, int n, const int* fields, const double* Vinv, const double* tpowers, int dst);
 
 /* reductions; results are global over all ranks (fixed combine order) */
 int  fgb_inner(fgb_ctx* ctx, int a, int b, int c_or_neg, double* out);           /* innerProductL2 fg:20871/20955 */
@@ -165,9 +169,18 @@ int  fgb_div_staggered(fgb_ctx* ctx, int field);                                
 int  fgb_g0_staggered(fgb_ctx* ctx, double mu0, double lambda0, double alpha);   /* G0OperatorStaggered* fg:20101-20153 on the u buffer     */
 int  fgb_eps_staggered(fgb_ctx* ctx, int field, const double* E);                /* epsOperatorStaggered* fg:18614-18846: u buffer -> field */
 /* displacement fluctuation of a strain field, get_raw_field("u") fg:15517-15557: u = G0 div_h tau(eps) with tau = C0:eps
- * (elasticity, heat), (P - C0):F (hyperelasticity) or the viscosity dual form; always the staggered-grid operators, alpha = 1.
+ * (elasticity, heat: staggered-grid div_h and G0), the viscosity dual form (staggered), or in hyperelasticity tau = (P - C0):F with
+ * the collocated G0DivOperatorHyper (fg:15524-15527); alpha = 1.
  * tmp is a scratch field (overwritten); the result is left in the u buffer (fgb_u_download: 3 components, 1 for heat). */
 int  fgb_calc_displacement(fgb_ctx* ctx, int eps, int tmp, double mu0, double lambda0);
+/* G0DivOperatorHyper fg:20281-20286 (fftTensor, G0DivOperatorFourierHyper fg:20155-20218, fftInvVector), in place: components 0..2 of
+ * the 9-component field become alpha * G0 Div tau, collocated Fourier discretisation with xi = 2 pi m / L; 3..8 are left undefined. */
+int  fgb_g0div_hyper(fgb_ctx* ctx, int field, double mu0, double lambda0, double alpha);
+/* fftTensor, GradOperatorFourierHyper fg:22069-22116, fftInvTensor: components 0..2 hold a vector field q, all 9 receive grad q */
+int  fgb_grad_hyper(fgb_ctx* ctx, int field);
+/* get_raw_field("p") fg:15559-15573 (calcStressDiff, divOperatorStaggered, divVector fg:19983, poisson_solve fg:23454): the pressure
+ * is left in component 0 of the u buffer (fgb_u_download with ncomp = 1); tmp is a scratch field */
+int  fgb_calc_pressure(fgb_ctx* ctx, int eps, int tmp, double mu0, double lambda0);
 int  fgb_u_upload(fgb_ctx* ctx, const double* const* comps, int ncomp);          /* test access to the displacement buffer */
 int  fgb_u_download(fgb_ctx* ctx, double* const* comps, int ncomp);
 /* fftTensor / fftInvTensor (fg:18531-18584) on all components of a field, in place (forward scaled by 1/nxyz) */

@@ -20,6 +20,7 @@
 
 #ifdef __cplusplus
 #include <string>
+#include <utility>
 #include <vector>
 #include <memory>
 
@@ -68,7 +69,7 @@ public:
     double calcMeanEnergy();                                                         // fg:17765
     Vec    calcMeanCauchyStress();                                                   // fg:17920 (hyperelasticity)
     Mat    calcEffectiveProperties();                                                // fg:26030-26160 (Voigt form)
-    void   getField(const std::string& name, double* const* comps);                 // get_raw_field fg:15396: "epsilon", "sigma", "u"
+    void   getField(const std::string& name, double* const* comps);                 // get_raw_field fg:15396: "epsilon", "sigma", "u", "p"
     int    fieldComponents(const std::string& name) const;                          // planes getField(name) writes
     double mu0() const { return _mu_0; }
     double lambda0() const { return _lambda_0; }
@@ -91,6 +92,9 @@ private:
     friend class ErrorEstimator;
     void check(int rc) const;
     void fail(const std::string& msg) const;
+    void set_impl(const std::string& key, const std::string& value);
+    Vec  expandLoad(const Vec& e, const char* what) const;
+    void extrapolateLoadstep(const std::vector<std::pair<double, int>>& last, double t);   // fg:21454-21513
     void pushBC();
     bool runLoadsteppingSolver(const Vec& Emax, const Vec& Smax);
     void runSolver(const Vec& E, const Vec& S);
@@ -115,6 +119,9 @@ private:
         _cg_inner_product, _G0_solver;
     bool _freq_hack;
     std::vector<double> _loadsteps;
+    size_t _loadstep_extrapolation_order;          // 0 = none, 1 = linear, ... (fg:14696)
+    std::string _loadstep_extrapolation_method;    // "polynomial" (fg:14697; "transformation" is refused)
+    long _first_loadstep;                          // < 0: automatic (fg:21591)
     std::vector<double> _laminate_params;
 
     struct MaterialDef {
@@ -126,6 +133,7 @@ private:
     double _mu_0, _lambda_0;
 
     Vec _E, _S, _current_E, _current_S, _Id;
+    Vec _E_raw, _S_raw;                            // loads as given by the caller (expanded to dim by init())
     Mat _BC_P, _BC_Q, _BC_QC0, _BC_M, _BC_MQ;
 
     int _epsilon, _f1, _f2, _f3, _f4, _f5;    // device field ids (-1 = not allocated)

@@ -900,7 +900,7 @@ class LSSolver:
                  gamma_scheme="auto", mixing_rule="voigt", error_estimator="epsilon",
                  outer_error_estimator="epsilon", tol=1e-4, abs_tol=EPS, bc_tol=1e-3, maxiter=10000,
                  ref_scale=1.0, bc_relax=1.0, newton_relax=1.0, update_ref="loadstep", freq_hack=False,
-                 cg_reinit=0, loadsteps=1):
+                 cg_reinit=0, loadsteps=1, loadstep_extrapolation_order=0):
         self.nx, self.ny, self.nz = int(nx), int(ny), int(nz)
         self.dx, self.dy, self.dz = float(dx), float(dy), float(dz)
         self.nzc = self.nz // 2 + 1
@@ -935,6 +935,7 @@ class LSSolver:
         self.lambda_0 = 0.0
         self.reference_set = False
         self.loadsteps = [i / loadsteps for i in range(loadsteps + 1)]
+        self.loadstep_extrapolation_order = loadstep_extrapolation_order
         self.E = np.zeros(d)
         self.S = np.zeros(d)
         self.Id = np.zeros(d)
@@ -1099,21 +1100,86 @@ class LSSolver:
         return vec9(np.einsum('nik,njk->nij', P, F)).sum(axis=1)
 
     def calcDisplacement(self, eps=None):
-        """get_raw_field('u') fg:15517-15557: the displacement fluctuation u = G0 div_h tau of the converged field, tau = C0:eps
-        (elasticity, heat: calcStressConst fg:17973), (P - C0):F (hyperelasticity: calcStressDiff fg:18030), always with the
-        staggered-grid operators and alpha = 1; viscosity uses the dual reference 1/(4 mu0), lambda0 = inf, alpha = 1/(2 mu0)"""
+        """get_raw_field('u') fg:15509-15557: the displacement fluctuation of the converged field with alpha = 1.
+        elasticity / heat: tau = C0:eps (calcStressConst fg:17973), staggered div_h and G0 (fg:15519-15521, fg:15539-15542);
+        viscosity: tau = calcStressDiff, staggered operators with the dual reference 1/(4 mu0), lambda0 = inf, alpha = 1/(2 mu0)
+        (fg:15530-15537); hyperelasticity: tau = calcStressDiff, then G0DivOperatorHyper -- the COLLOCATED Fourier divergence
+        and G0 with xi = 2 pi m / L (fg:15524-15527 -> fg:20281 -> fg:20155)."""
         eps = self.epsilon if eps is None else eps
+        if self.mode == "hyperelasticity":
+            return self.G0DivOperatorHyper(self.mu_0, self.lambda_0, self.calcStressDiff(eps), 1.0)
         if self.mode == "viscosity":
             tau = self.calcStressDiff(eps)
             m, l, a = 1 / (4 * self.mu_0), math.inf, 1 / (2 * self.mu_0)
-        elif self.mode == "hyperelasticity":
-            tau = self.calcStressDiff(eps)
-            m, l, a = self.mu_0, self.lambda_0, 1.0
         else:
             tau = self.calcStressConst(self.mu_0, self.lambda_0, eps)
             m, l, a = self.mu_0, self.lambda_0, 1.0
         f = self.divOperatorStaggered(tau)
         return self.ifft(self.G0OperatorFourierStaggered(m, l, self.fft(f), a))
+
+    def calcPressure(self, eps=None):
+        """get_raw_field('p') fg:15559-15573: calcStressDiff, divOperatorStaggered, divVector(alpha = 1/(2 mu0)), poisson_solve"""
+        eps = self.epsilon if eps is None else eps
+        f = self.divOperatorStaggered(self.calcStressDiff(eps))
+        return self.poisson_solve(self.divVector(f, 1 / (2 * self.mu_0)))
+
+    def divVector(self, tau, alpha=1.0):
+        """fg:19983-20003: b = sum_a (tau_a(x) - tau_a(x + e_a)) * alpha * n_a / L_a (forward neighbour, periodic)"""
+        hx, hy, hz = self._h()
+        return ((tau[0] - np.roll(tau[0], -1, 0)) * (alpha * hx) + (tau[1] - np.roll(tau[1], -1, 1)) * (alpha * hy)
+                + (tau[2] - np.roll(tau[2], -1, 2)) * (alpha * hz))
+
+    def poisson_solve(self, f):
+        """fg:23454-23499: unscaled forward transform, division by 2 nxyz sum_a (n_a/L_a)^2 (cos(2 pi i_a / n_a) - 1), zero mean,
+        unscaled backward transform"""
+        uc = sfft.rfftn(f, axes=(-3, -2, -1), workers=FFT_WORKERS)
+        c = 2.0 * self.nxyz
+        terms = []
+        for n, L, cnt, shape in ((self.nx, self.dx, self.nx, (-1, 1, 1)), (self.ny, self.dy, self.ny, (1, -1, 1)),
+                                 (self.nz, self.dz, self.nzc, (1, 1, -1))):
+            xi = (2.0 * math.pi / n) * np.arange(cnt, dtype=float)
+            terms.append(((n * n / (L * L)) * (np.cos(xi) - 1.0)).reshape(shape))
+        with np.errstate(divide='ignore', invalid='ignore'):
+            uc = uc / (c * (terms[0] + terms[1] + terms[2]))
+        uc[0, 0, 0] = 0
+        return sfft.irfftn(uc, s=(self.nx, self.ny, self.nz), axes=(-3, -2, -1), norm="forward", workers=FFT_WORKERS)
+
+    # -- collocated Fourier div / grad for hyperelasticity (fg:20155-20218, fg:22069-22116) ------------
+    def _xi2pi(self):
+        x0 = (2 * math.pi / self.dx) * self._freq(self.nx)
+        x1 = (2 * math.pi / self.dy) * self._freq(self.ny)
+        x2 = (2 * math.pi / self.dz) * self._freq(self.nz, self.nzc)
+        return x0[:, None, None], x1[None, :, None], x2[None, None, :]
+
+    def G0DivOperatorFourierHyper(self, mu_0, lambda_0, tau_hat, alpha=1.0):
+        """fg:20155-20218: f^ = i xi . tau^ (rows of the non-symmetric 9-component tensor), u^ = c1 f^ + c2 xi (xi . f^), u^(0) = 0"""
+        x = self._xi2pi()
+        c10 = -alpha / (2 * mu_0)
+        with np.errstate(divide='ignore'):
+            c20 = alpha / (2 * mu_0 * (1 + np.float64(2 * mu_0) / np.float64(lambda_0)))
+        norm2 = x[0] * x[0] + x[1] * x[1] + x[2] * x[2]
+        with np.errstate(divide='ignore', invalid='ignore'):
+            c1 = c10 / norm2
+            c2 = c20 / (norm2 * norm2)
+            f1 = 1j * (x[0] * tau_hat[0] + x[1] * tau_hat[5] + x[2] * tau_hat[4])
+            f2 = 1j * (x[0] * tau_hat[8] + x[1] * tau_hat[1] + x[2] * tau_hat[3])
+            f3 = 1j * (x[0] * tau_hat[7] + x[1] * tau_hat[6] + x[2] * tau_hat[2])
+            eta = np.stack([c1 * f1 + c2 * (x[0] * x[0] * f1 + x[0] * x[1] * f2 + x[0] * x[2] * f3),
+                            c1 * f2 + c2 * (x[1] * x[0] * f1 + x[1] * x[1] * f2 + x[1] * x[2] * f3),
+                            c1 * f3 + c2 * (x[2] * x[0] * f1 + x[2] * x[1] * f2 + x[2] * x[2] * f3)])
+        eta[:, 0, 0, 0] = 0
+        return eta
+
+    def G0DivOperatorHyper(self, mu_0, lambda_0, tau, alpha=-1.0):
+        """fg:20281-20286: fftTensor, G0DivOperatorFourierHyper, fftInvVector"""
+        return self.ifft(self.G0DivOperatorFourierHyper(mu_0, lambda_0, self.fft(tau), alpha))
+
+    def GradOperatorFourierHyper(self, q_hat):
+        """fg:22069-22116: W^ = i xi (x) q^ in the stored component order 11,22,33,23,13,12,32,31,21"""
+        x0, x1, x2 = self._xi2pi()
+        q0, q1, q2 = q_hat[0], q_hat[1], q_hat[2]
+        return np.stack([1j * x0 * q0, 1j * x1 * q1, 1j * x2 * q2, 1j * x2 * q1, 1j * x2 * q0, 1j * x1 * q0,
+                         1j * x1 * q2, 1j * x0 * q2, 1j * x0 * q1])
 
     # -- FFT wrappers (fg:18481-18584): forward scaled 1/nxyz, backward unscaled ---------
     def fft(self, x):
@@ -1396,11 +1462,7 @@ class LSSolver:
         if self.gamma_scheme == "staggered":                         # fg:20288-20300, 20342-20378
             return self._GammaOperatorStaggered(E, mu_0, lambda_0, tau, alpha)
         if self.gamma_scheme == "willot" and self.mode == "elasticity":   # GammaOperatorWillotR fg:20322-20330
-            tau_hat = self.fft(tau)
-            self.F0 = tau_hat[:, 0, 0, 0].real.copy()
-            eta_hat = self.GammaOperatorFourierWillotR(E, mu_0, lambda_0, tau_hat, alpha, beta)
-            eta_hat[:, 0, 0, 0] += alpha * self.calcBCProjector()
-            return self.ifft(eta_hat)
+            return self._GammaOperatorWillotR(E, mu_0, lambda_0, tau, alpha, beta)
         raise RuntimeError("Unknown gamma scheme '%s'" % self.gamma_scheme)
 
     def _GammaOperatorStaggered(self, E, mu_0, lambda_0, tau, alpha):
@@ -1412,13 +1474,36 @@ class LSSolver:
         return eta + R.reshape((-1, 1, 1, 1))
 
     def DeltaOperator(self, E, mu_0, lambda_0, tau, alpha=-1.0):
-        """fg:20422-20460 (staggered) -- viscosity dual formulation"""
-        if self.gamma_scheme != "staggered":
-            raise RuntimeError("oracle: viscosity implemented for the staggered scheme only")
+        """fg:20474-20486 -- viscosity dual formulation: DeltaOperatorStaggered fg:20422-20460, DeltaOperatorWillotR fg:20380-20418,
+        DeltaOperatorCollocated fg:20462-20471"""
+        if self.gamma_scheme == "collocated":
+            # fftTensor(zero_trace) fg:18531-18559: component 0 is not transformed, tau^_0 = -(tau^_1 + tau^_2)
+            tau_hat = self.fft(tau)
+            tau_hat[0] = -(tau_hat[1] + tau_hat[2])
+            m = 1 / (4 * mu_0)
+            self.F0 = tau_hat[:, 0, 0, 0].real.copy()                # applyDeltaFourier fg:19075-19080
+            eta_hat = self.GammaOperatorFourierCollocated(E, -1.0 / (4 * m), math.inf, tau_hat, alpha, 2 * alpha * m)
+            eta_hat[:, 0, 0, 0] += alpha * self.calcBCProjector()
+            eta = self.ifft(eta_hat)                                 # fftInvTensor(zero_trace) fg:18563-18584
+            eta[0] = -(eta[1] + eta[2])
+            return eta
         mu_0 = 1 / (4 * mu_0)
         adj = E - 2 * alpha * mu_0 * self.average(tau)
-        eta = self._GammaOperatorStaggered(adj, -1.0 / (4 * mu_0), math.inf, tau, alpha)
+        if self.gamma_scheme == "staggered":
+            eta = self._GammaOperatorStaggered(adj, -1.0 / (4 * mu_0), math.inf, tau, alpha)
+        elif self.gamma_scheme == "willot":
+            eta = self._GammaOperatorWillotR(adj, -1.0 / (4 * mu_0), math.inf, tau, alpha, 0.0)
+        else:
+            raise RuntimeError("Unknown gamma scheme '%s'" % self.gamma_scheme)
         return eta + (2 * alpha * mu_0) * tau
+
+    def _GammaOperatorWillotR(self, E, mu_0, lambda_0, tau, alpha, beta):
+        """GammaOperatorWillotR fg:20322-20330"""
+        tau_hat = self.fft(tau)
+        self.F0 = tau_hat[:, 0, 0, 0].real.copy()
+        eta_hat = self.GammaOperatorFourierWillotR(E, mu_0, lambda_0, tau_hat, alpha, beta)
+        eta_hat[:, 0, 0, 0] += alpha * self.calcBCProjector()
+        return self.ifft(eta_hat)
 
     # -- schemes (fg:20536-20590) ------------------------------------------------------
     def basicScheme(self, E, eps):
@@ -1524,14 +1609,32 @@ class LSSolver:
         if self.mode == "hyperelasticity":
             self.epsilon += self.Id.reshape(-1, 1, 1, 1)
         first = 0 if len(self.loadsteps) > 2 else 1
+        last = []                                                    # (t, eps) of the previous load steps, fg:21444-21447
         for istep in range(first, len(self.loadsteps)):
             t = self.loadsteps[istep]
             E = t * self.E
             S = t * self.S
             if self.mode == "hyperelasticity":
                 E = E + (1 - t) * dyad4_mv(self.BC_P, self.Id)
+            if self.loadstep_extrapolation_order > 0 and istep > first:      # fg:21634-21650
+                while len(last) > self.loadstep_extrapolation_order:
+                    last.pop(0)
+                last.append((self.loadsteps[istep - 1], self.epsilon.copy()))
+                if len(last) >= 2:
+                    self.extrapolateLoadstepPolynomial(last, t)
             self.runSolver(E, S)
         return False
+
+    def extrapolateLoadstepPolynomial(self, last, t):
+        """fg:21468-21513: per voxel the polynomial through the stored load steps (Vandermonde inverse by gesv), evaluated at t"""
+        import scipy.linalg as sla
+        n = len(last)
+        V = np.array([[ls[0] ** j for j in range(n)] for ls in last], dtype=float)
+        tp = np.array([t ** i for i in range(n)], dtype=float)
+        Vinv = sla.solve(V, np.eye(n))
+        f = np.stack([ls[1] for ls in last])                         # (n, d, nx, ny, nz)
+        pcoef = np.tensordot(Vinv, f, axes=(1, 0))
+        self.epsilon = np.tensordot(tp, pcoef, axes=(0, 0))
 
     def runSolver(self, E, S):
         self.current_E, self.current_S = E, S

@@ -1,4 +1,4 @@
-"""Writes tests/golden/golden_r01.npz from the CPU oracle:  python tests/golden/make_golden.py
+"""Writes tests/golden/golden_r02.npz from the CPU oracle:  python tests/golden/make_golden.py
 (run in the build container; a few seconds).  See cases.py for what a case is."""
 import os
 import sys
@@ -18,6 +18,8 @@ def solve(case):
         o.add_phase(name, gc.oracle_law(fo, case["mode"], law, params), phi)
     if case["normals"] is not None:
         o.set_normals(case["normals"])
+    if case["ref"] is not None:
+        o.set_reference(*case["ref"])
     o.setStrain(case["E"])
     o.run()
     return o

@@ -1,0 +1,172 @@
+"""Round-2 operators through the C ABI against the CPU oracle: the collocated Fourier div / grad of the hyperelastic
+post-processing (G0DivOperatorFourierHyper fg:20155, GradOperatorFourierHyper fg:22069) with the reference's own identities
+(fg:24518-24583), Willot's rotated-scheme operator (fg:19083), the zero-trace collocated Delta operator of the viscosity mode
+(fg:20462-20471), the pressure field (fg:15559-15573) and the load-step extrapolation (fg:21468-21513)."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+from oracle import fg_oracle as fo
+import fibergen_b200 as fb
+from fibergen_b200.solver import _dp
+from microstructures import sphere_phi
+from test_gpu_schemes import build_pair, compare, el_phases
+
+pytestmark = pytest.mark.gpu
+
+GRIDS = [((2, 1, 1), (1., 1., 1.)), ((41, 33, 11), (1., 1., 1.)), ((41, 33, 11), (41., 33., 11.)), ((12, 9, 1), (1., 2., 1.)),
+         ((16, 16, 16), (1., 1., 1.)), ((64, 8, 6), (2., 1., 3.)), ((7, 5, 3), (1., 1., 1.))]
+MU0, LAM0 = 1324.3, 324.2
+TOL = math.sqrt(np.finfo(float).eps)
+
+
+def relerr(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.mark.parametrize("n,L", GRIDS)
+def test_g0div_and_grad_hyper(n, L):
+    ctx = fb.Context(*n, *L, mode="hyperelasticity", gamma_scheme="staggered")
+    o = fo.LSSolver(*n, *L, mode="hyperelasticity")
+    rng = np.random.default_rng(11)
+    tau = rng.standard_normal((9,) + n)
+    for mu0, lam0, alpha in ((MU0, LAM0, 1.0), (0.7, 0.0, -1.0)):
+        f = ctx.field(tau)
+        ctx.chk(ctx.lib.fgb_g0div_hyper(ctx.h, f, mu0, lam0, alpha))
+        want = o.G0DivOperatorHyper(mu0, lam0, tau, alpha)
+        assert relerr(ctx.download(f)[:3], want) < 2e-12
+        ctx.chk(ctx.lib.fgb_field_free(ctx.h, f))
+    q = np.zeros((9,) + n)
+    q[:3] = rng.standard_normal((3,) + n)
+    f = ctx.field(q)
+    ctx.chk(ctx.lib.fgb_grad_hyper(ctx.h, f))
+    want = o.ifft(o.GradOperatorFourierHyper(o.fft(q[:3])))
+    assert relerr(ctx.download(f), want) < 2e-12
+    ctx.close()
+
+
+@pytest.mark.parametrize("n,L", GRIDS[:3])
+def test_reference_hyper_identities_on_device(n, L):
+    """fg:24518-24555 (grad G0 Div C0 grad u == grad u) and fg:24558-24583 (Gamma_collocated == grad G0 Div) on the device"""
+    ctx = fb.Context(*n, *L, mode="hyperelasticity", gamma_scheme="collocated")
+    rng = np.random.default_rng(12)
+    q = np.zeros((9,) + n)
+    q[:3] = rng.random((3,) + n)
+    W = ctx.field(q)
+    T = ctx.field()
+    ctx.chk(ctx.lib.fgb_grad_hyper(ctx.h, W))
+    org = ctx.download(W)
+    ctx.chk(ctx.lib.fgb_calc_stress_const(ctx.h, W, T, MU0, LAM0))
+    ctx.chk(ctx.lib.fgb_g0div_hyper(ctx.h, T, MU0, LAM0, 1.0))
+    ctx.chk(ctx.lib.fgb_grad_hyper(ctx.h, T))
+    scale = max(1.0, np.abs(org).max())
+    assert np.linalg.norm(np.abs(ctx.download(T) - org).reshape(9, -1).max(axis=1)) <= TOL * scale
+    ctx.upload(W, rng.random((9,) + n))
+    ctx.gamma(W, np.zeros(9), MU0, LAM0, -1.0, 0.0)
+    W1 = ctx.download(W)
+    ctx.chk(ctx.lib.fgb_calc_stress_const(ctx.h, W, T, MU0, LAM0))
+    ctx.chk(ctx.lib.fgb_g0div_hyper(ctx.h, T, MU0, LAM0, 1.0))
+    ctx.chk(ctx.lib.fgb_grad_hyper(ctx.h, T))
+    scale = max(1.0, np.abs(W1).max())
+    assert np.linalg.norm(np.abs(ctx.download(T) - W1).reshape(9, -1).max(axis=1)) <= TOL * scale
+    ctx.close()
+
+
+@pytest.mark.parametrize("n,L", GRIDS)
+def test_willot_operator(n, L):
+    """GammaOperatorWillotR (fg:20322) vs the oracle, and the reference's `WillotR epsG0div identity` (fg:24107) on the device"""
+    ctx = fb.Context(*n, *L, mode="elasticity", gamma_scheme="willot")
+    o = fo.LSSolver(*n, *L, mode="elasticity", gamma_scheme="willot")
+    rng = np.random.default_rng(13)
+    tau = rng.standard_normal((6,) + n)
+    E = rng.standard_normal(6)
+    for mu0, lam0, alpha, beta in ((MU0, LAM0, 1.0, 0.0), (2.0, 1.0, -8.0, 1.0)):
+        f = ctx.field(tau)
+        ctx.gamma(f, E, mu0, lam0, alpha, beta)
+        o.set_reference(mu0, lam0)
+        o.setBCProjector(fo.Id4(6))
+        want = o.GammaOperator(E, mu0, lam0, tau, alpha, beta)
+        got = ctx.download(f)
+        if np.isnan(want).any():
+            # 2x1x1: the rotated scheme's frequency vector vanishes at the Nyquist frequency (tan(pi/2) * (1 + e^{i pi}) = inf * 0)
+            assert np.array_equal(np.isnan(got), np.isnan(want))
+        else:
+            assert relerr(got, want) < 5e-12
+        ctx.chk(ctx.lib.fgb_field_free(ctx.h, f))
+    ctx.close()
+
+
+def test_willot_scheme_solve():
+    n = (16, 16, 16)
+    for method, ee in (("cg", "residual"), ("basic", "sigma")):
+        s = fb.LSSolver(*n, mode="elasticity", method=method, gamma_scheme="willot", error_estimator=ee, tol=1e-8)
+        o = fo.LSSolver(*n, mode="elasticity", method=method, gamma_scheme="willot", error_estimator=ee, tol=1e-8)
+        for m, (name, law, params, olaw, phi) in enumerate(el_phases(n)):
+            s.add_material(name, law, *params)
+            o.add_phase(name, olaw, phi)
+        s.set_reference(1.0, 2.0)
+        o.set_reference(1.0, 2.0)
+        s.init()
+        for m, (name, law, params, olaw, phi) in enumerate(el_phases(n)):
+            s.set_phase(m, phi)
+        compare(s, o, E=[1, 0, 0, 0, 0.3, 0])
+
+
+@pytest.mark.parametrize("scheme", ["collocated", "willot", "staggered"])
+@pytest.mark.parametrize("method,ee", [("cg", "residual"), ("basic", "epsilon")])
+def test_viscosity_all_schemes(scheme, method, ee):
+    """DeltaOperatorCollocated (zero-trace transform, fg:20462), DeltaOperatorWillotR (fg:20380), DeltaOperatorStaggered (fg:20422)"""
+    n = (12, 10, 8)
+    phi = sphere_phi(n, R=0.3, sub=1)
+    kw = dict(mode="viscosity", method=method, gamma_scheme=scheme, error_estimator=ee, tol=1e-7)
+    s = fb.LSSolver(*n, **kw)
+    o = fo.LSSolver(*n, **kw)
+    s.add_material("fluid", "iso", 1.0)
+    s.add_material("solid", "iso", 1e-3)
+    if scheme == "willot":
+        s.set_reference(1.0, 5.0)
+        o.set_reference(1.0, 5.0)
+    s.init()
+    s.set_phase(0, 1 - phi)
+    s.set_phase(1, phi)
+    o.add_phase("fluid", fo.ScalarLinearIsotropic(0.5 * 1.0, 6), 1 - phi)
+    o.add_phase("solid", fo.ScalarLinearIsotropic(0.5 * 1e-3, 6), phi)
+    compare(s, o, E=[0, 0, 0, 0, 0, 1.0])
+    p_o = o.calcPressure()
+    p_s = s.get_field("p")
+    assert p_s.shape == (1,) + n
+    assert np.abs(p_s[0] - p_o).max() <= 1e-8 * max(np.abs(p_o).max(), 1e-300)
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_loadstep_extrapolation(order):
+    """loadstep_extrapolation_order > 0: polynomial start value from the previous load steps (fg:21634-21650, fg:21468-21513)"""
+    n = (10, 10, 10)
+    phi = sphere_phi(n, R=0.3, sub=1)
+    phases = [("matrix", "nh", (10.0, 10.0), fo.NeoHooke(10.0, 10.0), 1 - phi),
+              ("incl", "nh", (10.0, 100.0), fo.NeoHooke(10.0, 100.0), phi)]
+    s, o = build_pair(n, mode="hyperelasticity", phases=phases, method="cg", error_estimator="residual",
+                      outer_error_estimator="sigma", tol=1e-6, loadsteps=4, loadstep_extrapolation_order=order)
+    compare(s, o, E=np.array([1, 1.1, 1, 0, 0, 0, 0, 0, 0], dtype=float))
+
+
+def test_loads_before_init_and_setting_validation():
+    """loads set before init() must neither corrupt memory nor be dropped; malformed values raise"""
+    n = (8, 8, 8)
+    s = fb.LSSolver(*n, mode="hyperelasticity", method="cg", error_estimator="residual", tol=1e-6)
+    F = np.array([1, 1.05, 1, 0, 0.01, 0, 0, 0.02, 0], dtype=float)
+    s.set_strain(F)                                   # before init: kept
+    s.add_material("m", "nh", 10.0, 10.0)
+    s.init()
+    s.set_phase(0, np.ones(n))
+    s.run()
+    assert np.allclose(s.get_mean_strain(), F, atol=1e-12)
+    for key, val in (("tol", "abc"), ("maxiter", "ten"), ("loadsteps", "0"), ("tol", "[0.25"), ("freq_hack", "maybe")):
+        with pytest.raises(fb.FgbError):
+            s.set(key, val)
+    s.set("loadsteps", [0.0, 0.25, 1.0])              # sequences are joined with ','
+    s2 = fb.LSSolver(4, 4, 4, mode="heat")
+    with pytest.raises(fb.FgbError, match="Invalid size"):
+        s2.set_strain([1, 0, 0, 0])

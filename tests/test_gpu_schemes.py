@@ -220,10 +220,14 @@ def test_homogeneous_and_error_paths():
     s2.add_material("m", "iso", 1.0, 1.0)
     with pytest.raises(fb.FgbError, match="Unknown solver method"):
         s2.init()
-    s3 = fb.LSSolver(4, 4, 4, gamma_scheme="willot")
+    s3 = fb.LSSolver(4, 4, 4, gamma_scheme="rotated")
     s3.add_material("m", "iso", 1.0, 1.0)
     with pytest.raises(fb.FgbError, match="gamma scheme"):
         s3.init()
+    s4 = fb.LSSolver(4, 4, 4, mode="heat", gamma_scheme="willot")           # fg:20488-20531: willot exists for elasticity / viscosity only
+    s4.add_material("m", "iso", 1.0)
+    with pytest.raises(fb.FgbError, match="gamma scheme"):
+        s4.init()
 
 
 def test_convergence_callback_and_maxiter():

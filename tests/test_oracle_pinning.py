@@ -75,6 +75,34 @@ def test_staggered_identity(n, L, mode):
     assert np.linalg.norm(np.abs(t - org).reshape(d, -1).max(axis=1)) <= TOL
 
 
+@pytest.mark.parametrize("n,L", GRIDS)
+def test_g0div_hyper_identity(n, L):
+    """fg:24518-24555 "G0DivHyper identity": grad G0 Div (C0 : grad u) == grad u with the collocated Fourier operators"""
+    s = mk(n, L, "hyperelasticity", "collocated")
+    rng = np.random.default_rng(4)
+    u = rng.random((3,) + n)
+    W = s.ifft(s.GradOperatorFourierHyper(s.fft(u)))
+    org = W.copy()
+    W = s.calcStressConst(s.mu_0, s.lambda_0, W)
+    u = s.G0DivOperatorHyper(s.mu_0, s.lambda_0, W, 1)
+    W = s.ifft(s.GradOperatorFourierHyper(s.fft(u)))
+    scale = max(1.0, np.abs(org).max())
+    assert np.linalg.norm(np.abs(W - org).reshape(9, -1).max(axis=1)) <= TOL * scale
+
+
+@pytest.mark.parametrize("n,L", GRIDS)
+def test_gamma_hyper_identity(n, L):
+    """fg:24558-24583 "GammaHyper identity": Gamma_collocated == grad G0 Div for fields in the range of Gamma"""
+    s = mk(n, L, "hyperelasticity", "collocated")
+    rng = np.random.default_rng(5)
+    W1 = s.GammaOperator(np.zeros(9), s.mu_0, s.lambda_0, rng.random((9,) + n))
+    W2 = s.calcStressConst(s.mu_0, s.lambda_0, W1)
+    h = s.G0DivOperatorFourierHyper(s.mu_0, s.lambda_0, s.fft(W2), 1)
+    W2 = s.ifft(s.GradOperatorFourierHyper(h))
+    scale = max(1.0, np.abs(W1).max())
+    assert np.linalg.norm(np.abs(W2 - W1).reshape(9, -1).max(axis=1)) <= TOL * scale
+
+
 @pytest.mark.parametrize("kw", [dict(), dict(tol=1e-10), dict(tol=1e-10, gamma_scheme="collocated"),
                                 dict(tol=1e-9, method="basic", error_estimator="sigma"),
                                 dict(tol=1e-9, method="polarization", error_estimator="sigma")])
