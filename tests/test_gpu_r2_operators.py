@@ -36,7 +36,7 @@ def test_g0div_and_grad_hyper(n, L):
         f = ctx.field(tau)
         ctx.chk(ctx.lib.fgb_g0div_hyper(ctx.h, f, mu0, lam0, alpha))
         want = o.G0DivOperatorHyper(mu0, lam0, tau, alpha)
-        assert relerr(ctx.download(f)[:3], want) < 2e-12
+        assert relerr(ctx.download(f)[:3], want) < 5e-11      # O(p^2) stages at the prime lengths 41, 11 + cancellation in i xi . tau
         ctx.chk(ctx.lib.fgb_field_free(ctx.h, f))
     q = np.zeros((9,) + n)
     q[:3] = rng.standard_normal((3,) + n)
