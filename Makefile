@@ -11,6 +11,9 @@ LIB := fibergen_b200/libfgb200.so
 
 all: $(LIB)
 
+# geometric predicates of the phase initialisation: same products and sums as the reference's scalar code (no FMA contraction)
+$(OBJ)/phase.o: NVFLAGS += -fmad=false
+
 $(OBJ)/%.o: $(SRC)/%.cu $(wildcard $(SRC)/*.h) $(wildcard $(SRC)/*.cuh) include/fgb200.h
 	@mkdir -p $(OBJ)
 	$(NVCC) $(NVFLAGS) -c $< -o $@

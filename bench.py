@@ -1,16 +1,20 @@
 #!/usr/bin/env python
-"""bench.py -- voxel-iterations/s of the Lippmann-Schwinger CG iteration on B200 (BASELINE.json metric).
+"""bench.py -- voxel-iterations/s of the Lippmann-Schwinger solve loop on B200 (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port on the host cores
+    python bench.py --gpus N --steps K --warmup W                 # this repo's CUDA path, BASELINE config 2, weak scaling
+    python bench.py --config c1|c3|c4 ...                         # the other single-GPU configurations (parity-test shapes, extra lines)
+    python bench.py --scaling strong --grid 1024 --gpus 8 ...     # north_star target: one 1024^3 cell over the ranks, solved to tolerance
+    python bench.py --impl reference --gpus N --steps K ...       # CPU arm: the OpenMP restatement of the same iteration on the host cores
 
-A "step" is one CG iteration (runCGElasticity hot loop, fg:23206-23246) = one pass of the hot path
-(material law -> div -> 3-D FFT -> G0 -> inverse FFT -> sym-grad -> dots -> vector updates) over the grid.
-Workload at N=1: BASELINE config 2 -- 256^3 short-fibre composite, linear elasticity, CG, staggered grid,
-Voigt mixing, residual estimator.  N>1: weak scaling, 256^3 voxels per GPU, global grid 256x512x256 / 256x512x512 /
-512x512x512 for N = 2 / 4 / 8 (periodic tiling of the same cell), x-slab partition.
-Timing: CUDA events on the launching stream, W warm-up iterations, K timed, barrier + synchronize on both
-sides, max over ranks.  Inputs (3.5 GB of fields) are far larger than the 126 MB L2, so no explicit flush.
+A "step" is one solver iteration = one pass of the hot path (material law -> div -> 3-D FFT -> Green operator -> inverse FFT ->
+sym-grad -> dots -> vector updates) over the grid: a CG iteration of runCGElasticity (fg:23206-23246) for c2/c3/c5, a basic
+iteration (fg:21786) for c1, an inner CG iteration of runCGHyper (fg:22844-23088) for c4.
+Workload at N=1: BASELINE config 2 -- 256^3 short-fibre composite (648 capsules, 15 vol-%, committed fibre list), linear
+elasticity, CG, staggered grid, Voigt mixing, residual estimator.  N>1 (default): weak scaling, 256^3 voxels per GPU, the global
+grid is the periodic continuation of the cell (256x512x256 / 256x512x512 / 512^3 for N = 2 / 4 / 8), x-slab partition.
+The phase fractions are computed on the device from the fibre list (fgb_init_phase_capsules: the reference's initPhi).
+Timing: CUDA events on the launching stream, W warm-up iterations, K timed, barrier + synchronize on both sides, max over ranks.
+The fields (3.5 GB at 256^3) are far larger than the 126 MB L2, so there is no explicit flush.
 """
 import argparse
 import json
@@ -28,20 +32,27 @@ import numpy as np
 
 METRIC = "voxel-iterations/sec"
 UNIT = "voxel-iterations/s"
-B_ALG_CG_STAGGERED = 728.0        # algorithmic bytes per voxel-iteration, SURVEY.md 8(d) / BASELINE.md section 2
 
 # matrix / fibre of demo/elasticity/sfrp_parameter_fit
 E_M, NU_M, E_F, NU_F = 1.665, 0.36, 73.0, 0.18
 
-# algorithmic bytes per voxel of each kernel of the unfused iteration (d=6 tensor comps, u=3 vector comps, 2 phases)
-KERNEL_BYTES_PER_VOXEL = {
-    "calc_stress": (6 + 1 + 6) * 8, "div_staggered": (6 + 3) * 8, "fft_z_r2c": 2 * 3 * 8, "fft_y_fwd": 2 * 3 * 8,
-    "fft_x_green": 2 * 3 * 8, "fft_y_bwd": 2 * 3 * 8, "fft_z_c2r": 2 * 3 * 8, "eps_staggered": (3 + 6) * 8,
-    "inner_product": 2 * 6 * 8 + 6 * 8, "cg_update": 6 * 6 * 8, "xpay": 3 * 6 * 8,
-    "cg_direction_stress_div": (12 + 1 + 6 + 3) * 8, "stress_div": (6 + 1 + 3) * 8, "eps_dot": (3 + 6 + 6) * 8,
-    # implicit operator result (FGB_W_IMPLICIT): the sum reads u and p only, the update reads x, r, p, u and writes x, r
-    "eps_dot_implicit": (3 + 6) * 8, "cg_update_implicit": (3 * 6 + 3 + 2 * 6) * 8,
-}
+# algorithmic bytes per voxel-iteration, SURVEY.md 8(d) / BASELINE.md section 2; "moved": what this implementation actually moves
+# where it differs (the CG operator result w is never stored on the fused path: 72 B less)
+B_ALG = {"c1": 296.0, "c2": 728.0, "c3": 336.0, "c4": 1064.0}
+B_MOVED = {"c2": 656.0}
+
+# algorithmic bytes per voxel of each kernel (d tensor comps, u vector comps, 2 phases); d, u substituted per config
+def kernel_bytes(d, u, nph=2):
+    return {
+        "calc_stress": (d + nph - 1 + d) * 8, "calc_stress_deriv": (2 * d + nph - 1 + d) * 8, "div_staggered": (d + u) * 8,
+        "fft_z_r2c": 2 * u * 8, "fft_y_fwd": 2 * u * 8, "fft_x_green": 2 * u * 8, "fft_y_bwd": 2 * u * 8, "fft_z_c2r": 2 * u * 8,
+        "fft_y_fwd_p2p": 2 * u * 8,
+        "eps_staggered": (u + d) * 8, "inner_product": 3 * d * 8, "cg_update": 6 * d * 8, "xpay": 3 * d * 8,
+        "cg_direction_stress_div": (2 * d + nph - 1 + d + u) * 8, "stress_div": (d + nph - 1 + u) * 8, "eps_dot": (u + 2 * d) * 8,
+        # implicit operator result (FGB_W_IMPLICIT): the sum reads u and p only, the update reads x, r, p, u and writes x, r
+        "eps_dot_implicit": (u + d) * 8, "cg_update_implicit": (3 * d + u + 2 * d) * 8,
+        "heat_dir_flux_div": (2 * d + d + d + u) * 8, "copy": 2 * d * 8,
+    }
 
 
 def lame(E, nu):
@@ -103,14 +114,65 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def microstructure(n, seed=0):
-    from microstructures import capsule_fibers
-    phi, nf = capsule_fibers(n, seed=seed, vol_frac=0.15, diameter_vox=8.0, aspect=10.0, acg=(0.7, 0.2, 0.1), max_tries=6000)
-    return phi, nf
+# ------------------------------------------------------------------------------------------------ workloads
+def workload(cfg, world, scaling, grid):
+    """-> dict: cell n (voxels of the periodic fibre cell), tile (cells per axis), solver settings, materials, load, fibres"""
+    from microstructures import config2_fibres
+    w = {"cfg": cfg}
+    if cfg in ("c2", "c3", "c4"):
+        Cs, Ds, R, Lc = config2_fibres()
+        w["cell"] = 256
+        w["fibres"] = (Cs, Ds, R, Lc)
+    if cfg == "c1":
+        w.update(cell=grid or 64, tile=(1, 1, 1), mode="elasticity",
+                 settings=dict(method="basic", gamma_scheme="staggered", mixing_rule="voigt", error_estimator="sigma"),
+                 materials=[("matrix", "iso", lame(1.0, 0.3)[::-1]), ("inclusion", "iso", lame(10.0, 0.3)[::-1])],
+                 load=[1, 0, 0, 0, 0, 0], d=6, u=3, sphere=0.25,
+                 name="config 1: single spherical inclusion (R = 0.25 L), linear elasticity, basic scheme, staggered grid")
+        return w
+    if cfg == "c2":
+        if scaling == "strong":
+            t = (grid or 1024) // 256
+            tile = (t, t, t)
+        else:
+            tile = {1: (1, 1, 1), 2: (1, 2, 1), 4: (1, 2, 2), 8: (2, 2, 2)}.get(world, (world, 1, 1))
+            if 256 * tile[0] % world or 256 * tile[1] % world:
+                tile = (world, 1, 1)
+        lam_m, mu_m = lame(E_M, NU_M)
+        lam_f, mu_f = lame(E_F, NU_F)
+        w.update(tile=tile, mode="elasticity",
+                 settings=dict(method="cg", gamma_scheme="staggered", mixing_rule="voigt", error_estimator="residual"),
+                 materials=[("matrix", "iso", (mu_m, lam_m)), ("fibre", "iso", (mu_f, lam_f))],
+                 load=[1, 0, 0, 0, 0, 0], d=6, u=3,
+                 name="config %s: short-fibre composite, linear elasticity, CG, staggered grid, Voigt mixing, residual estimator"
+                      % ("5" if scaling == "strong" else "2"))
+        return w
+    if cfg == "c3":
+        t = (grid or 512) // 256
+        w.update(tile=(t, t, t), mode="heat",
+                 settings=dict(method="cg", gamma_scheme="staggered", mixing_rule="laminate", error_estimator="residual"),
+                 materials=[("matrix", "iso", (1.0,)), ("fibre", "iso", (10.0,))],
+                 load=[1, 0, 0], d=3, u=1, normals=True,
+                 name="config 3: heat conduction in the short-fibre microstructure, CG, staggered grid, laminate mixing at interface voxels")
+        return w
+    if cfg == "c4":
+        w.update(tile=(1, 1, 1), mode="hyperelasticity",
+                 settings=dict(method="cg", gamma_scheme="staggered", mixing_rule="voigt", error_estimator="residual",
+                               outer_error_estimator="sigma"),
+                 materials=[("matrix", "nh", (10.0, 10.0)), ("fibre", "nh", (10.0, 100.0))],
+                 load=[1, 1.1, 1, 0, 0, 0, 0, 0, 0], d=9, u=3,
+                 name="config 4: Neo-Hooke short-fibre composite, F = I + 0.1 e2 x e2, Newton outer + CG inner (step = inner CG iteration)")
+        return w
+    raise SystemExit("unknown --config %s" % cfg)
 
 
-def tile_x(phi, reps):
-    return np.concatenate([phi] * reps, axis=0) if reps > 1 else phi
+def fibre_list(w):
+    from microstructures import fiber_list
+    c = w["cell"]
+    if "sphere" in w:
+        return [((0.5, 0.5, 0.5), (1, 0, 0), 0.0, w["sphere"], 1)], (1.0, 1.0, 1.0)
+    Cs, Ds, R, Lc = w["fibres"]
+    return fiber_list((c, c, c), Cs, Ds, R, Lc, material=1, tile=w["tile"])
 
 
 # ------------------------------------------------------------------------------------------------ CUDA arm
@@ -129,31 +191,23 @@ def run_cuda(args):
         import torch.distributed as dist_
         dist = dist_
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    base = args.grid
-    # weak scaling: every rank owns base^3 voxels; the global grid grows along y, z and x in turn so that no axis exceeds
-    # 2*base (x-slabs of nx/P planes; nx and ny must be divisible by P)
-    mult = {1: (1, 1, 1), 2: (1, 2, 1), 4: (1, 2, 2), 8: (2, 2, 2)}.get(world, (world, 1, 1))
-    if base * mult[0] % world or base * mult[1] % world:
-        mult = (world, 1, 1)
-    n = (base * mult[0], base * mult[1], base * mult[2])
+    cfg = args.config
+    w = workload(cfg, world, args.scaling, args.grid)
+    c = w["cell"]
+    n = (c * w["tile"][0], c * w["tile"][1], c * w["tile"][2])
     nxyz = n[0] * n[1] * n[2]
     K, W = args.steps, max(args.warmup, 3)
-
-    phi_cell, nfib = microstructure((base, base, base))
+    fibres, box = fibre_list(w)
     lnx = n[0] // world
-    # the global microstructure is the periodic tiling of the cell; this rank's x-slab of it
-    x0 = rank * lnx
-    reps = (mult[0], mult[1], mult[2])
-    phi_local = np.tile(phi_cell, reps)[x0:x0 + lnx]
-    vf = float(phi_cell.mean())
-    lam_m, mu_m = lame(E_M, NU_M)
-    lam_f, mu_f = lame(E_F, NU_F)
+    d, u = w["d"], w["u"]
+    KB = kernel_bytes(d, u)
 
-    def make_solver(tol, maxiter):
-        s = fb.LSSolver(*n, rank=rank, nranks=world, device=local_rank, mode="elasticity", method="cg", gamma_scheme="staggered",
-                        mixing_rule="voigt", error_estimator="residual", tol=tol, maxiter=maxiter)
-        s.add_material("matrix", "iso", mu_m, lam_m)
-        s.add_material("fibre", "iso", mu_f, lam_f)
+    def make_solver(tol, maxiter, **extra):
+        st = dict(w["settings"])
+        st.update(extra)
+        s = fb.LSSolver(*n, *box, rank=rank, nranks=world, device=local_rank, mode=w["mode"], tol=tol, maxiter=maxiter, **st)
+        for name, law, params in w["materials"]:
+            s.add_material(name, law, *params)
         s.init()
         if world > 1:
             idbuf = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -168,15 +222,6 @@ def run_cuda(args):
             s.init_comm(bytes(idbuf.cpu().numpy().tobytes()))
         return s
 
-    # pinned host staging of the phase planes (padded reference layout)
-    nzp = fb.nzp_of(n[2])
-    host_phi = torch.empty((2, lnx, n[1], nzp), dtype=torch.float64).pin_memory()
-    hp = host_phi.numpy()
-    hp[...] = 0
-    hp[0, :, :, :n[2]] = 1 - phi_local
-    hp[1, :, :, :n[2]] = phi_local
-    host_eps = torch.empty((6, lnx, n[1], nzp), dtype=torch.float64).pin_memory()
-
     stream = torch.cuda.current_stream()
 
     def barrier():
@@ -184,14 +229,26 @@ def run_cuda(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- device-resident timing: W warm-up + K timed CG iterations ----------------
-    s = make_solver(tol=1e-300, maxiter=10 ** 6)
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- device-resident timing: W warm-up + K timed iterations ----------------
+    strong = args.scaling == "strong"
+    s = make_solver(tol=(args.tol if strong else 1e-300), maxiter=(args.e2e_maxiter if strong else 10 ** 6))
     s.lib.fgb_set_stream(s.ctx(), stream.cuda_stream)
-    s.set_phase(0, hp[0], padded=True)
-    s.set_phase(1, hp[1], padded=True)
-    s.set_strain([1, 0, 0, 0, 0, 0])
+    ep0, ep1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ep0.record(stream)
+    s.init_phase(fibres, matrix_mat=0, normals=bool(w.get("normals")))          # initPhi on the device
+    ep1.record(stream)
+    torch.cuda.synchronize()
+    init_phase_ms = ep0.elapsed_time(ep1)
+    s.set_strain(w["load"])
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    state = {"n": 0, "launch0": 0, "launch1": 0}
+    state = {"n": 0, "launch0": 0, "launch1": 0, "timed": 0}
     sampler = ClockSampler(local_rank)
     ctxp = s.ctx()
 
@@ -204,23 +261,29 @@ def run_cuda(args):
             s.lib.fgb_profile_enable(ctxp, 1)
             state["launch0"] = s.launches()
             ev0.record(stream)
-        if state["n"] == W + K:
+        if state["n"] == W + K and not strong:
             ev1.record(stream)
             barrier()
             state["launch1"] = s.launches()
+            state["timed"] = K
             return True
         return False
 
     s.set_convergence_callback(cb)
     s.run()
+    if strong or state["timed"] == 0:
+        # solved to tolerance: the timed region is everything after the W warm-up iterations
+        ev1.record(stream)
+        barrier()
+        state["launch1"] = s.launches()
+        state["timed"] = state["n"] - W
     clocks = sampler.stop() if rank == 0 else None
-    ms = ev0.elapsed_time(ev1)
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    value = nxyz * K / (ms * 1e-3)
+    Kt = max(state["timed"], 1)
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    value = nxyz * Kt / (ms * 1e-3)
     launches = state["launch1"] - state["launch0"]
+    res_dev = s.get_residuals()
+    mean_stress_run = s.get_mean_stress() if strong else None
 
     # per-kernel durations from the library's own events (same stream, same timed region)
     ctxobj = fb.Context.__new__(fb.Context)
@@ -235,7 +298,7 @@ def run_cuda(args):
         if cnt == 0:
             continue
         avg = tot_ms / cnt
-        bpv = KERNEL_BYTES_PER_VOXEL.get(name)
+        bpv = KB.get(name)
         kernels[name] = {"launches": int(cnt), "avg_ms": avg, "share": tot_ms / ms,
                          "gbs": (bpv * nloc / (avg * 1e-3) / 1e9) if bpv else None}
     top = max(kernels, key=lambda k: kernels[k]["avg_ms"] * kernels[k]["launches"]) if kernels else None
@@ -243,84 +306,109 @@ def run_cuda(args):
     if top and kernels[top]["gbs"]:
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
+        if os.path.exists(tp) and cfg == "c2":
             try:
                 traffic = json.load(open(tp)).get(top)
             except Exception:
                 traffic = None
         roofline = {"bound": "hbm", "kernel": top, "achieved": kernels[top]["gbs"], "peak": peak, "unit": "GB/s",
                     "frac": kernels[top]["gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": KERNEL_BYTES_PER_VOXEL[top] * nloc}
-    iter_frac = B_ALG_CG_STAGGERED * value / (world * peak * 1e9)
+                    "algorithmic_bytes_per_launch": KB[top] * nloc}
+    iteration_hbm = {"algorithmic_bytes_per_voxel_iteration": B_ALG[cfg], "achieved_gbs_per_gpu": B_ALG[cfg] * value / world / 1e9,
+                     "frac_of_peak": B_ALG[cfg] * value / (world * peak * 1e9), "peak_gbs": peak, "peak_source": peak_src}
+    if cfg in B_MOVED:
+        iteration_hbm["bytes_moved_per_voxel_iteration"] = B_MOVED[cfg]
+        iteration_hbm["frac_of_peak_bytes_moved"] = B_MOVED[cfg] * value / (world * peak * 1e9)
+    # NVLink: the two transposing passes move (P-1)/P of the u components per rank and pass
+    nvlink = None
+    if world > 1:
+        sent = 2 * u * 8.0 * nloc * (world - 1) / world          # bytes per rank and iteration (two transposes of u complex half-spectra)
+        tt = sum(kernels[k]["avg_ms"] * kernels[k]["launches"] for k in ("fft_y_fwd_p2p", "fft_x_green") if k in kernels) / Kt
+        nvlink = {"bytes_sent_per_gpu_per_iteration": sent, "transposing_kernels_ms_per_iteration": tt,
+                  "achieved_gbs_per_direction": (sent / (tt * 1e-3) / 1e9) if tt > 0 else None,
+                  "note": "time of the two kernels that store into peer memory (forward y pass, fused x pass); peak 900 GB/s per direction"}
+    # phase fractions back to the host for the end-to-end leg and the parity check (pinned staging)
+    nzp = fb.nzp_of(n[2])
+    nph = len(w["materials"])
+    host_phi = torch.empty((nph, lnx, n[1], nzp), dtype=torch.float64).pin_memory()
+    hp = host_phi.numpy()
+    for m in range(nph):
+        hp[m] = s.get_phase(m, padded=True)
+    hp[:, :, :, n[2]:] = 0
+    vf = float(hp[1, :, :, :n[2]].mean())
     s.set_convergence_callback(None)
+    strong_out = None
+    if strong:
+        strong_out = {"iterations": int(len(res_dev)), "final_residual": float(res_dev[-1]), "tol": args.tol,
+                      "mean_stress": [float(x) for x in mean_stress_run], "timed_iterations": int(Kt)}
     s.close()
 
     # ---------------- end to end: host phase planes in, strain field out, complete solve ----------------
-    # A fresh solver pays one-time costs on its first run (field allocation, peer-memory mapping, NCCL connection set-up) that a
-    # user amortises over the load cases of one job (calc_effective_properties runs 6): warm the solver with a 3-iteration run,
-    # then time a complete cold-data solve: phase planes from pinned host memory in, converged strain field out.
-    s2 = make_solver(tol=1e-6, maxiter=3)
-    s2.lib.fgb_set_stream(s2.ctx(), stream.cuda_stream)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s2.set_strain([1, 0, 0, 0, 0, 0])
-    s2.set_phase(0, hp[0], padded=True)
-    s2.set_phase(1, hp[1], padded=True)
-    s2.run()
-    s2.get_field("epsilon", padded=True, out=host_eps.numpy())
-    s2.set("maxiter", args.e2e_maxiter)
-    barrier()
-    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    s2.set_phase(0, hp[0], padded=True)            # H2D from pinned memory
-    s2.set_phase(1, hp[1], padded=True)
-    ea.record(stream)
-    s2.run()
-    eb.record(stream)
-    s2.get_field("epsilon", padded=True, out=host_eps.numpy())      # D2H of the solution
-    sm = s2.get_mean_stress()
-    e1.record(stream)
-    barrier()
-    e2e_ms = e0.elapsed_time(e1)
-    e2e_parts = {"h2d_ms": e0.elapsed_time(ea), "solve_ms": ea.elapsed_time(eb), "d2h_and_mean_stress_ms": eb.elapsed_time(e1)}
-    t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
-    iters = len(s2.get_residuals())
-    res_last = float(s2.get_residuals()[-1])
-    e2e = {"value": nxyz * iters / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(host_phi.numel() * 8 * world / iters),
-           "d2h_bytes_per_step": int(host_eps.numel() * 8 * world / iters), "iterations": iters, "ms_total": e2e_ms,
-           "final_residual": res_last, "mean_stress_11": float(sm[0]), "parts": e2e_parts,
-           "what": "fgls (warm solver): set_phase (H2D, pinned) + run() to tol 1e-6 + get_field('epsilon') (D2H) + mean stress"}
-    s2.close()
+    e2e = None
+    if not strong and not args.no_e2e:
+        host_eps = torch.empty((d, lnx, n[1], nzp), dtype=torch.float64).pin_memory()
+        # A fresh solver pays one-time costs on its first run (field allocation, peer-memory mapping, NCCL connection set-up) that a
+        # user amortises over the load cases of one job (calc_effective_properties runs 6): warm the solver with a 3-iteration run,
+        # then time a complete cold-data solve: phase planes from pinned host memory in, converged strain field out.
+        s2 = make_solver(tol=args.tol, maxiter=3)
+        s2.lib.fgb_set_stream(s2.ctx(), stream.cuda_stream)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s2.set_strain(w["load"])
+        if w.get("normals"):
+            s2.init_phase(fibres, matrix_mat=0, normals=True)        # normals stay device-resident; the phase planes below replace phi
+        for m in range(nph):
+            s2.set_phase(m, hp[m], padded=True)
+        s2.run()
+        s2.get_field("epsilon", padded=True, out=host_eps.numpy())
+        s2.set("maxiter", args.e2e_maxiter)
+        barrier()
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for m in range(nph):
+            s2.set_phase(m, hp[m], padded=True)                      # H2D from pinned memory
+        ea.record(stream)
+        s2.run()
+        eb.record(stream)
+        s2.get_field("epsilon", padded=True, out=host_eps.numpy())  # D2H of the solution
+        sm = s2.get_mean_stress()
+        e1.record(stream)
+        barrier()
+        e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+        iters = len(s2.get_residuals())
+        e2e = {"value": nxyz * iters / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(host_phi.numel() * 8 * world / iters),
+               "d2h_bytes_per_step": int(host_eps.numel() * 8 * world / iters), "iterations": iters, "ms_total": e2e_ms,
+               "final_residual": float(s2.get_residuals()[-1]), "mean_stress_11": float(sm[0]),
+               "parts": {"h2d_ms": e0.elapsed_time(ea), "solve_ms": ea.elapsed_time(eb), "d2h_and_mean_stress_ms": eb.elapsed_time(e1),
+                         "device_phase_init_ms_not_in_total": init_phase_ms},
+               "what": "fgls (warm solver): set_phase (H2D, pinned) + run() to tol %g + get_field('epsilon') (D2H) + mean stress" % args.tol}
+        s2.close()
 
-    # ---------------- CPU baseline: the oracle port on this host, bounded sample ----------------
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(base, phi_cell, iters=2)
+    # ---------------- CPU baseline + parity at the benchmark size: the oracle on this host, bounded sample ----------------
+    cpu, parity = None, None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and cfg == "c2":
+        phi_cell = np.ascontiguousarray(hp[1, :, :, :n[2]])
+        cpu, parity = cpu_baseline_and_parity(n, box, phi_cell, res_dev, iters=2)
 
     if rank == 0:
-        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
-               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-               "config": {"workload": "config 2: short-fibre composite %dx%dx%d, linear elasticity, CG, staggered grid, Voigt mixing, "
-                                      "residual estimator" % n, "grid": list(n), "fibres_per_cell": nfib, "fibre_volume_fraction": vf,
-                          "partition": "x-slabs, %d rank(s)" % world, "l2": "inputs larger than L2 (3.5 GB of fields vs 126 MB), no flush",
-                          "step": "one CG iteration"},
-               "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-               "iteration_hbm": {"algorithmic_bytes_per_voxel_iteration": B_ALG_CG_STAGGERED, "achieved_gbs_per_gpu": B_ALG_CG_STAGGERED * value / world / 1e9,
-                                 "frac_of_peak": iter_frac, "peak_gbs": peak, "peak_source": peak_src},
-               "kernels": kernels, "cpu_baseline": cpu}
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": int(Kt), "warmup": W, "ms_per_step": ms / Kt,
+               "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": "%s, grid %dx%dx%d" % ((w["name"],) + n), "grid": list(n), "fibres_in_grid": len(fibres),
+                          "fibre_volume_fraction": vf, "partition": "x-slabs, %d rank(s)" % world,
+                          "phase_fractions": "composite voxels, initPhi on the device (%.1f ms)" % init_phase_ms,
+                          "l2": "fields far larger than L2 (126 MB), no flush", "step": "one solver iteration"},
+               "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "iteration_hbm": iteration_hbm,
+               "nvlink": nvlink, "kernels": kernels, "cpu_baseline": cpu, "parity_256": parity, "strong_scaling": strong_out}
         print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def oracle_solver(n, phi, tol=1e-300, maxiter=10 ** 6):
+def oracle_solver(n, box, phi, tol=1e-300, maxiter=10 ** 6):
     from oracle import fg_oracle as fo
     lam_m, mu_m = lame(E_M, NU_M)
     lam_f, mu_f = lame(E_F, NU_F)
-    o = fo.LSSolver(*n, mode="elasticity", method="cg", gamma_scheme="staggered", mixing_rule="voigt",
+    o = fo.LSSolver(*n, *box, mode="elasticity", method="cg", gamma_scheme="staggered", mixing_rule="voigt",
                     error_estimator="residual", tol=tol, maxiter=maxiter)
     o.add_phase("matrix", fo.LinearIsotropic(mu_m, lam_m), 1 - phi)
     o.add_phase("fibre", fo.LinearIsotropic(mu_f, lam_f), phi)
@@ -328,9 +416,9 @@ def oracle_solver(n, phi, tol=1e-300, maxiter=10 ** 6):
     return o
 
 
-def time_oracle_iterations(n, phi, warm, steps):
-    """times `steps` CG iterations of the oracle after `warm` untimed ones (callback = reference's convergence callback)"""
-    o = oracle_solver(n, phi)
+def time_oracle_iterations(n, box, phi, warm, steps):
+    """times `steps` CG iterations of the numpy oracle after `warm` untimed ones; returns (seconds, residual history)"""
+    o = oracle_solver(n, box, phi)
     st = {"n": 0, "t0": None, "t1": None}
 
     def cb():
@@ -344,39 +432,68 @@ def time_oracle_iterations(n, phi, warm, steps):
     o.callback = cb
     # the reference-material scan is excluded from the loop timing
     o.run()
-    return st["t1"] - st["t0"]
+    return st["t1"] - st["t0"], np.array(o.residuals)
 
 
-def cpu_baseline(base, phi, iters=2):
+def cpu_baseline_and_parity(n, box, phi, res_dev, iters=2):
+    """the CPU restatement on the SAME grid and phase fractions: throughput of a bounded sample, and the residual history of
+    its first iterations against the device's (scheme-level parity at the benchmark size)"""
     cores = os.cpu_count() or 1
-    n = (base, base, base)
-    dt = time_oracle_iterations(n, phi, 1, iters)
-    return {"value": n[0] * n[1] * n[2] * iters / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d CG iterations of the same %d^3 problem with the numpy/pocketfft oracle (oracle/fg_oracle.py), "
-                      "FFT on all %d host threads, elementwise work single-threaded numpy" % (iters, base, cores)}
+    cpu = None
+    try:
+        from oracle import fg_cpu
+        r = fg_cpu.cg_iterations(n, box, phi, (lame(E_M, NU_M)[::-1], lame(E_F, NU_F)[::-1]), [1, 0, 0, 0, 0, 0], warm=1, steps=iters)
+        res_o = r["residuals"]
+        cpu = {"value": n[0] * n[1] * n[2] * iters / r["seconds"], "unit": UNIT, "cores": r["threads"], "kind": "port",
+               "sample": "%d CG iterations of the same %dx%dx%d problem with the OpenMP C++ restatement (oracle/fg_cpu.cpp: threaded "
+                         "elementwise sweeps + its own threaded FFT), %d threads" % (iters, n[0], n[1], n[2], r["threads"])}
+    except Exception as e:          # the C++ restatement is optional test infrastructure; fall back to the numpy oracle
+        dt, res_o = time_oracle_iterations(n, box, phi, 1, iters)
+        cpu = {"value": n[0] * n[1] * n[2] * iters / dt, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "%d CG iterations of the same %dx%dx%d problem with the numpy/pocketfft oracle (oracle/fg_oracle.py), FFT on "
+                         "%d host threads, elementwise work single-threaded (%s)" % (iters, n[0], n[1], n[2], cores, type(e).__name__)}
+    m = min(len(res_o), len(res_dev))
+    rel = np.abs(np.asarray(res_dev[:m]) - np.asarray(res_o[:m])) / np.abs(np.asarray(res_o[:m])).max()
+    parity = {"iters": int(m), "max_rel": float(rel.max()), "tolerance": 1e-10, "ok": bool(rel.max() <= 1e-10),
+              "what": "residual history of the first %d CG iterations at the benchmark size, device vs CPU restatement on the same phase "
+                      "fractions (north_star: <= 1e-10 relative)" % m}
+    return cpu, parity
 
 
 def run_reference(args):
+    """CPU arm: the reference's algorithm on the host cores.  The reference binary itself cannot be built in this image (Boost,
+    FFTW3, LAPACK bindings, libpng are absent), so this is the repo's CPU restatement: kind "port"."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    from microstructures import config2_fibres, fiber_list
+    from oracle import fg_phase as fp
     base = args.ref_grid
     n = (base, base, base)
-    phi, nfib = microstructure(n)
+    Cs, Ds, R, Lc = config2_fibres()
+    s = base / 256.0                       # the same cell sampled on a base^3 grid
+    fibres, box = fiber_list(n, Cs * s, Ds, R * s, Lc * s, material=1)
+    phi = fp.init_phi(n, box, fibres, 2)[0][1]
     K, W = args.steps, max(args.warmup, 1)
     cores = os.cpu_count() or 1
-    dt = time_oracle_iterations(n, phi, W, K)
+    try:
+        from oracle import fg_cpu
+        r = fg_cpu.cg_iterations(n, box, phi, (lame(E_M, NU_M)[::-1], lame(E_F, NU_F)[::-1]), [1, 0, 0, 0, 0, 0], warm=W, steps=K)
+        dt, cores = r["seconds"], r["threads"]
+        how = "OpenMP C++ restatement (oracle/fg_cpu.cpp: threaded elementwise sweeps + its own threaded FFT), %d threads" % cores
+    except Exception as e:
+        dt, _ = time_oracle_iterations(n, box, phi, W, K)
+        how = "numpy/pocketfft oracle (oracle/fg_oracle.py), FFT on %d host threads (%s)" % (cores, type(e).__name__)
     value = n[0] * n[1] * n[2] * K / dt
-    sample = ("each step = one CG iteration of the same workload family on a %d^3 cell (bounded sample of config 2), numpy/pocketfft "
-              "oracle port of the reference algorithm, FFT on %d host threads" % (base, cores))
+    sample = "each step = one CG iteration of config 2 on its own %d^3 grid, %s" % (base, how)
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
            "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": "config 2: short-fibre composite, linear elasticity, CG, staggered grid, Voigt mixing, residual estimator",
-                      "grid": list(n), "step": "one CG iteration"},
+           "config": {"workload": "config 2: short-fibre composite, linear elasticity, CG, staggered grid, Voigt mixing, residual estimator, "
+                                  "grid %dx%dx%d" % n, "grid": list(n), "step": "one solver iteration", "same_config": base == 256},
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-           "note": "the reference (Boost/FFTW3/LAPACK C++) cannot be built in this image; this is the repo's oracle port, not fibergen's own binary"}
+           "note": "the reference (Boost/FFTW3/LAPACK C++) cannot be built in this image; this is the repo's CPU restatement, not fibergen's own binary"}
     print(json.dumps(out))
 
 
@@ -386,10 +503,14 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--grid", type=int, default=256, help="cell edge per GPU (BASELINE config 2: 256)")
-    ap.add_argument("--ref-grid", type=int, default=128, help="cell edge of the CPU arm's bounded sample")
+    ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3", "c4"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--grid", type=int, default=0, help="edge of the global grid (strong scaling: 1024; c1: 64; c3: 512); 0 = the configuration's own")
+    ap.add_argument("--tol", type=float, default=1e-6)
+    ap.add_argument("--ref-grid", type=int, default=256, help="grid edge of the CPU arm (config 2's own 256)")
     ap.add_argument("--e2e-maxiter", type=int, default=400)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

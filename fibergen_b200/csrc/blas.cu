@@ -68,7 +68,9 @@ __global__ void __launch_bounds__(256) k_set_constant(double* __restrict__ f, Gr
 // r = x + a*(y - z) (z may be null -> r = x + a*y); also used for copy (a = 0)
 template <int MODE>
 __global__ void __launch_bounds__(256) k_axpy(double* __restrict__ r, const double* __restrict__ x, double a,
-                                              const double* __restrict__ y, const double* __restrict__ z, size_t n2) {
+                                              const double* __restrict__ y, const double* __restrict__ z, size_t n2,
+                                              const double* __restrict__ scal) {
+    if (scal) a = *scal;          // device-resident CG scalar (fgb_cgdev_*)
     for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < n2; v += (size_t)gridDim.x * blockDim.x) {
         const double2 xv = reinterpret_cast<const double2*>(x)[v];
         double2 o;
@@ -172,7 +174,9 @@ __global__ void __launch_bounds__(256) k_component_dot(const double* __restrict_
 // fused CG update: x += a*p ; r -= a*(p - w) ; delta = <r,r>   (fg:23221, fg:23237, fg:23240)
 template <int D>
 __global__ void __launch_bounds__(256) k_cg_update(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p,
-                                                   const double* __restrict__ w, double a, GridDev g, double* __restrict__ partials) {
+                                                   const double* __restrict__ w, double a, GridDev g, double* __restrict__ partials,
+                                                   const double* __restrict__ scal) {
+    if (scal) a = scal[2];
     double s = 0;
     FGB_VOXEL_PAIR_LOOP(g) {
         FGB_PAIR_INDEX(g)
@@ -226,6 +230,11 @@ __global__ void k_reduce_finish(const double* __restrict__ partials, int nblocks
 int fgb_reduce_finish(fgb_ctx* ctx, int nblocks, int nvals, int op, double* host_out) {
     k_reduce_finish<<<nvals, 256, 0, ctx->stream>>>(ctx->d_partials, nblocks, nvals, op, ctx->d_result);
     FGB_CHECK_LAUNCH(ctx, "k_reduce_finish");
+    if (ctx->reduce_on_device) {
+        // fgb_cgdev_*: the sum stays on the device (d_result, or d_gather with one entry per rank); no host synchronisation
+        for (int i = 0; i < nvals; i++) host_out[i] = 0.0;
+        return ctx->nranks > 1 ? fgb_allgather_dev(ctx, nvals) : FGB_OK;
+    }
     // slab partition: the per-rank results are gathered on the device and combined in rank order (one host synchronisation)
     if (ctx->nranks > 1) return fgb_allreduce_host(ctx, host_out, nvals, op);
     FGB_CUDA(ctx, cudaMemcpyAsync(ctx->h_result, ctx->d_result, sizeof(double) * nvals, cudaMemcpyDeviceToHost, ctx->stream));
@@ -262,7 +271,15 @@ int fgb_k_copy(fgb_ctx* ctx, const double* src, double* dst, int ncomp) {
 int fgb_k_xpay(fgb_ctx* ctx, double* r, const double* x, double a, const double* y) {
     const size_t n2 = ctx->g.plane * ctx->dim / 2;
     ProfScope ps(ctx, "xpay");
-    k_axpy<1><<<grid_for(ctx, n2, 256), 256, 0, ctx->stream>>>(r, x, a, y, nullptr, n2);
+    k_axpy<1><<<grid_for(ctx, n2, 256), 256, 0, ctx->stream>>>(r, x, a, y, nullptr, n2, nullptr);
+    FGB_CHECK_LAUNCH(ctx, "k_axpy<1>");
+    return FGB_OK;
+}
+
+int fgb_k_xpay_dev(fgb_ctx* ctx, double* r, const double* x, int scal_index, const double* y) {
+    const size_t n2 = ctx->g.plane * ctx->dim / 2;
+    ProfScope ps(ctx, "xpay");
+    k_axpy<1><<<grid_for(ctx, n2, 256), 256, 0, ctx->stream>>>(r, x, 0.0, y, nullptr, n2, ctx->d_scalars + scal_index);
     FGB_CHECK_LAUNCH(ctx, "k_axpy<1>");
     return FGB_OK;
 }
@@ -270,7 +287,7 @@ int fgb_k_xpay(fgb_ctx* ctx, double* r, const double* x, double a, const double*
 int fgb_k_xpaymz(fgb_ctx* ctx, double* r, const double* x, double a, const double* y, const double* z) {
     const size_t n2 = ctx->g.plane * ctx->dim / 2;
     ProfScope ps(ctx, "xpaymz");
-    k_axpy<2><<<grid_for(ctx, n2, 256), 256, 0, ctx->stream>>>(r, x, a, y, z, n2);
+    k_axpy<2><<<grid_for(ctx, n2, 256), 256, 0, ctx->stream>>>(r, x, a, y, z, n2, nullptr);
     FGB_CHECK_LAUNCH(ctx, "k_axpy<2>");
     return FGB_OK;
 }
@@ -348,11 +365,12 @@ int fgb_k_component_dot(fgb_ctx* ctx, const double* a, const double* b, double* 
 int fgb_k_cg_update(fgb_ctx* ctx, double* x, double* r, const double* p, const double* w, double a, double* delta) {
     const void* kp = ctx->dim == 3 ? (const void*)k_cg_update<3> : ctx->dim == 6 ? (const void*)k_cg_update<6> : (const void*)k_cg_update<9>;
     const unsigned grid = fgb_wave_grid(ctx, kp, 256, npairs_of(ctx), ctx->red_blocks);
+    const double* scal = ctx->cg_dev ? ctx->d_scalars : nullptr;
     {
         ProfScope ps(ctx, "cg_update");
-        DISPATCH_D(ctx, (k_cg_update<3><<<grid, 256, 0, ctx->stream>>>(x, r, p, w, a, ctx->g, ctx->d_partials)),
-                   (k_cg_update<6><<<grid, 256, 0, ctx->stream>>>(x, r, p, w, a, ctx->g, ctx->d_partials)),
-                   (k_cg_update<9><<<grid, 256, 0, ctx->stream>>>(x, r, p, w, a, ctx->g, ctx->d_partials)));
+        DISPATCH_D(ctx, (k_cg_update<3><<<grid, 256, 0, ctx->stream>>>(x, r, p, w, a, ctx->g, ctx->d_partials, scal)),
+                   (k_cg_update<6><<<grid, 256, 0, ctx->stream>>>(x, r, p, w, a, ctx->g, ctx->d_partials, scal)),
+                   (k_cg_update<9><<<grid, 256, 0, ctx->stream>>>(x, r, p, w, a, ctx->g, ctx->d_partials, scal)));
         FGB_CHECK_LAUNCH(ctx, "k_cg_update");
     }
     int rc = fgb_reduce_finish(ctx, grid, 1, 0, delta);
@@ -389,5 +407,43 @@ int fgb_k_extrapolate_poly(fgb_ctx* ctx, int n, const double* const* fields, con
     const size_t ntot = ctx->g.plane * ctx->dim;
     k_extrapolate_poly<<<grid_for(ctx, ntot, 256), 256, 0, ctx->stream>>>(dst, A, ntot);
     FGB_CHECK_LAUNCH(ctx, "k_extrapolate_poly");
+    return FGB_OK;
+}
+
+// Device-resident CG scalars.  The arithmetic is the host loop's (runCGElasticity fg:23211-23245), operation by operation, so that
+// both forms of the loop produce the same bits: sum / nxyz, + tiny, quotient.
+__global__ void k_cg_scalars(int mode, int nranks, const double* __restrict__ sums, double* __restrict__ scal, double nxyz,
+                             double* __restrict__ ring) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double s = sums[0];
+    for (int r = 1; r < nranks; r++) s = s + sums[r];          // rank order (fgb_allreduce_host)
+    s /= nxyz;
+    const double tiny = 2.2250738585072014e-308;              // boost::numeric::bounds<double>::smallest()
+    if (mode == 0) {
+        scal[3] = s;
+        const double a = s + tiny;
+        scal[2] = scal[0] / a;
+    } else {
+        ring[0] = scal[0];
+        ring[1] = scal[3];
+        ring[2] = scal[2];
+        ring[3] = s;
+        const double delta = s + tiny;
+        scal[4] = delta;
+        scal[1] = delta / scal[0];
+        scal[0] = delta;
+    }
+}
+
+int fgb_k_cg_scalars(fgb_ctx* ctx, int mode, int ring_slot) {
+    const double nxyz = (double)ctx->g.nx * ctx->g.ny * ctx->g.nz;
+    const double* sums = ctx->nranks > 1 ? ctx->d_gather : ctx->d_result;
+    double* ring = ctx->d_scalars + 8;
+    k_cg_scalars<<<1, 32, 0, ctx->stream>>>(mode, ctx->nranks, sums, ctx->d_scalars, nxyz, ring);
+    FGB_CHECK_LAUNCH(ctx, "k_cg_scalars");
+    if (mode == 1) {
+        FGB_CUDA(ctx, cudaMemcpyAsync(ctx->h_ring + 4 * ring_slot, ring, sizeof(double) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        FGB_CUDA(ctx, cudaEventRecord(ctx->ring_ev[ring_slot], ctx->stream));
+    }
     return FGB_OK;
 }

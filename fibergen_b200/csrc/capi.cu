@@ -137,6 +137,8 @@ extern "C" int fgb_create(fgb_ctx** out, int nx, int ny, int nz, double Lx, doub
         c->xi2pi_dev[a] = nullptr; c->wtan_dev[a] = nullptr; c->wex_dev[a] = nullptr; c->pois_dev[a] = nullptr;
     }
     c->d_partials = nullptr; c->d_result = nullptr; c->h_result = nullptr; c->d_scalars = nullptr; c->d_flag = nullptr; c->h_flag = nullptr;
+    c->cg_dev = false; c->reduce_on_device = false; c->h_ring = nullptr;
+    for (int i = 0; i < FGB_CG_RING; i++) c->ring_ev[i] = nullptr;
     c->nccl_comm = nullptr; c->nccl_lib = nullptr; c->sbuf = nullptr; c->xbuf = nullptr; c->xbuf_cap = 0;
     c->halo = nullptr; c->halo_slot = 0; c->d_gather = nullptr; c->visc_tmp = nullptr; c->p2p = false; c->iso_halo = nullptr; c->phi_halo_valid = false;
     c->halo_base = nullptr; c->iso_set = 0; c->halo_seq = c->iso_seq = 0;
@@ -163,6 +165,10 @@ extern "C" int fgb_create(fgb_ctx** out, int nx, int ny, int nz, double Lx, doub
     c->implicit_w_of = -1;
     CREATE_CUDA(cudaMalloc(&c->d_result, sizeof(double) * 64));
     CREATE_CUDA(cudaMallocHost(&c->h_result, sizeof(double) * 64));
+    CREATE_CUDA(cudaMalloc(&c->d_scalars, sizeof(double) * 16));
+    CREATE_CUDA(cudaMemset(c->d_scalars, 0, sizeof(double) * 16));
+    CREATE_CUDA(cudaMallocHost(&c->h_ring, sizeof(double) * 4 * FGB_CG_RING));
+    for (int i = 0; i < FGB_CG_RING; i++) CREATE_CUDA(cudaEventCreateWithFlags(&c->ring_ev[i], cudaEventDisableTiming));
     CREATE_CUDA(cudaMalloc(&c->d_flag, sizeof(int)));
     CREATE_CUDA(cudaMemset(c->d_flag, 0, sizeof(int)));
     CREATE_CUDA(cudaMallocHost(&c->h_flag, sizeof(int)));
@@ -194,6 +200,9 @@ extern "C" void fgb_destroy(fgb_ctx* c) {
     if (c->h_result) cudaFreeHost(c->h_result);
     if (c->d_flag) cudaFree(c->d_flag);
     if (c->h_flag) cudaFreeHost(c->h_flag);
+    if (c->d_scalars) cudaFree(c->d_scalars);
+    if (c->h_ring) cudaFreeHost(c->h_ring);
+    for (int i = 0; i < FGB_CG_RING; i++) if (c->ring_ev[i]) cudaEventDestroy(c->ring_ev[i]);
     for (auto& p : g_pending[c]) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
     for (auto& e : g_event_pool[c]) cudaEventDestroy(e);
     g_pending.erase(c);
@@ -835,7 +844,12 @@ extern "C" int fgb_cg_apply(fgb_ctx* c, int F, int p, int w, double mu0, double 
             if ((rc = delta_impl(c, c->fields[w], tmp, zero, mu0, -1.0))) return rc;
         } else if ((rc = gamma_impl(c, c->fields[w], zero, mu0, lambda0, -1.0, 0.0))) return rc;
     }
-    if (pAp) return fgb_k_inner(c, c->fields[p], c->fields[p], c->fields[w], pAp);
+    if (pAp) {
+        c->reduce_on_device = c->cg_dev;
+        rc = fgb_k_inner(c, c->fields[p], c->fields[p], c->fields[w], pAp);
+        c->reduce_on_device = false;
+        return rc;
+    }
     return FGB_OK;
 }
 
@@ -863,14 +877,26 @@ extern "C" int fgb_cg_step(fgb_ctx* c, int F, int r, double beta, int p_old, int
         if (c->nranks > 1 && (rc = fgb_comm_halo_u(c))) return rc;
         if (implicit_w) {
             // w = sym-grad(u) is not written out: the sum is taken on the fly and fgb_cg_update re-evaluates w from u
-            if ((rc = fgb_k_eps_dot(c, c->ubuf, nullptr, zero, c->fields[p_new], pAp))) return rc;
+            c->reduce_on_device = c->cg_dev;
+            rc = fgb_k_eps_dot(c, c->ubuf, nullptr, zero, c->fields[p_new], pAp);
+            c->reduce_on_device = false;
+            if (rc) return rc;
             c->implicit_w_of = p_new;
             return FGB_OK;
         }
-        if (pAp) return fgb_k_eps_dot(c, c->ubuf, c->fields[w], zero, c->fields[p_new], pAp);
+        if (pAp) {
+            c->reduce_on_device = c->cg_dev;
+            rc = fgb_k_eps_dot(c, c->ubuf, c->fields[w], zero, c->fields[p_new], pAp);
+            c->reduce_on_device = false;
+            return rc;
+        }
         return fgb_k_eps(c, c->ubuf, c->fields[w], zero);
     }
-    if (r >= 0 && (rc = fgb_k_xpay(c, c->fields[p_new], c->fields[r], beta, c->fields[p_old]))) return rc;      // p = r + beta*p fg:23245
+    if (r >= 0) {                                                                                                 // p = r + beta*p fg:23245
+        if (c->cg_dev) rc = fgb_k_xpay_dev(c, c->fields[p_new], c->fields[r], 1, c->fields[p_old]);
+        else rc = fgb_k_xpay(c, c->fields[p_new], c->fields[r], beta, c->fields[p_old]);
+        if (rc) return rc;
+    }
     return fgb_cg_apply(c, F, p_new, w, mu0, lambda0, pAp);
 }
 
@@ -880,10 +906,56 @@ extern "C" int fgb_cg_update(fgb_ctx* c, int x, int r, int p, int w, double a, d
         if (c->implicit_w_of != p || x == p || r == p || x == r)
             return fgb_fail(c, FGB_EINVAL, "fgb_cg_update: no implicit operator result for field %d (call fgb_cg_step with w = FGB_W_IMPLICIT first)", p);
         const double zero[9] = {0};
-        return fgb_k_cg_update_implicit(c, c->ubuf, zero, c->fields[x], c->fields[r], c->fields[p], a, delta);
+        c->reduce_on_device = c->cg_dev;
+        const int rc = fgb_k_cg_update_implicit(c, c->ubuf, zero, c->fields[x], c->fields[r], c->fields[p], a, delta);
+        c->reduce_on_device = false;
+        return rc;
     }
     CHECK_FIELD(c, w);
-    return fgb_k_cg_update(c, c->fields[x], c->fields[r], c->fields[p], c->fields[w], a, delta);
+    c->reduce_on_device = c->cg_dev;
+    const int rc = fgb_k_cg_update(c, c->fields[x], c->fields[r], c->fields[p], c->fields[w], a, delta);
+    c->reduce_on_device = false;
+    return rc;
+}
+
+// ---- CG with device-resident scalars -------------------------------------------------------------------------------------------
+// The same iteration as fgb_cg_step / fgb_cg_update (runCGElasticity fg:23206-23246), but gamma, beta and alpha never leave the
+// device: a step and the following update are enqueued without any host synchronisation, and the host learns delta through a
+// pinned ring buffer when it asks for it (fgb_cgdev_wait).  The decision of iteration k depends on gamma_k only (fg:23223-23226),
+// so a host loop can enqueue the operator application of iteration k+1 before it waits for delta_k.
+extern "C" int fgb_cgdev_begin(fgb_ctx* c, double gamma) {
+    CHECK_CTX(c);
+    const double init[5] = {gamma, 0.0, 0.0, 0.0, 0.0};            // gamma, beta = 0 (first direction p = r), alpha, <p,p-w>, delta
+    FGB_CUDA(c, cudaMemcpyAsync(c->d_scalars, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+    FGB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return FGB_OK;
+}
+extern "C" int fgb_cgdev_step(fgb_ctx* c, int F, int r, int p_old, int p_new, int w, double mu0, double lambda0) {
+    CHECK_CTX(c);
+    if (r < 0) return fgb_fail(c, FGB_EINVAL, "fgb_cgdev_step needs the residual field");
+    double dummy = 0;
+    c->cg_dev = true;
+    int rc = fgb_cg_step(c, F, r, 0.0, p_old, p_new, w, mu0, lambda0, &dummy);
+    if (!rc) rc = fgb_k_cg_scalars(c, 0, 0);
+    c->cg_dev = false;
+    return rc;
+}
+extern "C" int fgb_cgdev_update(fgb_ctx* c, int x, int r, int p, int w, int slot) {
+    CHECK_CTX(c);
+    if (slot < 0 || slot >= FGB_CG_RING) return fgb_fail(c, FGB_EINVAL, "ring slot %d out of range 0..%d", slot, FGB_CG_RING - 1);
+    double dummy = 0;
+    c->cg_dev = true;
+    int rc = fgb_cg_update(c, x, r, p, w, 0.0, &dummy);
+    if (!rc) rc = fgb_k_cg_scalars(c, 1, slot);
+    c->cg_dev = false;
+    return rc;
+}
+extern "C" int fgb_cgdev_wait(fgb_ctx* c, int slot, double* out4) {
+    CHECK_CTX(c);
+    if (slot < 0 || slot >= FGB_CG_RING) return fgb_fail(c, FGB_EINVAL, "ring slot %d out of range 0..%d", slot, FGB_CG_RING - 1);
+    FGB_CUDA(c, cudaEventSynchronize(c->ring_ev[slot]));
+    for (int i = 0; i < 4; i++) out4[i] = c->h_ring[4 * slot + i];
+    return FGB_OK;
 }
 
 extern "C" int fgb_cg_direction(fgb_ctx* c, int p, int r, double beta) {

@@ -418,6 +418,13 @@ int fgb_allreduce_host(fgb_ctx* ctx, double* vals, int n, int op) {
     return FGB_OK;
 }
 
+int fgb_allgather_dev(fgb_ctx* ctx, int n) {
+    int rc = need_comm(ctx);
+    if (rc) return rc;
+    FGB_NCCL(ctx, g_nccl.AllGather(ctx->d_result, ctx->d_gather, (size_t)n, ncclDouble, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+    return FGB_OK;
+}
+
 // planes for the fused isotropic sweep (fused.cu): see fgb_internal.h for the slot order
 int fgb_comm_halo_iso(fgb_ctx* ctx, const double* r, const double* p_old) {
     int rc = need_comm(ctx);

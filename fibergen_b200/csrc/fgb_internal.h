@@ -10,6 +10,7 @@
 #include "../../include/fgb200.h"
 
 #define FGB_MAX_STAGES 24
+#define FGB_CG_RING 8
 #define FGB_MAX_LAW_PARAMS 36
 
 struct FftPlanDev {
@@ -94,7 +95,11 @@ struct fgb_ctx {
     double* d_result;           // [32]
     double* h_result;           // pinned [32]
     int red_blocks;
-    double* d_scalars;          // device-resident CG scalars
+    double* d_scalars;          // device-resident CG scalars: [0] gamma, [1] beta, [2] alpha, [3] <p, p - w>, [4] delta
+    bool cg_dev;                // fgb_cgdev_*: kernels take beta / alpha from d_scalars, reductions stay on the device
+    bool reduce_on_device;      // fgb_reduce_finish leaves the (rank-gathered) sums on the device instead of returning them
+    double* h_ring;             // pinned [FGB_CG_RING][4]: gamma, <p,p-w>, alpha, delta of the last iterations
+    cudaEvent_t ring_ev[8];
     int* d_flag;                // numeric error flag
     int* h_flag;
 
@@ -237,6 +242,11 @@ int fgb_reduce_finish(fgb_ctx* ctx, int nblocks, int nvals, int op, double* host
 // CTAs (148 SMs x occupancy) so that no partial last wave runs at reduced occupancy
 unsigned fgb_wave_grid(fgb_ctx* ctx, const void* kernel, int block, size_t n, size_t cap);
 int fgb_allreduce_host(fgb_ctx* ctx, double* vals, int n, int op);
+int fgb_allgather_dev(fgb_ctx* ctx, int n);       // d_result[0..n) of every rank -> d_gather[rank*n + i], no host synchronisation
+// device-resident CG scalars (fgb_cgdev_*): after a sum was left on the device by fgb_reduce_finish,
+// mode 0: <p,p-w> = sum/nxyz, alpha = gamma/(<p,p-w> + tiny);  mode 1: delta = sum/nxyz (+tiny), beta = delta/gamma, gamma = delta
+int fgb_k_cg_scalars(fgb_ctx* ctx, int mode, int ring_slot);
+int fgb_k_xpay_dev(fgb_ctx* ctx, double* r, const double* x, int scal_index, const double* y);   // r = x + d_scalars[i]*y
 
 // fused.cu -----------------------------------------------------------------------------------
 int fgb_fused_iso_applicable(const fgb_ctx* ctx);

@@ -95,7 +95,8 @@ __device__ __forceinline__ double pval(const double* __restrict__ r, const doubl
 template <int UPDATE>
 __global__ void __launch_bounds__(256) k_dir_stress_div_iso(const double* __restrict__ r, const double* __restrict__ p_old,
                                                             double* __restrict__ p_new, double* __restrict__ u, GridDev g, IsoPhases M,
-                                                            double cgbeta, double beta, double gamma, int JB) {
+                                                            double cgbeta, double beta, double gamma, int JB, const double* __restrict__ scal) {
+    if (scal) cgbeta = scal[1];          // device-resident CG scalar (fgb_cgdev_*)
     const int jblocks = (g.ny + JB - 1) / JB;
     const int i = blockIdx.x / jblocks;
     const int j0 = (blockIdx.x - i * jblocks) * JB;
@@ -211,7 +212,8 @@ __device__ __forceinline__ void diag_from(const IsoPhases& M, const double* phi,
 template <int UPDATE, int NP, int BJ, int HALO, int ZW, int NT>
 __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_dsd_march(const double* __restrict__ r, const double* __restrict__ p_old, double* __restrict__ p_new,
                                                    double* __restrict__ u, GridDev g, IsoPhases M, double cgbeta, double beta, double gamma,
-                                                   int SEG, const double* __restrict__ halo) {
+                                                   int SEG, const double* __restrict__ halo, const double* __restrict__ scal) {
+    if (scal) cgbeta = scal[1];          // device-resident CG scalar (fgb_cgdev_*)
     // halo != null (slab partition): planes i = -1 and i = lnx come from the neighbour ranks, layout
     // [r_lo 3][p_lo 3][r_hi 2][p_hi 2][phi_lo MAXP][phi_hi MAXP], each ny*nzp doubles (comm.cu: fgb_comm_halo_iso)
     const size_t pe = (size_t)g.ny * g.nzp;
@@ -396,6 +398,7 @@ static int launch_march(fgb_ctx* ctx, const double* r, const double* p_old, doub
     const GridDev& g = ctx->g;
     const double* halo = (ctx->nranks > 1) ? ctx->iso_halo : nullptr;
     const MarchTile mt = march_tile(ctx);
+    const double* scal = (UPDATE && ctx->cg_dev) ? ctx->d_scalars : nullptr;
     const int threads = mt.threads, kchunks = mt.kchunks, SEG = mt.SEG;
     const int segs = mt.segs;
 #define LAUNCH_MARCH5(BJ_, H_, Z_, NT_)                                                                              \
@@ -403,7 +406,7 @@ static int launch_march(fgb_ctx* ctx, const double* r, const double* p_old, doub
         const size_t smem = sizeof(double) * 2 * 3 * BJ_ * NT_;                                                     \
         if (smem > 48 * 1024)                                                                                        \
             FGB_CUDA(ctx, cudaFuncSetAttribute(k_dsd_march<UPDATE, NP, BJ_, H_, Z_, NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_dsd_march<UPDATE, NP, BJ_, H_, Z_, NT_><<<grid, threads, smem, ctx->stream>>>(r, p_old, p_new, ctx->ubuf, g, M, cgbeta, beta, gamma, SEG, halo); \
+        k_dsd_march<UPDATE, NP, BJ_, H_, Z_, NT_><<<grid, threads, smem, ctx->stream>>>(r, p_old, p_new, ctx->ubuf, g, M, cgbeta, beta, gamma, SEG, halo, scal); \
     } while (0)
 #define LAUNCH_MARCH(BJ_)                                     \
     do {                                                      \
@@ -436,7 +439,8 @@ template <int MODE>
 __global__ void __launch_bounds__(256) k_eps_dot6(const double* __restrict__ u, double* __restrict__ eta, const double* __restrict__ p,
                                                   GridDev g, Const9f E, double* __restrict__ partials, const double* __restrict__ halo_lo,
                                                   const double* __restrict__ halo_hi, size_t hslot, double* __restrict__ x,
-                                                  double* __restrict__ r, double a) {
+                                                  double* __restrict__ r, double a, const double* __restrict__ scal) {
+    if (MODE == 2 && scal) a = scal[2];
     const unsigned nvox = (unsigned)g.lnx * (unsigned)g.ny * (unsigned)g.nz;
     const size_t us = 2 * (size_t)g.unzcs;
     double acc = 0;
@@ -527,8 +531,8 @@ int fgb_k_dir_stress_div_iso(fgb_ctx* ctx, const double* r, double cgbeta, const
             case 3: return r ? launch_march<1, 3>(ctx, r, p_old, p_new, M, cgbeta, beta, gamma) : launch_march<0, 3>(ctx, nullptr, p_old, nullptr, M, 0.0, beta, gamma);
         }
     }
-    if (r) k_dir_stress_div_iso<1><<<grid, threads, 0, ctx->stream>>>(r, p_old, p_new, ctx->ubuf, g, M, cgbeta, beta, gamma, JB);
-    else k_dir_stress_div_iso<0><<<grid, threads, 0, ctx->stream>>>(nullptr, p_old, nullptr, ctx->ubuf, g, M, 0.0, beta, gamma, JB);
+    if (r) k_dir_stress_div_iso<1><<<grid, threads, 0, ctx->stream>>>(r, p_old, p_new, ctx->ubuf, g, M, cgbeta, beta, gamma, JB, ctx->cg_dev ? ctx->d_scalars : nullptr);
+    else k_dir_stress_div_iso<0><<<grid, threads, 0, ctx->stream>>>(nullptr, p_old, nullptr, ctx->ubuf, g, M, 0.0, beta, gamma, JB, nullptr);
     FGB_CHECK_LAUNCH(ctx, "k_dir_stress_div_iso");
     return FGB_OK;
 }
@@ -538,7 +542,9 @@ int fgb_k_dir_stress_div_iso(fgb_ctx* ctx, const double* r, double cgbeta, const
 template <int DOT_ONLY>
 __global__ void __launch_bounds__(256, 4) k_cg_update_u6(const double* __restrict__ u, const double* __restrict__ p, double* __restrict__ x,
                                                       double* __restrict__ r, double a, GridDev g, Const9f E, double* __restrict__ partials,
-                                                      const double* __restrict__ halo_lo, const double* __restrict__ halo_hi, size_t hslot) {
+                                                      const double* __restrict__ halo_lo, const double* __restrict__ halo_hi, size_t hslot,
+                                                      const double* __restrict__ scal) {
+    if (!DOT_ONLY && scal) a = scal[2];
     const unsigned nzh = (unsigned)(g.nz + 1) / 2;
     const unsigned npairs = (unsigned)g.lnx * (unsigned)g.ny * nzh;
     const size_t us = 2 * (size_t)g.unzcs;
@@ -630,9 +636,10 @@ static int eps_dot_launch(fgb_ctx* ctx, int mode, const double* u, double* eta, 
         ProfScope ps(ctx, mode == 2 ? "cg_update_implicit" : (mode == 1 ? "eps_dot_implicit" : "eps_dot"));
         const double* lo = (ctx->nranks > 1) ? ctx->halo : nullptr;
         const double* hi = (ctx->nranks > 1) ? ctx->halo + 3 * ctx->halo_slot : nullptr;
-        if (mode == 0) k_eps_dot6<0><<<grid, 256, 0, ctx->stream>>>(u, eta, p, g, E, ctx->d_partials, lo, hi, ctx->halo_slot, x, r, a);
-        else if (mode == 1) k_eps_dot6<1><<<grid, 256, 0, ctx->stream>>>(u, eta, p, g, E, ctx->d_partials, lo, hi, ctx->halo_slot, x, r, a);
-        else k_eps_dot6<2><<<grid, 256, 0, ctx->stream>>>(u, eta, p, g, E, ctx->d_partials, lo, hi, ctx->halo_slot, x, r, a);
+        const double* scal = ctx->cg_dev ? ctx->d_scalars : nullptr;
+        if (mode == 0) k_eps_dot6<0><<<grid, 256, 0, ctx->stream>>>(u, eta, p, g, E, ctx->d_partials, lo, hi, ctx->halo_slot, x, r, a, scal);
+        else if (mode == 1) k_eps_dot6<1><<<grid, 256, 0, ctx->stream>>>(u, eta, p, g, E, ctx->d_partials, lo, hi, ctx->halo_slot, x, r, a, scal);
+        else k_eps_dot6<2><<<grid, 256, 0, ctx->stream>>>(u, eta, p, g, E, ctx->d_partials, lo, hi, ctx->halo_slot, x, r, a, scal);
         FGB_CHECK_LAUNCH(ctx, "k_eps_dot6");
     }
     int rc = fgb_reduce_finish(ctx, grid, 1, 0, out);
@@ -660,8 +667,9 @@ static int implicit_sweep(fgb_ctx* ctx, bool dot_only, const double* u, const do
         ProfScope ps(ctx, dot_only ? "eps_dot_implicit" : "cg_update_implicit");
         const double* lo = (ctx->nranks > 1) ? ctx->halo : nullptr;
         const double* hi = (ctx->nranks > 1) ? ctx->halo + 3 * ctx->halo_slot : nullptr;
-        if (dot_only) k_cg_update_u6<1><<<grid, 256, 0, ctx->stream>>>(u, p, x, r, a, g, E, ctx->d_partials, lo, hi, ctx->halo_slot);
-        else k_cg_update_u6<0><<<grid, 256, 0, ctx->stream>>>(u, p, x, r, a, g, E, ctx->d_partials, lo, hi, ctx->halo_slot);
+        const double* scal = ctx->cg_dev ? ctx->d_scalars : nullptr;
+        if (dot_only) k_cg_update_u6<1><<<grid, 256, 0, ctx->stream>>>(u, p, x, r, a, g, E, ctx->d_partials, lo, hi, ctx->halo_slot, scal);
+        else k_cg_update_u6<0><<<grid, 256, 0, ctx->stream>>>(u, p, x, r, a, g, E, ctx->d_partials, lo, hi, ctx->halo_slot, scal);
         FGB_CHECK_LAUNCH(ctx, "k_cg_update_u6");
     }
     int rc = fgb_reduce_finish(ctx, grid, 1, 0, out);

@@ -202,6 +202,9 @@ LSSolver::LSSolver(int nx, int ny, int nz, double dx, double dy, double dz, int 
     _loadstep_extrapolation_order = 0;                                                       // fg:14830-14831
     _loadstep_extrapolation_method = "polynomial";
     _first_loadstep = -1;
+    _pipelined_cg = true;
+    _smooth_levels = -1;                                                                     // fg:14842-14843
+    _smooth_tol = 0.001;
     // the reference sizes the prescribed loads in its constructor (mode is known there); here the mode may still change until
     // init(), so loads set earlier are kept as given and expanded to the tensor dimension by init()
     _E.assign(_dim, 0.0);
@@ -292,6 +295,9 @@ void LSSolver::set_impl(const std::string& key, const std::string& value) {
     else if (key == "freq_hack") _freq_hack = to_bool(value);
     else if (key == "G0_solver") _G0_solver = value;
     else if (key == "mixing_rule") _mixing_rule = value;
+    else if (key == "smooth_levels") _smooth_levels = (value.size() && value[0] == '-') ? -(int)to_size(value.substr(1)) : (int)to_size(value);   // fg:15055
+    else if (key == "smooth_tol") _smooth_tol = to_double(value);                                                                              // fg:15056
+    else if (key == "pipelined_cg") _pipelined_cg = to_bool(value);      // not a reference key: host-scalar CG loop when false (A/B parity)
     else if (key == "loadsteps") {
         // uniform_loadsteps(n) (fg:15033) or an explicit comma separated parameter list
         _loadsteps.clear();
@@ -445,6 +451,13 @@ Vec LSSolver::expandLoad(const Vec& e, const char* what) const {
     else fail(std::string("Invalid size of ") + what + " vector");
     return r;
 }
+
+void LSSolver::initPhase(int nfib, const fgb_capsule* fibers, int matrix_mat, bool normals, bool orientation) {
+    // initPhi fg:17152-17158 -> fg:17489 with the solver's smooth_levels / smooth_tol
+    if (!_ctx) fail("solver not initialised");
+    check(fgb_init_phase_capsules(_ctx, nfib, fibers, matrix_mat, _smooth_levels, _smooth_tol, nullptr, normals ? 1 : 0, orientation ? 1 : 0));
+}
+void LSSolver::getPhase(int m, double* phi) { check(fgb_get_phase(_ctx, m, phi)); }
 
 void LSSolver::setStrain(const Vec& e) {
     if (e.size() != 3 && e.size() != 6 && e.size() != 9) fail("Invalid size of strain vector");
@@ -795,6 +808,10 @@ void LSSolver::runCGElasticity(const Vec& E0, const Vec& S0) {
     const double gamma0 = gamma;
     Vec zero(_dim, 0.0);
     check(fgb_set_constant(_ctx, p, zero.data()));
+    if (_cg_reinit <= 0 && _pipelined_cg) {
+        runCGElasticityPipelined(E, r, p, p2, w, gamma, ee.get());
+        return;
+    }
     double beta = 0.0;                                                                       // p = r  ==  r + 0*p
     size_t iter = 0;
     for (;;) {
@@ -831,6 +848,29 @@ void LSSolver::runCGElasticity(const Vec& E0, const Vec& S0) {
         delta += SMALL;
         beta = delta / gamma;
         gamma = delta;
+    }
+}
+
+void LSSolver::runCGElasticityPipelined(const Vec& E, int r, int p, int p2, int w, double gamma, ErrorEstimator* ee) {
+    // The loop of fg:23206-23246 with gamma, beta, alpha on the device (fgb_cgdev_*).  The stop test of iteration k needs gamma_k
+    // only (fg:23223-23226), which the update of iteration k-1 produced: the operator application of iteration k+1 is enqueued
+    // before the host waits for delta_k, so the device never idles and an iteration costs one (hidden) host synchronisation.
+    (void)E;
+    const double gamma0 = gamma;
+    check(fgb_cgdev_begin(_ctx, gamma));
+    check(fgb_cgdev_step(_ctx, -1, r, p, p2, w, _mu_0, _lambda_0));
+    std::swap(p, p2);
+    size_t iter = 0;
+    for (size_t k = 0;; k++) {
+        const int slot = (int)(k % 8);
+        check(fgb_cgdev_update(_ctx, _epsilon, r, p, w, slot));                            // epsilon += alpha*p ; r -= alpha*(p - w)
+        ee->update_cg(gamma, gamma0);
+        if (converged(iter, ee->abs_error(), ee->rel_error())) break;
+        check(fgb_cgdev_step(_ctx, -1, r, p, p2, w, _mu_0, _lambda_0));                    // iteration k+1, before delta_k is known
+        std::swap(p, p2);
+        double s[4];
+        check(fgb_cgdev_wait(_ctx, slot, s));
+        gamma = s[3] + SMALL;
     }
 }
 
@@ -967,6 +1007,10 @@ int fgls_set_reference(fgls_solver* h, double mu, double lambda) { FGLS_TRY(h->s
 int fgls_init(fgls_solver* h) { FGLS_TRY(h->s->init()) }
 int fgls_init_comm(fgls_solver* h, const void* id) { FGLS_TRY(h->s->initComm(id)) }
 int fgls_set_phase(fgls_solver* h, int m, const double* phi) { FGLS_TRY(h->s->setPhase(m, phi)) }
+int fgls_init_phase_capsules(fgls_solver* h, int nfib, const fgb_capsule* fibers, int matrix_mat, int normals, int orientation) {
+    FGLS_TRY(h->s->initPhase(nfib, fibers, matrix_mat, normals != 0, orientation != 0))
+}
+int fgls_get_phase(fgls_solver* h, int m, double* phi) { FGLS_TRY(h->s->getPhase(m, phi)) }
 int fgls_set_normals(fgls_solver* h, const double* const* c) { FGLS_TRY(h->s->setNormals(c)) }
 int fgls_set_orientation(fgls_solver* h, const double* const* c) { FGLS_TRY(h->s->setOrientation(c)) }
 int fgls_set_strain(fgls_solver* h, const double* E) { FGLS_TRY(h->s->setStrain(fgb::Vec(E, E + h->s->dim()))) }

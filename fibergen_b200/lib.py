@@ -49,6 +49,8 @@ PROTOTYPES = {
     "fgb_set_normals": (C.c_int, [C.c_void_p, c_dpp]),
     "fgb_set_orientation": (C.c_int, [C.c_void_p, c_dpp]),
     "fgb_set_mixing": (C.c_int, [C.c_void_p, C.c_int, c_dp, C.c_int]),
+    "fgb_init_phase_capsules": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double, c_dp, C.c_int, C.c_int]),
+    "fgb_get_phase": (C.c_int, [C.c_void_p, C.c_int, c_dp]),
     "fgb_set_freq_hack": (C.c_int, [C.c_void_p, C.c_int]),
     "fgb_set_bc": (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_double]),
     "fgb_set_constant": (C.c_int, [C.c_void_p, C.c_int, c_dp]),
@@ -89,6 +91,10 @@ PROTOTYPES = {
     "fgb_cg_update": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, c_dp]),
     "fgb_cg_implicit_w_supported": (C.c_int, [C.c_void_p]),
     "fgb_cg_direction": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double]),
+    "fgb_cgdev_begin": (C.c_int, [C.c_void_p, C.c_double]),
+    "fgb_cgdev_step": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]),
+    "fgb_cgdev_update": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "fgb_cgdev_wait": (C.c_int, [C.c_void_p, C.c_int, c_dp]),
     "fgb_check_numeric": (C.c_int, [C.c_void_p]),
     "fgb_launch_count": (C.c_uint64, [C.c_void_p]),
     "fgb_launch_count_reset": (None, [C.c_void_p]),
@@ -106,6 +112,8 @@ PROTOTYPES = {
     "fgls_init": (C.c_int, [C.c_void_p]),
     "fgls_init_comm": (C.c_int, [C.c_void_p, C.c_void_p]),
     "fgls_set_phase": (C.c_int, [C.c_void_p, C.c_int, c_dp]),
+    "fgls_init_phase_capsules": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "fgls_get_phase": (C.c_int, [C.c_void_p, C.c_int, c_dp]),
     "fgls_set_normals": (C.c_int, [C.c_void_p, c_dpp]),
     "fgls_set_orientation": (C.c_int, [C.c_void_p, c_dpp]),
     "fgls_set_strain": (C.c_int, [C.c_void_p, c_dp]),
@@ -132,6 +140,13 @@ PROTOTYPES = {
     "fgls_launches": (C.c_uint64, [C.c_void_p]),
     "fgls_ctx": (C.c_void_p, [C.c_void_p]),
 }
+
+
+
+class Capsule(C.Structure):
+    """fgb_capsule (fgb200.h): a <place_fiber> capsule"""
+    _fields_ = [("c", C.c_double * 3), ("a", C.c_double * 3), ("L0", C.c_double), ("R", C.c_double), ("material", C.c_int)]
+
 
 _lib = None
 

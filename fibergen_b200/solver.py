@@ -48,6 +48,17 @@ def _planes(arr):
     return ptrs, arr
 
 
+def capsule_array(fibers):
+    """fibers: iterable of (centre, axis, L0, R, material) as the <place_fiber> action takes them (fg:25789-25823)"""
+    fibers = list(fibers)
+    arr = (L.Capsule * max(len(fibers), 1))()
+    for i, (c, a, L0, R, mat) in enumerate(fibers):
+        arr[i].c[:] = [float(x) for x in c]
+        arr[i].a[:] = [float(x) for x in a]
+        arr[i].L0, arr[i].R, arr[i].material = float(L0), float(R), int(mat)
+    return arr, len(fibers)
+
+
 class Context:
     """Raw device context (fgb_create ... fgb_destroy) with numpy conveniences -- operator-level tests."""
 
@@ -255,6 +266,16 @@ class LSSolver:
     def set_phase(self, m, phi, padded=False):
         pp = np.ascontiguousarray(phi if padded else pad(phi), dtype=np.float64)
         self.chk(self.lib.fgls_set_phase(self.h, m, _dp(pp)))
+
+    def init_phase(self, fibers, matrix_mat=0, normals=False, orientation=False):
+        """initPhi on the device from a fibre list [(centre, axis, L0, R, material), ...] (fg:17489)"""
+        arr, n = capsule_array(fibers)
+        self.chk(self.lib.fgls_init_phase_capsules(self.h, n, C.cast(arr, C.c_void_p), matrix_mat, int(normals), int(orientation)))
+
+    def get_phase(self, m, padded=False):
+        out = np.empty((self.lnx, self.ny, self.nzp))
+        self.chk(self.lib.fgls_get_phase(self.h, m, _dp(out)))
+        return out if padded else unpad(out, self.nz)
 
     def set_normals(self, n):
         ptrs, keep = _planes(pad(n))

@@ -119,6 +119,23 @@ int  fgb_set_orientation(fgb_ctx* ctx, const double* const* comps3);
 /* mixing rule + LaminateMixedMaterialLaw settings (fg:13110-13145):
  * lam_params = {eps_t, eps_a, eps_g, alpha, beta, delta, maxiter, backtrack, project_t, fixed_c1} or NULL for defaults */
 int  fgb_set_mixing(fgb_ctx* ctx, int rule_id, const double* lam_params, int nparams);
+/* Phase initialisation on the device: LSSolver::initPhi fg:17489-17581 for capsule fibres as the <place_fiber> action creates them
+ * (CapsuleFiber fg:5254: centre, axis, total length L0, radius R; L0 <= 4R/3 is a sphere).  Every non-matrix phase gets the
+ * composite-voxel volume fraction of integratePhiVoxel fg:16622 (smooth_levels < 0: adaptive with tolerance smooth_tol, the
+ * reference defaults are -1 and 1e-3, fg:14842-14843), then normalizePhi fg:17588 (the last material has the highest priority).
+ * Periodic images are separate entries of the list (the reference's ghost fibres).  x0 = cell origin (NULL: 0).  Optionally the
+ * normals (gradient of the distance to the closest fibre, fg:6905-6924) and the orientation (its axis, fg:6885-6903) are
+ * written for every voxel that has a fibre within reach (about 8 voxels); they are only read at interface voxels. */
+typedef struct {
+    double c[3];      /* centre */
+    double a[3];      /* axis (need not be normalised) */
+    double L0, R;     /* total length, radius */
+    int material;     /* phase index */
+} fgb_capsule;
+int  fgb_init_phase_capsules(fgb_ctx* ctx, int nfib, const fgb_capsule* fibers, int matrix_mat, int smooth_levels, double smooth_tol,
+                             const double* x0, int with_normals, int with_orientation);
+/* Phase::phi back to the host: one padded plane (writeRawPhase fg:17004) */
+int  fgb_get_phase(fgb_ctx* ctx, int phase, double* phi_plane);
 /* freq_hack (fg:19392-19394) for the collocated elasticity operator */
 int  fgb_set_freq_hack(fgb_ctx* ctx, int on);
 
@@ -214,6 +231,18 @@ int  fgb_cg_update(fgb_ctx* ctx, int x, int r, int p, int w, double a, double* d
 #define FGB_W_IMPLICIT (-2)
 int  fgb_cg_implicit_w_supported(const fgb_ctx* ctx);
 int  fgb_cg_direction(fgb_ctx* ctx, int p, int r, double beta);
+/* The same iteration with gamma, beta and alpha resident on the device (no host synchronisation inside an iteration):
+ *   fgb_cgdev_begin : gamma = <r, r> + tiny of the start residual, beta = 0
+ *   fgb_cgdev_step  : p_new = r + beta*p_old ; w = operator(p_new) ; alpha = gamma / (<p_new, p_new - w> + tiny)      (fg:23245, 23209-23218)
+ *   fgb_cgdev_update: x += alpha*p ; r -= alpha*(p - w) ; delta = <r, r> + tiny ; beta = delta/gamma ; gamma = delta (fg:23221-23245);
+ *                     {gamma before, <p,p-w>, alpha, <r,r>} go to ring slot `slot` (0..7) of a pinned buffer
+ *   fgb_cgdev_wait  : blocks until that update has finished and returns the four values.
+ * The arithmetic is operation by operation that of the host-scalar form, so both give identical residual histories.  The stop
+ * test of iteration k needs gamma_k only, so the caller may enqueue fgb_cgdev_step of iteration k+1 before waiting for delta_k. */
+int  fgb_cgdev_begin(fgb_ctx* ctx, double gamma);
+int  fgb_cgdev_step(fgb_ctx* ctx, int F_or_neg, int r, int p_old, int p_new, int w, double mu0, double lambda0);
+int  fgb_cgdev_update(fgb_ctx* ctx, int x, int r, int p, int w, int slot);
+int  fgb_cgdev_wait(fgb_ctx* ctx, int slot, double* out4);
 /* returns FGB_ENUMERIC if a material law flagged a domain error since the last call (fg:10293, fg:21202) */
 int  fgb_check_numeric(fgb_ctx* ctx);
 

@@ -47,6 +47,9 @@ public:
 
     // --- phase data (initPhi fg:17489, padded planes of local_nx*ny*nzp doubles)
     void setPhase(int material, const double* phi);
+    // the same on the device from the fibre list (initPhi fg:17152-17158 with the settings smooth_levels / smooth_tol)
+    void initPhase(int nfib, const fgb_capsule* fibers, int matrix_mat = 0, bool normals = false, bool orientation = false);
+    void getPhase(int material, double* phi);
     void setNormals(const double* const* comps3);
     void setOrientation(const double* const* comps3);
 
@@ -101,6 +104,7 @@ private:
     void runBasic(const Vec& E0, const Vec& S0);
     void runPolarization(const Vec& E0, const Vec& S0);
     void runCGElasticity(const Vec& E0, const Vec& S0);
+    void runCGElasticityPipelined(const Vec& E, int r, int p, int p2, int w, double gamma, ErrorEstimator* ee);
     void runCGHyper(const Vec& E0, const Vec& S0);
     bool converged(size_t& iter, double abs_err, double rel_err, bool check_bc = true);
     ErrorEstimator* create_error_estimator(const std::string& name = "");
@@ -118,6 +122,9 @@ private:
     std::string _update_ref, _error_estimator, _outer_error_estimator, _method, _gamma_scheme, _mode, _mixing_rule,
         _cg_inner_product, _G0_solver;
     bool _freq_hack;
+    int _smooth_levels;                            // fg:14670-14671
+    double _smooth_tol;
+    bool _pipelined_cg;                            // CG scalars resident on the device (default); false: host-scalar loop
     std::vector<double> _loadsteps;
     size_t _loadstep_extrapolation_order;          // 0 = none, 1 = linear, ... (fg:14696)
     std::string _loadstep_extrapolation_method;    // "polynomial" (fg:14697; "transformation" is refused)
@@ -164,6 +171,8 @@ int  fgls_set_reference(fgls_solver* s, double mu, double lambda);
 int  fgls_init(fgls_solver* s);
 int  fgls_init_comm(fgls_solver* s, const void* id128);
 int  fgls_set_phase(fgls_solver* s, int material, const double* phi);
+int  fgls_init_phase_capsules(fgls_solver* s, int nfib, const fgb_capsule* fibers, int matrix_mat, int normals, int orientation);
+int  fgls_get_phase(fgls_solver* s, int material, double* phi);
 int  fgls_set_normals(fgls_solver* s, const double* const* comps3);
 int  fgls_set_orientation(fgls_solver* s, const double* const* comps3);
 int  fgls_set_strain(fgls_solver* s, const double* E);

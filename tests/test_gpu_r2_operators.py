@@ -170,3 +170,67 @@ def test_loads_before_init_and_setting_validation():
     s2 = fb.LSSolver(4, 4, 4, mode="heat")
     with pytest.raises(fb.FgbError, match="Invalid size"):
         s2.set_strain([1, 0, 0, 0])
+
+
+def test_device_phase_init_matches_restated_initphi():
+    """fgb_init_phase_capsules (initPhi fg:17489 on the device) against the C restatement oracle/fg_phase.c: the Hashin demo's coated
+    sphere (three phases, priority of the last material) and a periodic short-fibre cell with its images"""
+    from oracle import fg_phase as fp
+    from microstructures import rsa_capsules, fiber_list
+    from test_oracle_pinning import HASHIN_FIBERS
+    cases = [((64, 64, 64), HASHIN_FIBERS, 3)]
+    n = (48, 48, 48)
+    Cs, Ds, R, Lc = rsa_capsules(n, seed=3, vol_frac=0.12, diameter_vox=6.0, aspect=4.0, max_tries=400)
+    fibs, box = fiber_list(n, Cs, Ds, R, Lc, material=1)
+    assert abs(box[0] - 1) < 1e-15
+    cases.append((n, fibs, 2))
+    for n, fibers, nmat in cases:
+        s = fb.LSSolver(*n, mode="elasticity")
+        for m in range(nmat):
+            s.add_material("m%d" % m, "iso", 1.0 + m, 1.0)
+        s.init()
+        s.init_phase(fibers, matrix_mat=0, normals=True)
+        want, cnt = fp.init_phi(n, (1., 1., 1.), fibers, nmat)
+        got = np.stack([s.get_phase(m) for m in range(nmat)])
+        assert cnt > 1000
+        assert np.abs(got - want).max() <= 1e-12
+        assert np.abs(got.sum(axis=0) - 1).max() <= 1e-15
+        s.close()
+
+
+def test_pipelined_cg_is_the_same_iteration():
+    """fgb_cgdev_* (gamma, beta, alpha resident on the device, operator application enqueued ahead of the stop test) against the
+    host-scalar loop: identical residual histories, bit for bit, and the same solution"""
+    n = (32, 24, 20)
+    res, eps = [], []
+    for pipelined in (True, False):
+        s = fb.LSSolver(*n, mode="elasticity", method="cg", gamma_scheme="staggered", error_estimator="residual", tol=1e-9,
+                        pipelined_cg=pipelined)
+        for name, law, params, olaw, phi in el_phases(n, contrast=30.0):
+            s.add_material(name, law, *params)
+        s.init()
+        for m, (name, law, params, olaw, phi) in enumerate(el_phases(n, contrast=30.0)):
+            s.set_phase(m, phi)
+        s.set_strain([0.3, -0.1, 0.2, 0.5, 0.1, -0.4])
+        s.run()
+        res.append(s.get_residuals())
+        eps.append(s.get_field())
+        s.close()
+    assert len(res[0]) == len(res[1]) > 10
+    assert np.array_equal(res[0], res[1])
+    assert np.array_equal(eps[0], eps[1])
+    # a path without the fused sweep (collocated: explicit operator result, generic kernels)
+    res = []
+    for pipelined in (True, False):
+        s = fb.LSSolver(*n, mode="elasticity", method="cg", gamma_scheme="collocated", error_estimator="residual", tol=1e-9,
+                        pipelined_cg=pipelined)
+        for name, law, params, olaw, phi in el_phases(n, contrast=30.0):
+            s.add_material(name, law, *params)
+        s.init()
+        for m, (name, law, params, olaw, phi) in enumerate(el_phases(n, contrast=30.0)):
+            s.set_phase(m, phi)
+        s.set_strain([0.3, -0.1, 0.2, 0.5, 0.1, -0.4])
+        s.run()
+        res.append(s.get_residuals())
+        s.close()
+    assert np.array_equal(res[0], res[1])
