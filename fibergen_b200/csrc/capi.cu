@@ -142,6 +142,8 @@ extern "C" int fgb_create(fgb_ctx** out, int nx, int ny, int nz, double Lx, doub
     c->nccl_comm = nullptr; c->nccl_lib = nullptr; c->sbuf = nullptr; c->xbuf = nullptr; c->xbuf_cap = 0;
     c->halo = nullptr; c->halo_slot = 0; c->d_gather = nullptr; c->visc_tmp = nullptr; c->p2p = false; c->iso_halo = nullptr; c->phi_halo_valid = false;
     c->halo_base = nullptr; c->iso_set = 0; c->halo_seq = c->iso_seq = 0;
+    c->sync_base = nullptr; c->bar_seq = c->ex_seq = 0;
+    for (int q = 0; q < 8; q++) c->peer_sync[q] = nullptr;
     for (int q = 0; q < 8; q++) c->peer_halo[q] = nullptr;
     c->launches = 0; c->profiling = false;
     c->bc_active = false; c->bc_relax = 1.0;
@@ -411,6 +413,10 @@ extern "C" int fgb_component_dot(fgb_ctx* c, int a, int b, double* out) {
 static int poll_flag(fgb_ctx* c) {
     FGB_CUDA(c, cudaMemcpyAsync(c->h_flag, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     FGB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (*c->h_flag & 4) {
+        FGB_CUDA(c, cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->stream));
+        return fgb_fail(c, FGB_ECOMM, "peer synchronisation timed out (a rank of the slab partition did not reach the barrier within 4 s)");
+    }
     if (*c->h_flag) {
         FGB_CUDA(c, cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->stream));
         return fgb_fail(c, FGB_ENUMERIC, "material law domain error on the device (log/pow of a non-positive det F, or >2 phases in a laminate voxel)");
@@ -633,6 +639,18 @@ extern "C" int fgb_g0div_hyper(fgb_ctx* c, int f, double mu0, double lambda0, do
     memset(&ga, 0, sizeof(ga));
     ga.kind = 6;
     ga.c10 = -alpha / (2 * mu0);                                   // fg:20162-20163
+    ga.c20 = alpha / (2 * mu0 * (1 + 2 * mu0 / lambda0));
+    return fourier_operator(c, c->fields[f], ga);
+}
+
+// fftTensor, G0DivOperatorFourierHyper, GradOperatorFourierHyper, fftInvTensor (fg:24572-24575): grad G0 Div applied in Fourier space
+extern "C" int fgb_grad_g0div_hyper(fgb_ctx* c, int f, double mu0, double lambda0, double alpha) {
+    CHECK_CTX(c); CHECK_FIELD(c, f);
+    if (c->dim != 9) return fgb_fail(c, FGB_EINVAL, "fgb_grad_g0div_hyper needs the 9-component hyperelasticity layout");
+    GreenArgs ga;
+    memset(&ga, 0, sizeof(ga));
+    ga.kind = 11;
+    ga.c10 = -alpha / (2 * mu0);
     ga.c20 = alpha / (2 * mu0 * (1 + 2 * mu0 / lambda0));
     return fourier_operator(c, c->fields[f], ga);
 }

@@ -85,8 +85,81 @@ static int ensure_xbuf(fgb_ctx* ctx, size_t need) {
 }
 
 
-// stream-ordered barrier over all ranks (tiny all-gather): everything the peers enqueued before it has completed when it completes
+// ---- synchronisation over peer memory --------------------------------------------------------------------------------------
+// Every rank owns a small block (sync_base, mapped by all peers with CUDA IPC):
+//   u64 bar[8]        bar[q]  = number of the last barrier rank q has entered
+//   u64 exf[8]        exf[q]  = number of the last scalar exchange rank q has published
+//   f64 exv[2][8][8]  exv[parity][q][i] = value i of rank q in the exchange with that parity
+// A barrier / exchange is ONE single-warp kernel: lane q publishes to rank q (values, system fence, flag) and then polls its own
+// block until rank q's flag has arrived.  It is stream ordered, so the stores of the preceding FFT kernel into peer memory have
+// completed before the flag goes out, and the following kernel starts only after every peer has signalled.  The poll gives up
+// after ~4 s and raises the context's error flag instead of hanging the device.
+#define FGB_SYNC_BYTES 4096
+struct SyncPeers {
+    unsigned long long* p[8];
+};
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__global__ void k_peer_barrier(SyncPeers P, int me, int n, unsigned long long seq, int* flag) {
+    const int q = threadIdx.x;
+    __threadfence_system();
+    if (q < n) {
+        st_release_sys(P.p[q] + me, seq);                    // bar[me] on rank q
+        const unsigned long long* mine = P.p[me] + q;        // bar[q] on this rank
+        const unsigned long long t0 = global_ns();
+        while (ld_acquire_sys(mine) < seq) {
+            if (global_ns() - t0 > 4000000000ull) { atomicOr(flag, 4); break; }
+        }
+    }
+    __syncwarp();
+    __threadfence_system();
+}
+// all-gather of nv <= 8 doubles per rank: out[q*nv + i] = value i of rank q
+__global__ void k_peer_allgather(SyncPeers P, int me, int n, unsigned long long seq, const double* __restrict__ vals, int nv,
+                                 double* __restrict__ out, int* flag) {
+    const int q = threadIdx.x;
+    const int par = (int)(seq & 1ull);
+    if (q < n) {
+        double* dst = reinterpret_cast<double*>(P.p[q] + 16) + ((size_t)par * 8 + me) * 8;      // exv[par][me][.] on rank q
+        for (int i = 0; i < nv; i++) reinterpret_cast<volatile double*>(dst)[i] = vals[i];
+        __threadfence_system();
+        st_release_sys(P.p[q] + 8 + me, seq);                // exf[me] on rank q
+        const unsigned long long* mine = P.p[me] + 8 + q;
+        const unsigned long long t0 = global_ns();
+        bool ok = true;
+        while (ld_acquire_sys(mine) < seq) {
+            if (global_ns() - t0 > 4000000000ull) { atomicOr(flag, 4); ok = false; break; }
+        }
+        const volatile double* src = reinterpret_cast<const volatile double*>(reinterpret_cast<double*>(P.p[me] + 16) + ((size_t)par * 8 + q) * 8);
+        for (int i = 0; i < nv; i++) out[q * nv + i] = ok ? src[i] : NAN;
+    }
+}
+
+static bool use_peer_sync(const fgb_ctx* ctx) {
+    static const bool off = getenv("FGB_NCCL_BARRIER") != nullptr;
+    return ctx->p2p && !off;
+}
+
+// stream-ordered barrier over all ranks: everything the peers enqueued before it has completed when it completes
 static int comm_barrier(fgb_ctx* ctx) {
+    if (use_peer_sync(ctx)) {
+        SyncPeers P;
+        for (int q = 0; q < 8; q++) P.p[q] = ctx->peer_sync[q];
+        k_peer_barrier<<<1, 32, 0, ctx->stream>>>(P, ctx->rank, ctx->nranks, ++ctx->bar_seq, ctx->d_flag);
+        FGB_CHECK_LAUNCH(ctx, "k_peer_barrier");
+        return FGB_OK;
+    }
     FGB_NCCL(ctx, g_nccl.AllGather(ctx->d_result + 60, ctx->d_gather, 1, ncclDouble, (ncclComm_t)ctx->nccl_comm, ctx->stream));
     return FGB_OK;
 }
@@ -97,15 +170,15 @@ static int comm_barrier(fgb_ctx* ctx) {
 static int map_peers(fgb_ctx* ctx) {
     ctx->p2p = false;
     const int P = ctx->nranks, me = ctx->rank;
-    for (int q = 0; q < 8; q++) ctx->peer_xbuf[q] = ctx->peer_sbuf[q] = ctx->peer_halo[q] = nullptr;
+    for (int q = 0; q < 8; q++) { ctx->peer_xbuf[q] = ctx->peer_sbuf[q] = ctx->peer_halo[q] = nullptr; ctx->peer_sync[q] = nullptr; }
     if (P > 8) return FGB_OK;
-    struct Handles { cudaIpcMemHandle_t x, s, h; double ok; };
+    struct Handles { cudaIpcMemHandle_t x, s, h, y; double ok; };
     static_assert(sizeof(Handles) % 8 == 0, "handle record must be a multiple of 8 bytes");
     Handles mine;
     memset(&mine, 0, sizeof(mine));
     bool ok = getenv("FGB_NO_P2P") == nullptr;
     if (ok) ok = cudaIpcGetMemHandle(&mine.x, ctx->xbuf) == cudaSuccess && cudaIpcGetMemHandle(&mine.s, ctx->sbuf) == cudaSuccess &&
-                 cudaIpcGetMemHandle(&mine.h, ctx->halo_base) == cudaSuccess;
+                 cudaIpcGetMemHandle(&mine.h, ctx->halo_base) == cudaSuccess && cudaIpcGetMemHandle(&mine.y, ctx->sync_base) == cudaSuccess;
     cudaGetLastError();
     mine.ok = ok ? 1.0 : 0.0;
     Handles* d_all = nullptr;
@@ -120,14 +193,19 @@ static int map_peers(fgb_ctx* ctx) {
     for (int q = 0; q < P; q++) ok = ok && all[q].ok == 1.0;
     if (ok) {
         for (int q = 0; q < P && ok; q++) {
-            if (q == me) { ctx->peer_xbuf[q] = ctx->xbuf; ctx->peer_sbuf[q] = ctx->sbuf; ctx->peer_halo[q] = ctx->halo_base; continue; }
-            void *px = nullptr, *psb = nullptr, *ph = nullptr;
+            if (q == me) {
+                ctx->peer_xbuf[q] = ctx->xbuf; ctx->peer_sbuf[q] = ctx->sbuf; ctx->peer_halo[q] = ctx->halo_base; ctx->peer_sync[q] = ctx->sync_base;
+                continue;
+            }
+            void *px = nullptr, *psb = nullptr, *ph = nullptr, *py = nullptr;
             ok = cudaIpcOpenMemHandle(&px, all[q].x, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess &&
                  cudaIpcOpenMemHandle(&psb, all[q].s, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess &&
-                 cudaIpcOpenMemHandle(&ph, all[q].h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+                 cudaIpcOpenMemHandle(&ph, all[q].h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess &&
+                 cudaIpcOpenMemHandle(&py, all[q].y, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
             ctx->peer_xbuf[q] = (double*)px;
             ctx->peer_sbuf[q] = (double*)psb;
             ctx->peer_halo[q] = (double*)ph;
+            ctx->peer_sync[q] = (unsigned long long*)py;
         }
         cudaGetLastError();
     }
@@ -177,6 +255,9 @@ extern "C" int fgb_comm_init(fgb_ctx* ctx, const void* id128) {
     ctx->halo_seq = ctx->iso_seq = 0;
     ctx->phi_halo_valid = false;
     FGB_CUDA(ctx, cudaMalloc(&ctx->d_gather, sizeof(double) * 64 * ctx->nranks));
+    FGB_CUDA(ctx, cudaMalloc(&ctx->sync_base, FGB_SYNC_BYTES));
+    FGB_CUDA(ctx, cudaMemset(ctx->sync_base, 0, FGB_SYNC_BYTES));
+    ctx->bar_seq = ctx->ex_seq = 0;
     // transposition buffers are allocated once (their addresses are exported to the peers)
     // sized for the scheme's own operator and for the staggered-grid operators that get_raw_field("u") applies on every context
     // (fg:15517-15557): max(dim*nzc, udim*unzcs) complex numbers per row of the slab
@@ -196,11 +277,14 @@ int fgb_comm_free(fgb_ctx* ctx) {
                 if (ctx->peer_xbuf[q]) cudaIpcCloseMemHandle(ctx->peer_xbuf[q]);
                 if (ctx->peer_sbuf[q]) cudaIpcCloseMemHandle(ctx->peer_sbuf[q]);
                 if (ctx->peer_halo[q]) cudaIpcCloseMemHandle(ctx->peer_halo[q]);
+                if (ctx->peer_sync[q]) cudaIpcCloseMemHandle(ctx->peer_sync[q]);
             }
     ctx->p2p = false;
     if (ctx->sbuf) cudaFree(ctx->sbuf);
     if (ctx->xbuf) cudaFree(ctx->xbuf);
     if (ctx->halo_base) cudaFree(ctx->halo_base);
+    if (ctx->sync_base) cudaFree(ctx->sync_base);
+    ctx->sync_base = nullptr;
     ctx->halo_base = ctx->iso_halo = nullptr;
     if (ctx->d_gather) cudaFree(ctx->d_gather);
     ctx->sbuf = ctx->xbuf = ctx->halo = ctx->d_gather = nullptr;
@@ -403,7 +487,9 @@ int fgb_allreduce_host(fgb_ctx* ctx, double* vals, int n, int op) {
     if (n > 64) return fgb_fail(ctx, FGB_EINVAL, "too many reduction values");
     ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
     // d_result still holds this rank's n values (fgb_reduce_finish wrote them); gather all ranks' vectors
-    FGB_NCCL(ctx, g_nccl.AllGather(ctx->d_result, ctx->d_gather, (size_t)n, ncclDouble, comm, ctx->stream));
+    if (use_peer_sync(ctx) && n <= 8) {
+        if ((rc = fgb_allgather_dev(ctx, n))) return rc;
+    } else FGB_NCCL(ctx, g_nccl.AllGather(ctx->d_result, ctx->d_gather, (size_t)n, ncclDouble, comm, ctx->stream));
     std::vector<double> all((size_t)n * ctx->nranks);
     FGB_CUDA(ctx, cudaMemcpyAsync(all.data(), ctx->d_gather, sizeof(double) * all.size(), cudaMemcpyDeviceToHost, ctx->stream));
     FGB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -421,6 +507,13 @@ int fgb_allreduce_host(fgb_ctx* ctx, double* vals, int n, int op) {
 int fgb_allgather_dev(fgb_ctx* ctx, int n) {
     int rc = need_comm(ctx);
     if (rc) return rc;
+    if (use_peer_sync(ctx) && n <= 8) {
+        SyncPeers P;
+        for (int q = 0; q < 8; q++) P.p[q] = ctx->peer_sync[q];
+        k_peer_allgather<<<1, 32, 0, ctx->stream>>>(P, ctx->rank, ctx->nranks, ++ctx->ex_seq, ctx->d_result, n, ctx->d_gather, ctx->d_flag);
+        FGB_CHECK_LAUNCH(ctx, "k_peer_allgather");
+        return FGB_OK;
+    }
     FGB_NCCL(ctx, g_nccl.AllGather(ctx->d_result, ctx->d_gather, (size_t)n, ncclDouble, (ncclComm_t)ctx->nccl_comm, ctx->stream));
     return FGB_OK;
 }

@@ -548,6 +548,12 @@ int fgb_fft_strided(fgb_ctx* ctx, int axis, const double* src_, double* dst_, co
         FGB_CHECK_LAUNCH(ctx, "k_ffts_p3");
         return FGB_OK;
     }
+    // 1024 with stores into peer memory: 8-lane tiles (128-byte segments over NVLink); the two-pass kernel only fits 4 lanes
+    if (n == 1024 && pt.n > 0 && !no_p3) {
+        launch_s_p3<16, 8, 8, 8>(ctx, src, dst, tw, mi, mo, ninner, nouter, ncomp, dir, pt);
+        FGB_CHECK_LAUNCH(ctx, "k_ffts_p3");
+        return FGB_OK;
+    }
     if (is_fast_pow2(n)) {
         switch (n) {
             case 64: launch_s_p2<64, 8, 8, 8>(ctx, src, dst, tw, mi, mo, ninner, nouter, ncomp, dir, pt); break;
@@ -620,6 +626,7 @@ int fgb_fft_x_green_layout(fgb_ctx* ctx, double* base, const GreenArgs* ga, long
         case 6: return fgb_xg_g0div9(ctx, b, G, estride, nzc_valid, nouter, ostride, cstride, jbase, xo, pt);
         case 7: return fgb_xg_grad9(ctx, b, G, estride, nzc_valid, nouter, ostride, cstride, jbase, xo, pt);
         case 8: return fgb_xg_willot6(ctx, b, G, estride, nzc_valid, nouter, ostride, cstride, jbase, xo, pt);
+        case 11: return fgb_xg_gradg0div9(ctx, b, G, estride, nzc_valid, nouter, ostride, cstride, jbase, xo, pt);
         case 10: return fgb_xg_poisson1(ctx, b, G, estride, nzc_valid, nouter, ostride, cstride, jbase, xo, pt);
         case 9: return fgb_xg_colloc6_zt(ctx, b, G, estride, nzc_valid, nouter, ostride, cstride, jbase, xo, pt);
     }

@@ -460,6 +460,12 @@ __device__ __forceinline__ void green_apply(const GreenDev& G, int ii, int jj, i
     if (KIND == 6) green_g0div_hyper(G, ii, jj, kk, f);
     if (KIND == 7) green_grad_hyper(G, ii, jj, kk, f);
     if (KIND == 8) green_willot(G, ii, jj, kk, f);
+    if (KIND == 11) {
+        // G0DivOperatorFourierHyper followed by GradOperatorFourierHyper without leaving Fourier space (the sequence of the
+        // reference's "GammaHyper identity" test, fg:24573-24574)
+        green_g0div_hyper(G, ii, jj, kk, f);
+        green_grad_hyper(G, ii, jj, kk, f);
+    }
     if (KIND == 10) {
         // poisson_solve fg:23454-23493: u^ = f^ / (2 sum_a (n_a/L_a)^2 (cos(2 pi i_a/n_a) - 1)); the reference folds the 1/nxyz of its
         // unscaled forward transform into the same divisor, here the forward pass has already applied it

@@ -33,6 +33,7 @@ int fgb_xg_colloc3(FGB_XG_ARGS);          // kind 4
 int fgb_xg_colloc9(FGB_XG_ARGS);          // kind 5
 int fgb_xg_g0div9(FGB_XG_ARGS);           // kind 6: G0DivOperatorFourierHyper
 int fgb_xg_grad9(FGB_XG_ARGS);            // kind 7: GradOperatorFourierHyper
+int fgb_xg_gradg0div9(FGB_XG_ARGS);       // kind 11: GradOperatorFourierHyper o G0DivOperatorFourierHyper
 int fgb_xg_willot6(FGB_XG_ARGS);          // kind 8: GammaOperatorFourierWillotR
 int fgb_xg_colloc6_zt(FGB_XG_ARGS);       // kind 9: collocated elasticity operator on the zero-trace representation (viscosity)
 cudaError_t fgb_w32_set_xg1(const double2*);

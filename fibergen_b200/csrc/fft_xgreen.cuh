@@ -265,12 +265,15 @@ static int launch_x_green(fgb_ctx* ctx, double2* base, const GreenDev& G, long e
     constexpr int MB = (NC <= 3 ? 2 : 1);
     if (!no_p3) {
 #define XG3(R1, R2, R3, T) rc = launch_xg_p3<R1, R2, R3, NC, KIND, T, MB>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt)
-        // FGB_XG_P3_T8 (not validated on hardware yet, off by default): 8-lane tiles = 128-byte segments for the nx = 512 pass
-        // when it stores to peer memory; the 4-lane tile's 64-byte stores reach only ~430 GB/s over NVLink at 8 GPUs
-        static const bool t8_peer = getenv("FGB_XG_P3_T8") != nullptr;
+        // stores into peer memory (slab partition): wider tiles so that a row segment is 128 bytes (nx = 512) or 64 bytes (nx = 1024)
+        // instead of 64 / 32; over NVLink the segment size decides the achieved bandwidth (4-lane tiles reached ~430 GB/s at 8 GPUs).
+        // FGB_XG_NARROW_PEER selects the single-GPU tile shapes for comparison.
+        static const bool narrow = getenv("FGB_XG_NARROW_PEER") != nullptr;
         if constexpr (NC <= 3) {
-            if (nx == 512 && t8_peer && pt.n > 0)
-                rc = launch_xg_p3<8, 8, 8, NC, KIND, 8, 1>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt);
+            if (pt.n > 0 && !narrow) {
+                if (nx == 512) rc = launch_xg_p3<8, 8, 8, NC, KIND, 8, 1>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt);
+                else if (nx == 1024) rc = launch_xg_p3<16, 8, 8, NC, KIND, 4, 1>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt);
+            }
         }
         if (rc != -1) return rc;
         if (nx == 512) XG3(8, 8, 8, 4);

@@ -121,6 +121,9 @@ struct fgb_ctx {
     size_t iso_set;               // doubles per iso-halo set
     unsigned halo_seq, iso_seq;   // exchange counters (set = seq & 1)
     double* peer_sbuf[8];
+    unsigned long long* sync_base;      // barrier / scalar-exchange block of this rank (comm.cu), mapped by every peer
+    unsigned long long* peer_sync[8];
+    unsigned long long bar_seq, ex_seq;
 
     // mixed boundary conditions (fgb_set_bc): row-major dim x dim matrices MQ and M:(QC0)
     bool bc_active;

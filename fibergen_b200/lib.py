@@ -69,6 +69,7 @@ PROTOTYPES = {
     "fgb_calc_displacement": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double]),
     "fgb_g0div_hyper": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double]),
     "fgb_grad_hyper": (C.c_int, [C.c_void_p, C.c_int]),
+    "fgb_grad_g0div_hyper": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double]),
     "fgb_calc_pressure": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double]),
     "fgb_extrapolate_polynomial": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), c_dp, c_dp, C.c_int]),
     "fgb_ref_material": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_dp, c_dp]),

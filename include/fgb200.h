@@ -195,6 +195,9 @@ int  fgb_calc_displacement(fgb_ctx* ctx, int eps, int tmp, double mu0, double la
 int  fgb_g0div_hyper(fgb_ctx* ctx, int field, double mu0, double lambda0, double alpha);
 /* fftTensor, GradOperatorFourierHyper fg:22069-22116, fftInvTensor: components 0..2 hold a vector field q, all 9 receive grad q */
 int  fgb_grad_hyper(fgb_ctx* ctx, int field);
+/* fftTensor, G0DivOperatorFourierHyper, GradOperatorFourierHyper, fftInvTensor (fg:24572-24575): field <- alpha * grad G0 Div field,
+ * both operators applied in Fourier space (no real-space round trip in between, which would drop the imaginary Nyquist parts) */
+int  fgb_grad_g0div_hyper(fgb_ctx* ctx, int field, double mu0, double lambda0, double alpha);
 /* get_raw_field("p") fg:15559-15573 (calcStressDiff, divOperatorStaggered, divVector fg:19983, poisson_solve fg:23454): the pressure
  * is left in component 0 of the u buffer (fgb_u_download with ncomp = 1); tmp is a scratch field */
 int  fgb_calc_pressure(fgb_ctx* ctx, int eps, int tmp, double mu0, double lambda0);
