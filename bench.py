@@ -327,15 +327,18 @@ def run_cuda(args):
         nvlink = {"bytes_sent_per_gpu_per_iteration": sent, "transposing_kernels_ms_per_iteration": tt,
                   "achieved_gbs_per_direction": (sent / (tt * 1e-3) / 1e9) if tt > 0 else None,
                   "note": "time of the two kernels that store into peer memory (forward y pass, fused x pass); peak 900 GB/s per direction"}
-    # phase fractions back to the host for the end-to-end leg and the parity check (pinned staging)
+    # phase fractions back to the host for the end-to-end leg and the parity check (pinned staging); not at strong-scaling sizes
     nzp = fb.nzp_of(n[2])
     nph = len(w["materials"])
-    host_phi = torch.empty((nph, lnx, n[1], nzp), dtype=torch.float64).pin_memory()
-    hp = host_phi.numpy()
-    for m in range(nph):
-        hp[m] = s.get_phase(m, padded=True)
-    hp[:, :, :, n[2]:] = 0
-    vf = float(hp[1, :, :, :n[2]].mean())
+    need_host_phi = not strong and (not args.no_e2e or (world == 1 and not args.no_cpu_baseline and cfg == "c2"))
+    vf = None
+    if need_host_phi:
+        host_phi = torch.empty((nph, lnx, n[1], nzp), dtype=torch.float64).pin_memory()
+        hp = host_phi.numpy()
+        for m in range(nph):
+            hp[m] = s.get_phase(m, padded=True)
+        hp[:, :, :, n[2]:] = 0
+        vf = float(hp[1, :, :, :n[2]].mean())
     s.set_convergence_callback(None)
     strong_out = None
     if strong:
