@@ -141,6 +141,8 @@ extern "C" int fgb_create(fgb_ctx** out, int nx, int ny, int nz, double Lx, doub
     for (int i = 0; i < FGB_CG_RING; i++) c->ring_ev[i] = nullptr;
     c->nccl_comm = nullptr; c->nccl_lib = nullptr; c->sbuf = nullptr; c->xbuf = nullptr; c->xbuf_cap = 0;
     c->halo = nullptr; c->halo_slot = 0; c->d_gather = nullptr; c->visc_tmp = nullptr; c->p2p = false; c->iso_halo = nullptr; c->phi_halo_valid = false;
+    c->dfg = 0; c->dfg1 = c->dfg2 = nullptr; c->normals_f = c->orient_f = nullptr;
+    for (int i = 0; i < FGB_MAX_PHASES; i++) c->phi_f[i] = nullptr;
     c->halo_base = nullptr; c->iso_set = 0; c->halo_seq = c->iso_seq = 0;
     c->sync_base = nullptr; c->bar_seq = c->ex_seq = 0;
     for (int q = 0; q < 8; q++) c->peer_sync[q] = nullptr;
@@ -196,6 +198,11 @@ extern "C" void fgb_destroy(fgb_ctx* c) {
     if (c->visc_tmp) cudaFree(c->visc_tmp);
     if (c->normals) cudaFree(c->normals);
     if (c->orient) cudaFree(c->orient);
+    for (int i = 0; i < FGB_MAX_PHASES; i++) if (c->phi_f[i]) cudaFree(c->phi_f[i]);
+    if (c->dfg1) cudaFree(c->dfg1);
+    if (c->dfg2) cudaFree(c->dfg2);
+    if (c->normals_f) cudaFree(c->normals_f);
+    if (c->orient_f) cudaFree(c->orient_f);
     fgb_fft_free(c);
     if (c->d_partials) cudaFree(c->d_partials);
     if (c->d_result) cudaFree(c->d_result);
@@ -296,14 +303,37 @@ extern "C" int fgb_set_num_phases(fgb_ctx* c, int n) {
     return FGB_OK;
 }
 
-static int upload_planes(fgb_ctx* c, double** dst, const double* const* comps, int n) {
+static int upload_planes(fgb_ctx* c, double** dst, const double* const* comps, int n, size_t plane) {
     if (!*dst) {
-        cudaError_t e = cudaMalloc(dst, sizeof(double) * c->g.plane * n);
+        cudaError_t e = cudaMalloc(dst, sizeof(double) * plane * n);
         if (e != cudaSuccess) { *dst = nullptr; return fgb_fail(c, FGB_ENOMEM, "device allocation failed: %s", cudaGetErrorString(e)); }
     }
     for (int d = 0; d < n; d++)
-        FGB_CUDA(c, cudaMemcpyAsync(*dst + (size_t)d * c->g.plane, comps[d], sizeof(double) * c->g.plane, cudaMemcpyHostToDevice, c->stream));
+        FGB_CUDA(c, cudaMemcpyAsync(*dst + (size_t)d * plane, comps[d], sizeof(double) * plane, cudaMemcpyHostToDevice, c->stream));
     FGB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return FGB_OK;
+}
+
+// use_dfg (fg:14894-14897): the half_staggered / full_staggered schemes evaluate the material on a doubly fine grid
+extern "C" int fgb_set_dfg(fgb_ctx* c, int mode) {
+    CHECK_CTX(c);
+    if (mode < 0 || mode > 2) return fgb_fail(c, FGB_EINVAL, "dfg mode %d (0 off, 1 half_staggered, 2 full_staggered)", mode);
+    if (mode && c->scheme != FGB_GAMMA_STAGGERED) return fgb_fail(c, FGB_EINVAL, "the doubly fine grid belongs to the staggered scheme");
+    if (mode && c->nranks > 1) return fgb_fail(c, FGB_EUNSUPPORTED, "half_staggered / full_staggered are single-GPU in this build");
+    c->dfg = mode;
+    if (!mode) return FGB_OK;
+    GridDev& f = c->gf;
+    f = c->g;
+    f.nx = 2 * c->g.nx; f.ny = 2 * c->g.ny; f.nz = 2 * c->g.nz;
+    f.lnx = 2 * c->g.lnx; f.x0 = 2 * c->g.x0;
+    f.nzc = f.nz / 2 + 1;
+    f.nzp = 2 * f.nzc;
+    f.plane = (size_t)f.lnx * f.ny * f.nzp;
+    f.hx = f.nx / c->L[0]; f.hy = f.ny / c->L[1]; f.hz = f.nz / c->L[2];
+    if (!c->dfg1) {
+        cudaError_t e = cudaMalloc(&c->dfg1, sizeof(double) * f.plane * c->dim);                     // _temp_dfg_1 fg:15145-15147
+        if (e != cudaSuccess) { c->dfg1 = nullptr; return fgb_fail(c, FGB_ENOMEM, "cannot allocate the doubly fine grid (%zu doubles per component)", f.plane); }
+    }
     return FGB_OK;
 }
 
@@ -312,7 +342,28 @@ extern "C" int fgb_set_phase(fgb_ctx* c, int p, const double* phi) {
     if (p < 0 || p >= c->nphases) return fgb_fail(c, FGB_EINVAL, "phase index %d out of range", p);
     const double* comps[1] = {phi};
     c->phi_halo_valid = false;
-    return upload_planes(c, &c->phi[p], comps, 1);
+    if (c->dfg == 2) return upload_planes(c, &c->phi_f[p], comps, 1, c->gf.plane);                    // full_staggered: phases live on the fine grid (fg:17154-17156)
+    int rc = upload_planes(c, &c->phi[p], comps, 1, c->g.plane);
+    if (rc || c->dfg != 1) return rc;
+    // half_staggered: the fine-grid phase is the piecewise constant continuation of the coarse one (initFullStageredRawPhases fg:17648)
+    if (!c->phi_f[p]) {
+        cudaError_t e = cudaMalloc(&c->phi_f[p], sizeof(double) * c->gf.plane);
+        if (e != cudaSuccess) { c->phi_f[p] = nullptr; return fgb_fail(c, FGB_ENOMEM, "device allocation failed: %s", cudaGetErrorString(e)); }
+        FGB_CUDA(c, cudaMemsetAsync(c->phi_f[p], 0, sizeof(double) * c->gf.plane, c->stream));
+    }
+    return fgb_k_inject_phase(c, c->phi[p], c->phi_f[p]);
+}
+
+// prolongate_to_dfg fg:14216 / restrict_from_dfg fg:14273 between a field and _temp_dfg_1 (reference self-test fg:24491-24515)
+extern "C" int fgb_dfg_prolongate(fgb_ctx* c, int f) {
+    CHECK_CTX(c); CHECK_FIELD(c, f);
+    if (!c->dfg) return fgb_fail(c, FGB_EINVAL, "the doubly fine grid is not enabled (fgb_set_dfg)");
+    return fgb_k_prolongate(c, c->fields[f], c->dfg1);
+}
+extern "C" int fgb_dfg_restrict(fgb_ctx* c, int f) {
+    CHECK_CTX(c); CHECK_FIELD(c, f);
+    if (!c->dfg) return fgb_fail(c, FGB_EINVAL, "the doubly fine grid is not enabled (fgb_set_dfg)");
+    return fgb_k_restrict(c, c->dfg1, c->fields[f]);
 }
 
 extern "C" int fgb_set_law(fgb_ctx* c, int p, int law_id, const double* params, int nparams) {
@@ -331,13 +382,16 @@ extern "C" int fgb_set_law(fgb_ctx* c, int p, int law_id, const double* params, 
     return FGB_OK;
 }
 
+// with the doubly fine grid the normals / orientation live on the fine grid (get_normals / get_orientation fg:14911-14937)
 extern "C" int fgb_set_normals(fgb_ctx* c, const double* const* comps3) {
     CHECK_CTX(c);
-    return upload_planes(c, &c->normals, comps3, 3);
+    if (c->dfg) return upload_planes(c, &c->normals_f, comps3, 3, c->gf.plane);
+    return upload_planes(c, &c->normals, comps3, 3, c->g.plane);
 }
 extern "C" int fgb_set_orientation(fgb_ctx* c, const double* const* comps3) {
     CHECK_CTX(c);
-    return upload_planes(c, &c->orient, comps3, 3);
+    if (c->dfg) return upload_planes(c, &c->orient_f, comps3, 3, c->gf.plane);
+    return upload_planes(c, &c->orient, comps3, 3, c->g.plane);
 }
 
 extern "C" int fgb_set_mixing(fgb_ctx* c, int rule, const double* lp, int n) {

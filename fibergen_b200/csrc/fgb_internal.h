@@ -132,6 +132,16 @@ struct fgb_ctx {
     double F00[9];
     double* visc_tmp;           // copy of tau for the viscosity Delta operator (fg:21316-21320)
 
+    // doubly fine grid of the half_staggered / full_staggered schemes (use_dfg fg:14894): the constitutive sweeps run on a grid
+    // with twice the resolution; fields are prolongated before and restricted after (fg:14216-14339, fg:18143-18149, fg:18343-18347)
+    int dfg;                    // 0 off, 1 half_staggered (fine phases injected from the coarse grid), 2 full_staggered
+    GridDev gf;                 // the fine grid (2nx, 2ny, 2nz)
+    double* dfg1;               // _temp_dfg_1: dim fine planes
+    double* dfg2;               // _temp_dfg_2 (tangent sweeps)
+    double* phi_f[FGB_MAX_PHASES];
+    double* normals_f;
+    double* orient_f;
+
     uint64_t launches;
     bool profiling;
     std::map<std::string, ProfEntry> prof;
@@ -215,6 +225,9 @@ int fgb_fft_x_green_layout(fgb_ctx* ctx, double* base, const GreenArgs* ga, long
 int fgb_k_div(fgb_ctx* ctx, const double* tau, double* u);
 int fgb_k_eps(fgb_ctx* ctx, const double* u, double* eta, const double* Econst /*dim, host*/);
 int fgb_k_div_vector(fgb_ctx* ctx, const double* u, double* b, double alpha);   // divVector fg:19983: 3-component u buffer -> one component (u layout)
+int fgb_k_prolongate(fgb_ctx* ctx, const double* coarse, double* fine);          // prolongate_to_dfg fg:14216
+int fgb_k_restrict(fgb_ctx* ctx, const double* fine, double* coarse);            // restrict_from_dfg fg:14273
+int fgb_k_inject_phase(fgb_ctx* ctx, const double* coarse, double* fine);        // initFullStageredRawPhases fg:17648-17680
 int fgb_k_mxpy(fgb_ctx* ctx, double* r, const double* x, const double* y);        // mxpyTensor fg:20590 on one component plane
 
 // material.cu --------------------------------------------------------------------------------

@@ -500,7 +500,7 @@ __global__ void __launch_bounds__(256) k_eps_dot6(const double* __restrict__ u, 
 // returns 1 if the fused path applies to this context (D = 6 elasticity, staggered, Voigt, all phases isotropic, one rank)
 int fgb_fused_iso_applicable(const fgb_ctx* ctx) {
     if (ctx->dim != 6 || ctx->mode != FGB_MODE_ELASTICITY || ctx->scheme != FGB_GAMMA_STAGGERED) return 0;
-    if (ctx->mix != FGB_MIX_VOIGT || ctx->nphases < 1) return 0;
+    if (ctx->mix != FGB_MIX_VOIGT || ctx->nphases < 1 || ctx->dfg) return 0;
     if (ctx->nranks > 1 && (ctx->nphases > 3 || !ctx->nccl_comm || getenv("FGB_NO_MARCH"))) return 0;   // slab runs need the marching kernel
     for (int p = 0; p < ctx->nphases; p++)
         if (ctx->laws[p].id != FGB_LAW_ISO || !ctx->phi[p]) return 0;

@@ -376,7 +376,8 @@ void LSSolver::init() {
     if (_gamma_scheme == "collocated") scheme = FGB_GAMMA_COLLOCATED;
     else if (_gamma_scheme == "staggered") scheme = FGB_GAMMA_STAGGERED;
     else if (_gamma_scheme == "willot") scheme = FGB_GAMMA_WILLOT;
-    else { fail("Unknown gamma scheme '" + _gamma_scheme + "' (this build provides collocated, staggered and willot)"); return; }
+    else if (_gamma_scheme == "half_staggered" || _gamma_scheme == "full_staggered") scheme = FGB_GAMMA_STAGGERED;   // fg:20480, fg:20496
+    else { fail("Unknown gamma scheme '" + _gamma_scheme + "' (this build provides collocated, staggered, half_staggered, full_staggered and willot)"); return; }
     if (_loadstep_extrapolation_method != "polynomial")
         fail("Unknown loadstep extrapolation method '" + _loadstep_extrapolation_method + "' (this build provides polynomial)");
     if (_G0_solver != "fft") fail("Unknown G0-solver '" + _G0_solver + "' (multigrid is not provided)");
@@ -388,6 +389,8 @@ void LSSolver::init() {
     if (rc) fail(std::string(fgb_last_error(nullptr)));
     _dim = fgb_dim(_ctx);
     _epsilon = _f1 = _f2 = _f3 = _f4 = _f5 = -1;
+    if (_gamma_scheme == "half_staggered") check(fgb_set_dfg(_ctx, 1));
+    else if (_gamma_scheme == "full_staggered") check(fgb_set_dfg(_ctx, 2));
 
     if (_materials.empty()) fail("No materials specified");                               // fg:15306
     check(fgb_set_num_phases(_ctx, (int)_materials.size()));

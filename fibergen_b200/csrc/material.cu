@@ -20,16 +20,54 @@ MaterialDev fgb_material_dev(fgb_ctx* ctx) {
     memset(&M, 0, sizeof(M));
     M.nphases = ctx->nphases;
     M.mix = ctx->mix;
+    // select_dfg (fg:18146): with the doubly fine grid the phase data of the fine grid is used
+    const bool f = ctx->dfg != 0;
+    const double* normals = f ? ctx->normals_f : ctx->normals;
+    const double* orient = f ? ctx->orient_f : ctx->orient;
+    const size_t plane = f ? ctx->gf.plane : ctx->g.plane;
     for (int p = 0; p < ctx->nphases; p++) {
-        M.phi[p] = ctx->phi[p];
+        M.phi[p] = f ? ctx->phi_f[p] : ctx->phi[p];
         M.law[p] = ctx->laws[p];
     }
     for (int a = 0; a < 3; a++) {
-        M.normals[a] = ctx->normals ? ctx->normals + (size_t)a * ctx->g.plane : nullptr;
-        M.orient[a] = ctx->orient ? ctx->orient + (size_t)a * ctx->g.plane : nullptr;
+        M.normals[a] = normals ? normals + (size_t)a * plane : nullptr;
+        M.orient[a] = orient ? orient + (size_t)a * plane : nullptr;
     }
     M.lam = ctx->lam;
     return M;
+}
+
+// The grid a constitutive sweep runs on.  With the doubly fine grid (half_staggered / full_staggered) the operands are prolongated
+// into _temp_dfg_1 / _temp_dfg_2, the sweep runs in place on the fine grid and the result is restricted (fg:18143-18149, 18343-18347).
+struct SweepGrid {
+    GridDev g;
+    const double* a;      // first operand
+    const double* b;      // second operand (tangent sweeps) or null
+    double* out;          // where the kernel writes
+    double* final_dst;    // coarse destination to restrict into (dfg) or null
+};
+static int sweep_begin(fgb_ctx* ctx, const double* a, const double* b, double* dst, SweepGrid& S) {
+    S.g = ctx->g; S.a = a; S.b = b; S.out = dst; S.final_dst = nullptr;
+    if (!ctx->dfg) return FGB_OK;
+    int rc;
+    if ((rc = fgb_k_prolongate(ctx, a, ctx->dfg1))) return rc;
+    S.a = ctx->dfg1;
+    if (b) {
+        if (!ctx->dfg2) {
+            cudaError_t e = cudaMalloc(&ctx->dfg2, sizeof(double) * ctx->gf.plane * ctx->dim);
+            if (e != cudaSuccess) { ctx->dfg2 = nullptr; return fgb_fail(ctx, FGB_ENOMEM, "cannot allocate the second doubly-fine-grid field"); }
+        }
+        if ((rc = fgb_k_prolongate(ctx, b, ctx->dfg2))) return rc;
+        S.b = ctx->dfg2;
+    }
+    S.g = ctx->gf;
+    S.out = ctx->dfg1;
+    S.final_dst = dst;
+    return FGB_OK;
+}
+static int sweep_end(fgb_ctx* ctx, const SweepGrid& S) {
+    if (S.final_dst) return fgb_k_restrict(ctx, S.out, S.final_dst);
+    return FGB_OK;
 }
 
 // 32-bit voxel index arithmetic (a slab never exceeds 2^32 voxels); 64-bit divisions were the bottleneck of v1
@@ -312,10 +350,10 @@ __global__ void __launch_bounds__(128) k_ref_material(const double* __restrict__
 static int check_material(fgb_ctx* ctx) {
     if (ctx->nphases < 1) return fgb_fail(ctx, FGB_EINVAL, "no materials specified");     // fg:15306
     for (int p = 0; p < ctx->nphases; p++)
-        if (!ctx->phi[p]) return fgb_fail(ctx, FGB_EINVAL, "phase %d has no volume fraction field", p);
-    if (ctx->mix == FGB_MIX_LAMINATE && !ctx->normals) return fgb_fail(ctx, FGB_EINVAL, "laminate mixing needs normals");
+        if (!(ctx->dfg ? ctx->phi_f[p] : ctx->phi[p])) return fgb_fail(ctx, FGB_EINVAL, "phase %d has no volume fraction field", p);
+    if (ctx->mix == FGB_MIX_LAMINATE && !(ctx->dfg ? ctx->normals_f : ctx->normals)) return fgb_fail(ctx, FGB_EINVAL, "laminate mixing needs normals");
     for (int p = 0; p < ctx->nphases; p++)
-        if (ctx->laws[p].id == FGB_LAW_TISO && !ctx->orient && ctx->laws[p].p[5] == 0 && ctx->laws[p].p[6] == 0 && ctx->laws[p].p[7] == 0)
+        if (ctx->laws[p].id == FGB_LAW_TISO && !(ctx->dfg ? ctx->orient_f : ctx->orient) && ctx->laws[p].p[5] == 0 && ctx->laws[p].p[6] == 0 && ctx->laws[p].p[7] == 0)
             return fgb_fail(ctx, FGB_EINVAL, "tiso law needs the orientation field or a constant axis");
     return FGB_OK;
 }
@@ -330,14 +368,16 @@ int fgb_k_calc_stress(fgb_ctx* ctx, const double* src, double* dst, double mu0, 
     if (rc) return rc;
     const double beta = -alpha * 2 * mu0, gamma = -alpha * lambda0;
     const MaterialDev M = fgb_material_dev(ctx);
-    const size_t nvox = (size_t)ctx->g.lnx * ctx->g.ny * ctx->g.nz;
+    SweepGrid S;
+    if ((rc = sweep_begin(ctx, src, nullptr, dst, S))) return rc;
+    const size_t nvox = (size_t)S.g.lnx * S.g.ny * S.g.nz;
     const unsigned grid = grid_for(ctx, nvox, 256);
     ProfScope ps(ctx, "calc_stress");
-    DISPATCH_D(ctx, (k_calc_stress<3, 0><<<grid, 256, 0, ctx->stream>>>(src, nullptr, dst, ctx->g, M, alpha, beta, gamma, ctx->d_flag)),
-               (k_calc_stress<6, 0><<<grid, 256, 0, ctx->stream>>>(src, nullptr, dst, ctx->g, M, alpha, beta, gamma, ctx->d_flag)),
-               (k_calc_stress<9, 0><<<grid, 256, 0, ctx->stream>>>(src, nullptr, dst, ctx->g, M, alpha, beta, gamma, ctx->d_flag)));
+    DISPATCH_D(ctx, (k_calc_stress<3, 0><<<grid, 256, 0, ctx->stream>>>(S.a, nullptr, S.out, S.g, M, alpha, beta, gamma, ctx->d_flag)),
+               (k_calc_stress<6, 0><<<grid, 256, 0, ctx->stream>>>(S.a, nullptr, S.out, S.g, M, alpha, beta, gamma, ctx->d_flag)),
+               (k_calc_stress<9, 0><<<grid, 256, 0, ctx->stream>>>(S.a, nullptr, S.out, S.g, M, alpha, beta, gamma, ctx->d_flag)));
     FGB_CHECK_LAUNCH(ctx, "k_calc_stress");
-    return check_flag(ctx);
+    return sweep_end(ctx, S);
 }
 
 int fgb_k_calc_stress_deriv(fgb_ctx* ctx, const double* F, const double* W, double* dst, double mu0, double lambda0, double alpha) {
@@ -345,43 +385,49 @@ int fgb_k_calc_stress_deriv(fgb_ctx* ctx, const double* F, const double* W, doub
     if (rc) return rc;
     const double beta = -alpha * 2 * mu0, gamma = -alpha * lambda0;
     const MaterialDev M = fgb_material_dev(ctx);
-    const size_t nvox = (size_t)ctx->g.lnx * ctx->g.ny * ctx->g.nz;
+    SweepGrid S;
+    if ((rc = sweep_begin(ctx, F, W, dst, S))) return rc;
+    const size_t nvox = (size_t)S.g.lnx * S.g.ny * S.g.nz;
     const unsigned grid = grid_for(ctx, nvox, 256);
     ProfScope ps(ctx, "calc_stress_deriv");
-    DISPATCH_D(ctx, (k_calc_stress<3, 1><<<grid, 256, 0, ctx->stream>>>(F, W, dst, ctx->g, M, alpha, beta, gamma, ctx->d_flag)),
-               (k_calc_stress<6, 1><<<grid, 256, 0, ctx->stream>>>(F, W, dst, ctx->g, M, alpha, beta, gamma, ctx->d_flag)),
-               (k_calc_stress<9, 1><<<grid, 256, 0, ctx->stream>>>(F, W, dst, ctx->g, M, alpha, beta, gamma, ctx->d_flag)));
+    DISPATCH_D(ctx, (k_calc_stress<3, 1><<<grid, 256, 0, ctx->stream>>>(S.a, S.b, S.out, S.g, M, alpha, beta, gamma, ctx->d_flag)),
+               (k_calc_stress<6, 1><<<grid, 256, 0, ctx->stream>>>(S.a, S.b, S.out, S.g, M, alpha, beta, gamma, ctx->d_flag)),
+               (k_calc_stress<9, 1><<<grid, 256, 0, ctx->stream>>>(S.a, S.b, S.out, S.g, M, alpha, beta, gamma, ctx->d_flag)));
     FGB_CHECK_LAUNCH(ctx, "k_calc_stress_deriv");
-    return FGB_OK;
+    return sweep_end(ctx, S);
 }
 
 int fgb_k_calc_polarization(fgb_ctx* ctx, const double* src, double* dst, double mu0, int inv) {
     int rc = check_material(ctx);
     if (rc) return rc;
     const MaterialDev M = fgb_material_dev(ctx);
-    const size_t nvox = (size_t)ctx->g.lnx * ctx->g.ny * ctx->g.nz;
+    SweepGrid S;
+    if ((rc = sweep_begin(ctx, src, nullptr, dst, S))) return rc;
+    const size_t nvox = (size_t)S.g.lnx * S.g.ny * S.g.nz;
     const unsigned grid = grid_for(ctx, nvox, 128);
     ProfScope ps(ctx, "calc_polarization");
-    DISPATCH_D(ctx, (k_calc_polarization<3><<<grid, 128, 0, ctx->stream>>>(src, dst, ctx->g, M, mu0, inv, ctx->d_flag)),
-               (k_calc_polarization<6><<<grid, 128, 0, ctx->stream>>>(src, dst, ctx->g, M, mu0, inv, ctx->d_flag)),
-               (k_calc_polarization<9><<<grid, 128, 0, ctx->stream>>>(src, dst, ctx->g, M, mu0, inv, ctx->d_flag)));
+    DISPATCH_D(ctx, (k_calc_polarization<3><<<grid, 128, 0, ctx->stream>>>(S.a, S.out, S.g, M, mu0, inv, ctx->d_flag)),
+               (k_calc_polarization<6><<<grid, 128, 0, ctx->stream>>>(S.a, S.out, S.g, M, mu0, inv, ctx->d_flag)),
+               (k_calc_polarization<9><<<grid, 128, 0, ctx->stream>>>(S.a, S.out, S.g, M, mu0, inv, ctx->d_flag)));
     FGB_CHECK_LAUNCH(ctx, "k_calc_polarization");
-    return FGB_OK;
+    return sweep_end(ctx, S);
 }
 
 int fgb_k_mean_pk1(fgb_ctx* ctx, const double* src, double alpha, double* out) {
     int rc = check_material(ctx);
     if (rc) return rc;
     const MaterialDev M = fgb_material_dev(ctx);
-    const size_t nvox = (size_t)ctx->g.lnx * ctx->g.ny * ctx->g.nz;
-    const double nxyz = (double)ctx->g.nx * ctx->g.ny * ctx->g.nz;
+    SweepGrid S;
+    if ((rc = sweep_begin(ctx, src, nullptr, nullptr, S))) return rc;
+    const size_t nvox = (size_t)S.g.lnx * S.g.ny * S.g.nz;
+    const double nxyz = (double)S.g.nx * S.g.ny * S.g.nz;
     const double a = alpha / nxyz;                                     // fg:12318
     const unsigned grid = grid_for(ctx, nvox, 256);
     {
         ProfScope ps(ctx, "mean_pk1");
-        DISPATCH_D(ctx, (k_mean_pk1<3><<<grid, 256, 0, ctx->stream>>>(src, ctx->g, M, a, ctx->d_partials, ctx->d_flag)),
-                   (k_mean_pk1<6><<<grid, 256, 0, ctx->stream>>>(src, ctx->g, M, a, ctx->d_partials, ctx->d_flag)),
-                   (k_mean_pk1<9><<<grid, 256, 0, ctx->stream>>>(src, ctx->g, M, a, ctx->d_partials, ctx->d_flag)));
+        DISPATCH_D(ctx, (k_mean_pk1<3><<<grid, 256, 0, ctx->stream>>>(S.a, S.g, M, a, ctx->d_partials, ctx->d_flag)),
+                   (k_mean_pk1<6><<<grid, 256, 0, ctx->stream>>>(S.a, S.g, M, a, ctx->d_partials, ctx->d_flag)),
+                   (k_mean_pk1<9><<<grid, 256, 0, ctx->stream>>>(S.a, S.g, M, a, ctx->d_partials, ctx->d_flag)));
         FGB_CHECK_LAUNCH(ctx, "k_mean_pk1");
     }
     return fgb_reduce_finish(ctx, grid, ctx->dim, 0, out);
@@ -392,12 +438,14 @@ int fgb_k_mean_cauchy(fgb_ctx* ctx, const double* src, double alpha, double* out
     if (rc) return rc;
     if (ctx->dim != 9) return fgb_fail(ctx, FGB_EINVAL, "the Cauchy stress needs the 9-component deformation gradient (hyperelasticity)");
     const MaterialDev M = fgb_material_dev(ctx);
-    const size_t nvox = (size_t)ctx->g.lnx * ctx->g.ny * ctx->g.nz;
-    const double a = alpha / ((double)ctx->g.nx * ctx->g.ny * ctx->g.nz);               // fg:12274
+    SweepGrid S;
+    if ((rc = sweep_begin(ctx, src, nullptr, nullptr, S))) return rc;
+    const size_t nvox = (size_t)S.g.lnx * S.g.ny * S.g.nz;
+    const double a = alpha / ((double)S.g.nx * S.g.ny * S.g.nz);               // fg:12274
     const unsigned grid = grid_for(ctx, nvox, 256);
     {
         ProfScope ps(ctx, "mean_cauchy");
-        k_mean_cauchy<<<grid, 256, 0, ctx->stream>>>(src, ctx->g, M, a, ctx->d_partials, ctx->d_flag);
+        k_mean_cauchy<<<grid, 256, 0, ctx->stream>>>(S.a, S.g, M, a, ctx->d_partials, ctx->d_flag);
         FGB_CHECK_LAUNCH(ctx, "k_mean_cauchy");
     }
     return fgb_reduce_finish(ctx, grid, 9, 0, out);
@@ -407,26 +455,31 @@ int fgb_k_mean_energy(fgb_ctx* ctx, const double* src, double* out) {
     int rc = check_material(ctx);
     if (rc) return rc;
     const MaterialDev M = fgb_material_dev(ctx);
-    const size_t nvox = (size_t)ctx->g.lnx * ctx->g.ny * ctx->g.nz;
+    SweepGrid S;
+    if ((rc = sweep_begin(ctx, src, nullptr, nullptr, S))) return rc;
+    const size_t nvox = (size_t)S.g.lnx * S.g.ny * S.g.nz;
     const unsigned grid = grid_for(ctx, nvox, 256);
     {
         ProfScope ps(ctx, "mean_energy");
-        DISPATCH_D(ctx, (k_mean_energy<3><<<grid, 256, 0, ctx->stream>>>(src, ctx->g, M, ctx->d_partials, ctx->d_flag)),
-                   (k_mean_energy<6><<<grid, 256, 0, ctx->stream>>>(src, ctx->g, M, ctx->d_partials, ctx->d_flag)),
-                   (k_mean_energy<9><<<grid, 256, 0, ctx->stream>>>(src, ctx->g, M, ctx->d_partials, ctx->d_flag)));
+        DISPATCH_D(ctx, (k_mean_energy<3><<<grid, 256, 0, ctx->stream>>>(S.a, S.g, M, ctx->d_partials, ctx->d_flag)),
+                   (k_mean_energy<6><<<grid, 256, 0, ctx->stream>>>(S.a, S.g, M, ctx->d_partials, ctx->d_flag)),
+                   (k_mean_energy<9><<<grid, 256, 0, ctx->stream>>>(S.a, S.g, M, ctx->d_partials, ctx->d_flag)));
         FGB_CHECK_LAUNCH(ctx, "k_mean_energy");
     }
     rc = fgb_reduce_finish(ctx, grid, 1, 0, out);
     if (rc) return rc;
-    out[0] /= (double)ctx->g.nx * ctx->g.ny * ctx->g.nz;
+    out[0] /= (double)S.g.nx * S.g.ny * S.g.nz;
     return FGB_OK;
 }
 
 int fgb_k_min_detF(fgb_ctx* ctx, const double* src, double* out) {
     if (ctx->dim != 9) return fgb_fail(ctx, FGB_EINVAL, "min det(F) needs a 9-component field");
-    const size_t nvox = (size_t)ctx->g.lnx * ctx->g.ny * ctx->g.nz;
+    SweepGrid S;
+    int rc = sweep_begin(ctx, src, nullptr, nullptr, S);
+    if (rc) return rc;
+    const size_t nvox = (size_t)S.g.lnx * S.g.ny * S.g.nz;
     const unsigned grid = grid_for(ctx, nvox, 256);
-    k_min_detF<<<grid, 256, 0, ctx->stream>>>(src, ctx->g, ctx->d_partials);
+    k_min_detF<<<grid, 256, 0, ctx->stream>>>(S.a, S.g, ctx->d_partials);
     FGB_CHECK_LAUNCH(ctx, "k_min_detF");
     return fgb_reduce_finish(ctx, grid, 1, 1, out);
 }
@@ -435,18 +488,20 @@ int fgb_k_ref_material(fgb_ctx* ctx, const double* src, int zero_trace, double* 
     int rc = check_material(ctx);
     if (rc) return rc;
     const MaterialDev M = fgb_material_dev(ctx);
-    const size_t nvox = (size_t)ctx->g.lnx * ctx->g.ny * ctx->g.nz;
+    SweepGrid S;
+    if ((rc = sweep_begin(ctx, src, nullptr, nullptr, S))) return rc;
+    const size_t nvox = (size_t)S.g.lnx * S.g.ny * S.g.nz;
     const unsigned grid = grid_for(ctx, nvox, 128);
     int linear = 0;   // the per-phase shortcut is disabled: every voxel is evaluated (robust; once per load step)
     {
         ProfScope ps(ctx, "ref_material");
         if (zero_trace) {
             if (ctx->dim != 6) return fgb_fail(ctx, FGB_EINVAL, "zero_trace reference material is defined for dim 6 only");
-            k_ref_material<6, 1><<<grid, 128, 0, ctx->stream>>>(src, ctx->g, M, ctx->d_partials, linear, ctx->d_flag);
+            k_ref_material<6, 1><<<grid, 128, 0, ctx->stream>>>(S.a, S.g, M, ctx->d_partials, linear, ctx->d_flag);
         } else {
-            DISPATCH_D(ctx, (k_ref_material<3, 0><<<grid, 128, 0, ctx->stream>>>(src, ctx->g, M, ctx->d_partials, linear, ctx->d_flag)),
-                       (k_ref_material<6, 0><<<grid, 128, 0, ctx->stream>>>(src, ctx->g, M, ctx->d_partials, linear, ctx->d_flag)),
-                       (k_ref_material<9, 0><<<grid, 128, 0, ctx->stream>>>(src, ctx->g, M, ctx->d_partials, linear, ctx->d_flag)));
+            DISPATCH_D(ctx, (k_ref_material<3, 0><<<grid, 128, 0, ctx->stream>>>(S.a, S.g, M, ctx->d_partials, linear, ctx->d_flag)),
+                       (k_ref_material<6, 0><<<grid, 128, 0, ctx->stream>>>(S.a, S.g, M, ctx->d_partials, linear, ctx->d_flag)),
+                       (k_ref_material<9, 0><<<grid, 128, 0, ctx->stream>>>(S.a, S.g, M, ctx->d_partials, linear, ctx->d_flag)));
         }
         FGB_CHECK_LAUNCH(ctx, "k_ref_material");
     }

@@ -365,12 +365,15 @@ extern "C" int fgb_init_phase_capsules(fgb_ctx* c, int nfib, const fgb_capsule* 
     if (c->nphases < 1) return fgb_fail(c, FGB_EINVAL, "fgb_init_phase_capsules: set the number of phases first");
     if (matrix_mat < 0 || matrix_mat >= c->nphases) return fgb_fail(c, FGB_EINVAL, "matrix material %d out of range", matrix_mat);
     if (nfib < 0 || (nfib > 0 && !fibers)) return fgb_fail(c, FGB_EINVAL, "invalid fibre list");
-    const GridDev& g = c->g;
+    // full_staggered: initPhi runs on the doubly fine grid (select_dfg fg:17154-17156); half_staggered: on the coarse grid, the fine
+    // phases are injected afterwards (fg:17160-17164)
+    const bool fine = c->dfg == 2;
+    const GridDev& g = fine ? c->gf : c->g;
     PhaseArgs A;
     memset(&A, 0, sizeof(A));
     A.g = g;
     for (int a = 0; a < 3; a++) A.x0[a] = x0 ? x0[a] : 0.0;
-    A.dv[0] = c->L[0] / g.nx; A.dv[1] = c->L[1] / g.ny; A.dv[2] = c->L[2] / g.nz;
+    A.dv[0] = c->L[0] / g.nx; A.dv[1] = c->L[1] / g.ny; A.dv[2] = c->L[2] / g.nz;          // voxel size of the grid being initialised
     A.nmat = c->nphases;
     A.matrix_mat = matrix_mat;
     A.smooth_levels = smooth_levels;
@@ -453,20 +456,29 @@ extern "C" int fgb_init_phase_capsules(fgb_ctx* c, int nfib, const fgb_capsule* 
     A.cell_start = d_start;
     A.cell_fibs = d_fibs;
     A.fib = d_fib;
+    double** phi_dst = fine ? c->phi_f : c->phi;
     for (int m = 0; m < c->nphases; m++) {
-        if (!c->phi[m]) PH_CUDA(cudaMalloc(&c->phi[m], sizeof(double) * g.plane));
-        PH_CUDA(cudaMemsetAsync(c->phi[m], 0, sizeof(double) * g.plane, c->stream));      // padding: zeros (the reference writes NaN there)
-        A.phi[m] = c->phi[m];
+        if (!phi_dst[m]) PH_CUDA(cudaMalloc(&phi_dst[m], sizeof(double) * g.plane));
+        PH_CUDA(cudaMemsetAsync(phi_dst[m], 0, sizeof(double) * g.plane, c->stream));      // padding: zeros (the reference writes NaN there)
+        A.phi[m] = phi_dst[m];
     }
+    // normals / orientation are sampled on the fine grid whenever the doubly fine grid is in use (fg:14911-14937); with
+    // half_staggered that needs a second pass over the fine grid, which this build does not provide
+    if ((with_normals || with_orientation) && c->dfg == 1) {
+        cleanup();
+        return fgb_fail(c, FGB_EUNSUPPORTED, "normals / orientation from the device phase initialisation need gamma_scheme staggered or full_staggered");
+    }
+    double** nrm_dst = fine ? &c->normals_f : &c->normals;
+    double** ori_dst = fine ? &c->orient_f : &c->orient;
     if (with_normals) {
-        if (!c->normals) PH_CUDA(cudaMalloc(&c->normals, sizeof(double) * g.plane * 3));
-        PH_CUDA(cudaMemsetAsync(c->normals, 0, sizeof(double) * g.plane * 3, c->stream));
-        A.normals = c->normals;
+        if (!*nrm_dst) PH_CUDA(cudaMalloc(nrm_dst, sizeof(double) * g.plane * 3));
+        PH_CUDA(cudaMemsetAsync(*nrm_dst, 0, sizeof(double) * g.plane * 3, c->stream));
+        A.normals = *nrm_dst;
     }
     if (with_orientation) {
-        if (!c->orient) PH_CUDA(cudaMalloc(&c->orient, sizeof(double) * g.plane * 3));
-        PH_CUDA(cudaMemsetAsync(c->orient, 0, sizeof(double) * g.plane * 3, c->stream));
-        A.orient = c->orient;
+        if (!*ori_dst) PH_CUDA(cudaMalloc(ori_dst, sizeof(double) * g.plane * 3));
+        PH_CUDA(cudaMemsetAsync(*ori_dst, 0, sizeof(double) * g.plane * 3, c->stream));
+        A.orient = *ori_dst;
     }
     A.flag = c->d_flag;
     c->phi_halo_valid = false;
@@ -479,6 +491,16 @@ extern "C" int fgb_init_phase_capsules(fgb_ctx* c, int nfib, const fgb_capsule* 
         c->launches++;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { cleanup(); return fgb_fail(c, FGB_ECUDA, "launch of k_init_phi failed: %s", cudaGetErrorString(e)); }
+    }
+    if (c->dfg == 1) {
+        for (int m = 0; m < c->nphases; m++) {
+            if (!c->phi_f[m]) {
+                PH_CUDA(cudaMalloc(&c->phi_f[m], sizeof(double) * c->gf.plane));
+                PH_CUDA(cudaMemsetAsync(c->phi_f[m], 0, sizeof(double) * c->gf.plane, c->stream));
+            }
+            int rci = fgb_k_inject_phase(c, c->phi[m], c->phi_f[m]);
+            if (rci) { cleanup(); return rci; }
+        }
     }
     PH_CUDA(cudaMemcpyAsync(c->h_flag, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     PH_CUDA(cudaStreamSynchronize(c->stream));
@@ -494,8 +516,9 @@ extern "C" int fgb_init_phase_capsules(fgb_ctx* c, int nfib, const fgb_capsule* 
 extern "C" int fgb_get_phase(fgb_ctx* c, int phase, double* phi_plane) {
     if (!c) return FGB_EINVAL;
     cudaSetDevice(c->device);
-    if (phase < 0 || phase >= c->nphases || !c->phi[phase]) return fgb_fail(c, FGB_EINVAL, "phase %d not initialised", phase);
-    FGB_CUDA(c, cudaMemcpyAsync(phi_plane, c->phi[phase], sizeof(double) * c->g.plane, cudaMemcpyDeviceToHost, c->stream));
+    const double* src = (c->dfg == 2) ? c->phi_f[phase] : c->phi[phase];          // full_staggered: the fine-grid plane
+    if (phase < 0 || phase >= c->nphases || !src) return fgb_fail(c, FGB_EINVAL, "phase %d not initialised", phase);
+    FGB_CUDA(c, cudaMemcpyAsync(phi_plane, src, sizeof(double) * (c->dfg == 2 ? c->gf.plane : c->g.plane), cudaMemcpyDeviceToHost, c->stream));
     FGB_CUDA(c, cudaStreamSynchronize(c->stream));
     return FGB_OK;
 }

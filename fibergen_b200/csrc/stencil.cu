@@ -218,3 +218,90 @@ int fgb_k_mxpy(fgb_ctx* ctx, double* r, const double* x, const double* y) {
     FGB_CHECK_LAUNCH(ctx, "k_mxpy");
     return FGB_OK;
 }
+
+// ---- doubly fine grid transfer (half_staggered / full_staggered schemes) ------------------------------------------------
+// component-wise shifts of the staggered positions, stored component order 11,22,33,23,13,12,32,31,21 (fg:14232-14234)
+__constant__ int c_dfg_si[9] = {0, 0, 0, 0, 1, 1, 0, 1, 1};
+__constant__ int c_dfg_sj[9] = {0, 0, 0, 1, 0, 1, 1, 0, 1};
+__constant__ int c_dfg_sk[9] = {0, 0, 0, 1, 1, 0, 1, 1, 0};
+
+// prolongate_to_dfg fg:14216-14268: fine(i,j,k) = coarse(((i + si) mod fnx)/2, ((j + sj) mod fny)/2, ((k + sk) mod fnz)/2) per component
+__global__ void __launch_bounds__(256) k_prolongate(const double* __restrict__ c, double* __restrict__ f, GridDev gc, GridDev gf, int dim) {
+    const unsigned nvox = (unsigned)gf.lnx * (unsigned)gf.ny * (unsigned)gf.nz;
+    for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += gridDim.x * blockDim.x) {
+        const unsigned row_ = v / (unsigned)gf.nz;
+        const int k = (int)(v - row_ * (unsigned)gf.nz);
+        const int i = (int)(row_ / (unsigned)gf.ny);
+        const int j = (int)(row_ - (unsigned)i * (unsigned)gf.ny);
+        const size_t o = (size_t)row_ * gf.nzp + k;
+        for (int d = 0; d < dim; d++) {
+            const int ii = ((i + gf.lnx + c_dfg_si[d]) % gf.lnx) / 2;
+            const int jj = ((j + gf.ny + c_dfg_sj[d]) % gf.ny) / 2;
+            const int kk = ((k + gf.nz + c_dfg_sk[d]) % gf.nz) / 2;
+            f[(size_t)d * gf.plane + o] = c[(size_t)d * gc.plane + ((size_t)ii * gc.ny + jj) * gc.nzp + kk];
+        }
+    }
+}
+
+// restrict_from_dfg fg:14273-14339: coarse(i,j,k) = mean of the 8 fine values at (2i + a - si, 2j + b - sj, 2k + c - sk) mod n, a,b,c in {0,1}
+__global__ void __launch_bounds__(256) k_restrict(const double* __restrict__ f, double* __restrict__ c, GridDev gc, GridDev gf, int dim) {
+    const unsigned nvox = (unsigned)gc.lnx * (unsigned)gc.ny * (unsigned)gc.nz;
+    for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += gridDim.x * blockDim.x) {
+        const unsigned row_ = v / (unsigned)gc.nz;
+        const int k = (int)(v - row_ * (unsigned)gc.nz);
+        const int i = (int)(row_ / (unsigned)gc.ny);
+        const int j = (int)(row_ - (unsigned)i * (unsigned)gc.ny);
+        const size_t o = (size_t)row_ * gc.nzp + k;
+        for (int d = 0; d < dim; d++) {
+            const size_t i0 = (size_t)((2 * i + gf.lnx - c_dfg_si[d]) % gf.lnx), i1 = (size_t)((2 * i + 1 + gf.lnx - c_dfg_si[d]) % gf.lnx);
+            const size_t j0 = (size_t)((2 * j + gf.ny - c_dfg_sj[d]) % gf.ny), j1 = (size_t)((2 * j + 1 + gf.ny - c_dfg_sj[d]) % gf.ny);
+            const size_t k0 = (size_t)((2 * k + gf.nz - c_dfg_sk[d]) % gf.nz), k1 = (size_t)((2 * k + 1 + gf.nz - c_dfg_sk[d]) % gf.nz);
+            const double* s = f + (size_t)d * gf.plane;
+#define FQ(a, b, cc) s[((a)*gf.ny + (b)) * gf.nzp + (cc)]
+            c[(size_t)d * gc.plane + o] = 0.125 * (FQ(i0, j0, k0) + FQ(i1, j0, k0) + FQ(i0, j1, k0) + FQ(i1, j1, k0) + FQ(i0, j0, k1) +
+                                                   FQ(i1, j0, k1) + FQ(i0, j1, k1) + FQ(i1, j1, k1));
+#undef FQ
+        }
+    }
+}
+
+int fgb_k_prolongate(fgb_ctx* ctx, const double* coarse, double* fine) {
+    const GridDev& gf = ctx->gf;
+    const size_t nvox = (size_t)gf.lnx * gf.ny * gf.nz;
+    ProfScope ps(ctx, "prolongate_to_dfg");
+    const unsigned grid = fgb_wave_grid(ctx, (const void*)k_prolongate, 256, nvox, (size_t)ctx->sm_count * 16);
+    k_prolongate<<<grid, 256, 0, ctx->stream>>>(coarse, fine, ctx->g, gf, ctx->dim);
+    FGB_CHECK_LAUNCH(ctx, "k_prolongate");
+    return FGB_OK;
+}
+
+int fgb_k_restrict(fgb_ctx* ctx, const double* fine, double* coarse) {
+    const GridDev& g = ctx->g;
+    const size_t nvox = (size_t)g.lnx * g.ny * g.nz;
+    ProfScope ps(ctx, "restrict_from_dfg");
+    const unsigned grid = fgb_wave_grid(ctx, (const void*)k_restrict, 256, nvox, (size_t)ctx->sm_count * 16);
+    k_restrict<<<grid, 256, 0, ctx->stream>>>(fine, coarse, g, ctx->gf, ctx->dim);
+    FGB_CHECK_LAUNCH(ctx, "k_restrict");
+    return FGB_OK;
+}
+
+// initFullStageredRawPhases fg:17648-17680: piecewise constant injection of one coarse plane, fine(i,j,k) = coarse(i/2, j/2, k/2)
+__global__ void __launch_bounds__(256) k_inject(const double* __restrict__ c, double* __restrict__ f, GridDev gc, GridDev gf) {
+    const unsigned nvox = (unsigned)gf.lnx * (unsigned)gf.ny * (unsigned)gf.nz;
+    for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += gridDim.x * blockDim.x) {
+        const unsigned row_ = v / (unsigned)gf.nz;
+        const int k = (int)(v - row_ * (unsigned)gf.nz);
+        const int i = (int)(row_ / (unsigned)gf.ny);
+        const int j = (int)(row_ - (unsigned)i * (unsigned)gf.ny);
+        f[(size_t)row_ * gf.nzp + k] = c[((size_t)(i / 2) * gc.ny + (j / 2)) * gc.nzp + (k / 2)];
+    }
+}
+
+int fgb_k_inject_phase(fgb_ctx* ctx, const double* coarse, double* fine) {
+    const GridDev& gf = ctx->gf;
+    const size_t nvox = (size_t)gf.lnx * gf.ny * gf.nz;
+    const unsigned grid = fgb_wave_grid(ctx, (const void*)k_inject, 256, nvox, (size_t)ctx->sm_count * 16);
+    k_inject<<<grid, 256, 0, ctx->stream>>>(coarse, fine, ctx->g, gf);
+    FGB_CHECK_LAUNCH(ctx, "k_inject");
+    return FGB_OK;
+}

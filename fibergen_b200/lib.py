@@ -45,6 +45,9 @@ PROTOTYPES = {
     "fgb_field_device_ptr": (C.c_void_p, [C.c_void_p, C.c_int, C.c_int]),
     "fgb_set_num_phases": (C.c_int, [C.c_void_p, C.c_int]),
     "fgb_set_phase": (C.c_int, [C.c_void_p, C.c_int, c_dp]),
+    "fgb_set_dfg": (C.c_int, [C.c_void_p, C.c_int]),
+    "fgb_dfg_prolongate": (C.c_int, [C.c_void_p, C.c_int]),
+    "fgb_dfg_restrict": (C.c_int, [C.c_void_p, C.c_int]),
     "fgb_set_law": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_dp, C.c_int]),
     "fgb_set_normals": (C.c_int, [C.c_void_p, c_dpp]),
     "fgb_set_orientation": (C.c_int, [C.c_void_p, c_dpp]),

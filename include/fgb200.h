@@ -110,6 +110,16 @@ void* fgb_field_device_ptr(fgb_ctx* ctx, int field, int comp);   /* for zero-cop
 /* ---- setup (LSSolver::readSettings fg:15044, initPhi fg:17489) ------------------------------ */
 
 int  fgb_set_num_phases(fgb_ctx* ctx, int nphases);
+/* half_staggered / full_staggered (use_dfg fg:14894-14897): the constitutive sweeps (calcStress, calcStressDeriv, calcPolarization, the
+ * means, the reference-material scan) run on a doubly fine grid (2nx, 2ny, 2nz): prolongate_to_dfg fg:14216 before, restrict_from_dfg
+ * fg:14273 after (fg:18143-18149, fg:18343-18347).  mode 0 off, 1 half_staggered: fgb_set_phase takes coarse planes and the fine
+ * phases are their piecewise constant continuation (fg:17648); 2 full_staggered: fgb_set_phase / fgb_get_phase / fgb_set_normals /
+ * fgb_set_orientation take planes of the fine grid, 2*local_nx * 2*ny * 2*(nz+1) doubles (fg:17154-17156, fg:14911-14937).
+ * Call it right after fgb_create, before any phase data is set.  Staggered scheme, single GPU. */
+int  fgb_set_dfg(fgb_ctx* ctx, int mode);
+/* the transfer operators themselves between a field and the internal fine field _temp_dfg_1 (reference self-test fg:24491-24515) */
+int  fgb_dfg_prolongate(fgb_ctx* ctx, int field);
+int  fgb_dfg_restrict(fgb_ctx* ctx, int field);
 /* Phase::phi (fg:12010): one padded plane per phase */
 int  fgb_set_phase(fgb_ctx* ctx, int phase, const double* phi_plane);
 int  fgb_set_law(fgb_ctx* ctx, int phase, int law_id, const double* params, int nparams);

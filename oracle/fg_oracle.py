@@ -26,6 +26,41 @@ IDX = np.array([[0, 5, 4], [8, 1, 3], [7, 6, 2]])
 FFT_WORKERS = -1
 
 
+# --------------------------------------------------------------------------- doubly fine grid transfer (fg:14216-14339)
+_DFG_S = (np.array([0, 0, 0, 0, 1, 1, 0, 1, 1]), np.array([0, 0, 0, 1, 0, 1, 1, 0, 1]), np.array([0, 0, 0, 1, 1, 0, 1, 1, 0]))
+
+
+def prolongate_to_dfg(c):
+    """fg:14216-14268: f[g](i,j,k) = c[g](((i + s_i) mod 2nx)//2, ((j + s_j) mod 2ny)//2, ((k + s_k) mod 2nz)//2), the shift s depending on
+    the component g (the staggered positions of the shear components)"""
+    d, nx, ny, nz = c.shape
+    f = np.empty((d, 2 * nx, 2 * ny, 2 * nz))
+    for g in range(d):
+        ii = ((np.arange(2 * nx) + _DFG_S[0][g]) % (2 * nx)) // 2
+        jj = ((np.arange(2 * ny) + _DFG_S[1][g]) % (2 * ny)) // 2
+        kk = ((np.arange(2 * nz) + _DFG_S[2][g]) % (2 * nz)) // 2
+        f[g] = c[g][np.ix_(ii, jj, kk)]
+    return f
+
+
+def restrict_from_dfg(f):
+    """fg:14273-14339: c[g](i,j,k) = mean of the 8 fine values at ((2i + a - s_i) mod 2nx, ...), a in {0,1}"""
+    d, fnx, fny, fnz = f.shape
+    c = np.zeros((d, fnx // 2, fny // 2, fnz // 2))
+    for g in range(d):
+        acc = 0.0
+        # summation order of the reference: (i0,j0,k0) (i1,j0,k0) (i0,j1,k0) (i1,j1,k0) (i0,j0,k1) ...
+        for ck in (0, 1):
+            for cj in (0, 1):
+                for ci in (0, 1):
+                    ii = (2 * np.arange(fnx // 2) + ci + fnx - _DFG_S[0][g]) % fnx
+                    jj = (2 * np.arange(fny // 2) + cj + fny - _DFG_S[1][g]) % fny
+                    kk = (2 * np.arange(fnz // 2) + ck + fnz - _DFG_S[2][g]) % fnz
+                    acc = acc + f[g][np.ix_(ii, jj, kk)]
+        c[g] = 0.125 * acc
+    return c
+
+
 # --------------------------------------------------------------------------- layout
 def nzp_of(nz):
     return 2 * (nz // 2 + 1)
@@ -912,6 +947,13 @@ class LSSolver:
             gamma_scheme = "collocated" if method == "polarization" else "staggered"
         if method == "polarization":
             gamma_scheme = "collocated"
+        if gamma_scheme in ("half-staggered", "full-staggered"):
+            gamma_scheme = gamma_scheme.replace("-", "_")
+        # use_dfg fg:14894: half_staggered / full_staggered evaluate the material on the doubly fine grid; the operators are the
+        # staggered ones (fg:20480, fg:20496)
+        self.dfg = {"half_staggered": 1, "full_staggered": 2}.get(gamma_scheme, 0)
+        if self.dfg:
+            gamma_scheme = "staggered"
         self.gamma_scheme = gamma_scheme
         self.error_estimator = error_estimator
         self.outer_error_estimator = outer_error_estimator
@@ -950,7 +992,22 @@ class LSSolver:
 
     # -- setup ----------------------------------------------------------------
     def add_phase(self, name, law, phi):
-        self.mat.phases.append(Phase(name, law, np.ascontiguousarray(phi, dtype=float)))
+        """phi on the solver grid; full_staggered: on the doubly fine grid (fg:17154-17156); half_staggered: on the coarse grid, continued
+        piecewise constant to the fine grid (initFullStageredRawPhases fg:17648-17680)"""
+        phi = np.ascontiguousarray(phi, dtype=float)
+        if self.dfg == 1:
+            phi = np.repeat(np.repeat(np.repeat(phi, 2, axis=0), 2, axis=1), 2, axis=2)
+        self.mat.phases.append(Phase(name, law, phi))
+
+    def _mat_in(self, eps):
+        return prolongate_to_dfg(eps) if self.dfg else eps
+
+    def _mat_out(self, tau):
+        return restrict_from_dfg(tau) if self.dfg else tau
+
+    @property
+    def nxyz_mat(self):
+        return self.nxyz * (8 if self.dfg else 1)
 
     def set_reference(self, mu, lam):
         self.mu_0, self.lambda_0, self.reference_set = float(mu), float(lam), True
@@ -1046,13 +1103,14 @@ class LSSolver:
     def calcStress(self, mu_0, lambda_0, eps, alpha=1.0):
         beta = -alpha * 2 * mu_0
         gamma = -alpha * lambda_0
+        eps = self._mat_in(eps)                                       # fg:18143-18149
         P = self.mat.PK1(eps, alpha)
         if beta != 0:
             P = P + beta * eps
         if gamma != 0:
             trF = eps[0] + eps[1] + eps[2]
             P[:3] = P[:3] + gamma * trF
-        return P
+        return self._mat_out(P)                                       # fg:18343-18347
 
     def calcStressDiff(self, eps, alpha=1.0):
         return self.calcStress(self.mu_0, self.lambda_0, eps, alpha)
@@ -1060,13 +1118,14 @@ class LSSolver:
     def calcStressDeriv(self, mu_0, lambda_0, F, W, alpha=1.0):
         beta = -alpha * 2 * mu_0
         gamma = -alpha * lambda_0
+        F, W = self._mat_in(F), self._mat_in(W)                       # fg:18435-18441
         dP = self.mat.dPK1(F, alpha, W)
         if beta != 0:
             dP = dP + beta * W
         if gamma != 0:
             trW = W[0] + W[1] + W[2]
             dP[:3] = dP[:3] + gamma * trW
-        return dP
+        return self._mat_out(dP)
 
     def calcStressConst(self, mu_0, lambda_0, eps):
         """fg:17973-18020: tau = C0:eps"""
@@ -1077,16 +1136,16 @@ class LSSolver:
         return tau
 
     def calcPolarization(self, mu_0, eps, inv=False):
-        return self.mat.calcPolarization(mu_0, eps, inv)
+        return self._mat_out(self.mat.calcPolarization(mu_0, self._mat_in(eps), inv))      # fg:18051, fg:18113
 
     def calcMeanStress(self, eps=None):
-        eps = self.epsilon if eps is None else eps
-        P = self.mat.PK1(eps, 1.0 / self.nxyz)                                               # fg:12318 alpha /= nxyz
+        eps = self._mat_in(self.epsilon if eps is None else eps)                             # fg:17797-17803
+        P = self.mat.PK1(eps, 1.0 / self.nxyz_mat)                                           # fg:12318 alpha /= nxyz
         return P.reshape(self.dim, -1).sum(axis=1)
 
     def calcMeanEnergy(self, eps=None):
-        eps = self.epsilon if eps is None else eps
-        return float(np.sum(self.mat.W(eps))) / self.nxyz
+        eps = self._mat_in(self.epsilon if eps is None else eps)                             # fg:17769-17774
+        return float(np.sum(self.mat.W(eps))) / self.nxyz_mat
 
     def calcMeanCauchyStress(self, eps=None):
         """fg:17920-17941 -> meanCauchy fg:12268-12308 -> Cauchy fg:10326-10346: per voxel sigma = P(F) F^T / det F with the mixed
@@ -1094,9 +1153,10 @@ class LSSolver:
         eps = self.epsilon if eps is None else eps
         if self.dim != 9:
             raise RuntimeError("oracle: Cauchy stress needs the 9-component deformation gradient")
+        eps = self._mat_in(eps)                                         # fg:17926-17932
         F = mat33(eps.reshape(9, -1))                                   # (n, 3, 3)
         c = 1.0 / np.linalg.det(F)
-        P = mat33(self.mat.PK1(eps, 1.0).reshape(9, -1)) * (c / self.nxyz)[:, None, None]
+        P = mat33(self.mat.PK1(eps, 1.0).reshape(9, -1)) * (c / self.nxyz_mat)[:, None, None]
         return vec9(np.einsum('nik,njk->nij', P, F)).sum(axis=1)
 
     def calcDisplacement(self, eps=None):
@@ -1525,7 +1585,8 @@ class LSSolver:
     # -- reference material (fg:22283-22313, fg:12153-12236, fg:12472-12559) ------------------
     def getRefMaterial(self, F, zero_trace, polarization):
         d = self.dim
-        n = self.nxyz
+        F = self._mat_in(F)                                          # fg:22288-22294
+        n = self.nxyz_mat
         Ff = F.reshape(d, n)
         linear = all(ph.law.linear for ph in self.mat.phases)
         if linear:

@@ -250,3 +250,115 @@ def test_pipelined_cg_is_the_same_iteration():
         res.append(s.get_residuals())
         s.close()
     assert np.array_equal(res[0], res[1])
+
+
+@pytest.mark.parametrize("mode,d", [("elasticity", 6), ("heat", 3), ("hyperelasticity", 9)])
+def test_dfg_transfer_and_sweeps(mode, d):
+    """prolongate_to_dfg / restrict_from_dfg (fg:14216-14339): the reference's `staggered dfg operator` identity (fg:24491-24515) on
+    the device, and the constitutive sweep through the doubly fine grid (fg:18143-18149, fg:18343-18347) against the oracle"""
+    n = (10, 6, 7)
+    nf = tuple(2 * x for x in n)
+    ctx = fb.Context(*n, mode=mode, gamma_scheme="staggered")
+    ctx.chk(ctx.lib.fgb_set_dfg(ctx.h, 2))
+    rng = np.random.default_rng(21)
+    c1 = rng.random((d,) + n)
+    f = ctx.field(c1)
+    ctx.chk(ctx.lib.fgb_dfg_prolongate(ctx.h, f))
+    ctx.upload(f, np.zeros((d,) + n))
+    ctx.chk(ctx.lib.fgb_dfg_restrict(ctx.h, f))
+    assert np.abs(ctx.download(f) - c1).max() <= 4e-16
+    phi = sphere_phi(nf, R=0.3, sub=2)
+    o = fo.LSSolver(*n, mode=mode, gamma_scheme="full_staggered")
+    if mode == "heat":
+        laws = [("scalar", [1.0]), ("scalar", [10.0])]
+        olaws = [fo.ScalarLinearIsotropic(1.0, 3), fo.ScalarLinearIsotropic(10.0, 3)]
+    elif mode == "elasticity":
+        laws = [("iso", [0.4, 0.6]), ("iso", [4.0, 6.0])]
+        olaws = [fo.LinearIsotropic(0.4, 0.6), fo.LinearIsotropic(4.0, 6.0)]
+    else:
+        laws = [("nh", [10.0, 10.0]), ("nh", [10.0, 100.0])]
+        olaws = [fo.NeoHooke(10.0, 10.0), fo.NeoHooke(10.0, 100.0)]
+    ctx.lnx, ctx.ny, ctx.nz, ctx.nzp = nf[0], nf[1], nf[2], fb.nzp_of(nf[2])        # set_phases pads to the shape it is given
+    ctx.set_phases([1 - phi, phi], laws)
+    ctx.lnx, ctx.ny, ctx.nz, ctx.nzp = n[0], n[1], n[2], fb.nzp_of(n[2])
+    o.add_phase("a", olaws[0], 1 - phi)
+    o.add_phase("b", olaws[1], phi)
+    eps = 0.05 * rng.standard_normal((d,) + n)
+    if d == 9:
+        eps[:3] += 1.0
+    src, dst = ctx.field(eps), ctx.field()
+    ctx.chk(ctx.lib.fgb_calc_stress(ctx.h, src, dst, 0.7, 0.3, 1.0))
+    want = o.calcStress(0.7, 0.3, eps, 1.0)
+    assert relerr(ctx.download(dst), want) < 1e-13
+    assert relerr(ctx.mean_pk1(src), o.calcMeanStress(eps)) < 1e-13
+    ctx.close()
+
+
+@pytest.mark.parametrize("scheme", ["half_staggered", "full_staggered"])
+@pytest.mark.parametrize("kind", ["elasticity", "heat_laminate", "neo_hooke"])
+def test_dfg_schemes(scheme, kind):
+    """gamma_scheme half_staggered / full_staggered (use_dfg fg:14894) end to end against the oracle"""
+    n = (12, 10, 8)
+    nf = tuple(2 * x for x in n)
+    fine = scheme == "full_staggered"
+    phi = sphere_phi(nf if fine else n, R=0.3, sub=1 if fine else 2)
+    normals = None
+    if kind == "elasticity":
+        mode, kw = "elasticity", dict(method="cg", error_estimator="residual", tol=1e-8)
+        phases = [("m", "iso", (0.4, 0.6), fo.LinearIsotropic(0.4, 0.6), 1 - phi), ("f", "iso", (4.0, 6.0), fo.LinearIsotropic(4.0, 6.0), phi)]
+        E = [1, 0, 0, 0, 0, 0.2]
+    elif kind == "heat_laminate":
+        mode, kw = "heat", dict(method="cg", mixing_rule="laminate", error_estimator="residual", tol=1e-8)
+        phases = [("m", "iso", (1.0,), fo.ScalarLinearIsotropic(1.0, 3), 1 - phi), ("f", "iso", (10.0,), fo.ScalarLinearIsotropic(10.0, 3), phi)]
+        from microstructures import sphere_normals
+        normals = sphere_normals(nf)          # with the doubly fine grid the normals live on the fine grid (fg:14925-14937)
+        E = [1, 0.3, 0]
+    else:
+        mode, kw = "hyperelasticity", dict(method="cg", error_estimator="residual", outer_error_estimator="sigma", tol=1e-6)
+        phases = [("m", "nh", (10.0, 10.0), fo.NeoHooke(10.0, 10.0), 1 - phi), ("f", "nh", (10.0, 100.0), fo.NeoHooke(10.0, 100.0), phi)]
+        E = np.array([1, 1.1, 1, 0, 0, 0, 0, 0, 0], dtype=float)
+    s, o = build_pair(n, mode=mode, phases=phases, normals=normals, gamma_scheme=scheme, **kw)
+    compare(s, o, E=E)
+
+
+def test_nunan_keller_viscosity_demo():
+    """demo/python/nunan_keller/project.xml: effective viscosity of a simple cubic lattice of rigid spheres (viscosity mode, CG,
+    full_staggered, n = 32, tol 1e-5, smooth_tol 1e-5) against the (alpha, beta) of Nunan & Keller (1984) that the demo prints next
+    to its result (project.xml:21-31).  The five traceless load cases and the 5x5 inversion are those of calc_effective_properties
+    (fg:26264-26312); alpha = (mu_eff[0][0] - mu_eff[0][1])/2 - 1, beta = mu_eff[3][3] - 1 (project.xml:38-40)."""
+    theory = {0.12: (0.46580, 0.28995), 0.28: (2.1459, 0.74379)}
+    n = (32, 32, 32)
+    for V, (alpha_t, beta_t) in theory.items():
+        R = (V / (4 * math.pi / 3)) ** (1 / 3.0)
+        s = fb.LSSolver(*n, mode="viscosity", method="cg", gamma_scheme="full_staggered", tol=1e-5, smooth_tol=1e-5)
+        s.add_material("matrix", "iso", 1.0)
+        s.add_material("fiber", "iso", 0.0)
+        s.init()
+        s.init_phase([((0.5, 0.5, 0.5), (1, 0, 0), 0.0, R, 1)])
+        Ecols = np.zeros((6, 5))
+        Ecols[0, 0] = Ecols[1, 1] = 1
+        Ecols[1, 0] = Ecols[2, 1] = -1
+        Ecols[3, 2] = Ecols[4, 3] = Ecols[5, 4] = 1
+        S = np.zeros((6, 5))
+        for i in range(5):
+            s.set_strain(Ecols[:, i])
+            s.run()
+            S[:, i] = s.get_mean_stress()
+        C55 = Ecols[1:, :] @ np.linalg.inv(S[1:, :])                     # "2*eta" (5x5), fg:26300-26301
+        C = np.zeros((6, 6))
+        C[1:, 1:] = C55
+        for i in range(5):
+            if S[0, i] != 0:
+                for j in range(1, 6):
+                    C[j, 0] = (Ecols[j, i] - C[j, 1:] @ S[1:, i]) / S[0, i]
+                break
+        C[0, :] = -(C[1, :] + C[2, :])
+        C[:, :3] -= C[:, :3].min(axis=1, keepdims=True)
+        Cv = C.copy()
+        Cv[:, 3:] *= 0.5                                                  # Voigt notation, fg:26343-26349
+        alpha = 0.5 * (Cv[0, 0] - Cv[0, 1]) - 1
+        beta = Cv[3, 3] - 1
+        print("Nunan-Keller V=%.2f: alpha %.4f (theory %.4f), beta %.4f (theory %.4f)" % (V, alpha, alpha_t, beta, beta_t))
+        assert abs(alpha - alpha_t) <= 0.05 * alpha_t
+        assert abs(beta - beta_t) <= 0.05 * beta_t
+        s.close()

@@ -267,3 +267,11 @@ def test_effective_stiffness_between_reuss_and_voigt_bounds():
     assert np.linalg.eigvalsh(K - W @ reuss).min() >= -1e-8
     # and strictly inside for a two-phase composite
     assert np.linalg.eigvalsh(W @ voigt - K).max() > 1e-3 and np.linalg.eigvalsh(K - W @ reuss).max() > 1e-3
+
+
+@pytest.mark.parametrize("n", [(2, 1, 1), (41, 33, 11), (5, 4, 3)])
+def test_dfg_transfer_identity(n):
+    """'staggered dfg operator' of fibergen --test (fg:24491-24515): restrict_from_dfg(prolongate_to_dfg(c)) == c"""
+    rng = np.random.default_rng(8)
+    c = rng.random((9,) + n)
+    assert np.linalg.norm(np.abs(fo.restrict_from_dfg(fo.prolongate_to_dfg(c)) - c).reshape(9, -1).max(axis=1)) <= TOL
