@@ -141,6 +141,7 @@ extern "C" int fgb_create(fgb_ctx** out, int nx, int ny, int nz, double Lx, doub
     for (int i = 0; i < FGB_CG_RING; i++) c->ring_ev[i] = nullptr;
     c->nccl_comm = nullptr; c->nccl_lib = nullptr; c->sbuf = nullptr; c->xbuf = nullptr; c->xbuf_cap = 0;
     c->halo = nullptr; c->halo_slot = 0; c->d_gather = nullptr; c->visc_tmp = nullptr; c->p2p = false; c->iso_halo = nullptr; c->phi_halo_valid = false;
+    c->heatK = nullptr; c->heatK_valid = false; c->heatK_diag = 0;
     c->dfg = 0; c->dfg1 = c->dfg2 = nullptr; c->normals_f = c->orient_f = nullptr;
     for (int i = 0; i < FGB_MAX_PHASES; i++) c->phi_f[i] = nullptr;
     c->halo_base = nullptr; c->iso_set = 0; c->halo_seq = c->iso_seq = 0;
@@ -196,6 +197,7 @@ extern "C" void fgb_destroy(fgb_ctx* c) {
     for (int i = 0; i < FGB_MAX_PHASES; i++) if (c->phi[i]) cudaFree(c->phi[i]);
     if (c->ubuf) cudaFree(c->ubuf);
     if (c->visc_tmp) cudaFree(c->visc_tmp);
+    if (c->heatK) cudaFree(c->heatK);
     if (c->normals) cudaFree(c->normals);
     if (c->orient) cudaFree(c->orient);
     for (int i = 0; i < FGB_MAX_PHASES; i++) if (c->phi_f[i]) cudaFree(c->phi_f[i]);
@@ -342,6 +344,7 @@ extern "C" int fgb_set_phase(fgb_ctx* c, int p, const double* phi) {
     if (p < 0 || p >= c->nphases) return fgb_fail(c, FGB_EINVAL, "phase index %d out of range", p);
     const double* comps[1] = {phi};
     c->phi_halo_valid = false;
+    c->heatK_valid = false;
     if (c->dfg == 2) return upload_planes(c, &c->phi_f[p], comps, 1, c->gf.plane);                    // full_staggered: phases live on the fine grid (fg:17154-17156)
     int rc = upload_planes(c, &c->phi[p], comps, 1, c->g.plane);
     if (rc || c->dfg != 1) return rc;
@@ -377,6 +380,7 @@ extern "C" int fgb_set_law(fgb_ctx* c, int p, int law_id, const double* params, 
     if (ldim[law_id] && ldim[law_id] != c->dim)
         return fgb_fail(c, FGB_EINVAL, "law %d acts on %d components but mode has %d (fg:15211-15294)", law_id, ldim[law_id], c->dim);
     if (law_id == FGB_LAW_SCALAR && c->dim == 9) return fgb_fail(c, FGB_EINVAL, "scalar law is not defined for hyperelasticity");
+    c->heatK_valid = false;
     c->laws[p].id = law_id;
     for (int i = 0; i < FGB_MAX_LAW_PARAMS; i++) c->laws[p].p[i] = i < nparams ? params[i] : 0.0;
     return FGB_OK;
@@ -385,6 +389,7 @@ extern "C" int fgb_set_law(fgb_ctx* c, int p, int law_id, const double* params, 
 // with the doubly fine grid the normals / orientation live on the fine grid (get_normals / get_orientation fg:14911-14937)
 extern "C" int fgb_set_normals(fgb_ctx* c, const double* const* comps3) {
     CHECK_CTX(c);
+    c->heatK_valid = false;
     if (c->dfg) return upload_planes(c, &c->normals_f, comps3, 3, c->gf.plane);
     return upload_planes(c, &c->normals, comps3, 3, c->g.plane);
 }
@@ -399,6 +404,7 @@ extern "C" int fgb_set_mixing(fgb_ctx* c, int rule, const double* lp, int n) {
     if (rule != FGB_MIX_VOIGT && rule != FGB_MIX_LAMINATE && rule != FGB_MIX_REUSS)
         return fgb_fail(c, FGB_EUNSUPPORTED, "Unknown material mixing rule %d (voigt, reuss and laminate only)", rule);
     c->mix = rule;
+    c->heatK_valid = false;
     if (lp) {
         if (n != 10) return fgb_fail(c, FGB_EINVAL, "laminate parameter vector must have 10 entries");
         c->lam.eps_t = lp[0]; c->lam.eps_a = lp[1]; c->lam.eps_g = lp[2]; c->lam.alpha = lp[3]; c->lam.beta = lp[4];
@@ -848,6 +854,7 @@ extern "C" int fgb_fft_backward(fgb_ctx* c, int f) {
 }
 
 // ---- scheme-level ----------------------------------------------------------------------------------------------
+static int fused_kind(fgb_ctx* c, double lambda0);
 static int scratch_field(fgb_ctx* c, double** out) {
     if (!c->visc_tmp) {
         cudaError_t e = cudaMalloc(&c->visc_tmp, sizeof(double) * c->g.plane * c->dim);
@@ -862,6 +869,14 @@ extern "C" int fgb_basic_step(fgb_ctx* c, int src, int dst, const double* E, dou
     CHECK_CTX(c); CHECK_FIELD(c, src); CHECK_FIELD(c, dst);
     int rc;
     if (c->bc_relax != 1.0 && (rc = fgb_k_component_dot(c, c->fields[src], nullptr, c->F00, 1))) return rc;   // fg:20563-20565
+    if (fused_kind(c, lambda0) == 2) {
+        // heat / porous: (K - 2 mu0) grad and div_h in one sweep (calcStressDiff fg:18030 + divOperatorStaggeredHeat fg:18914)
+        if (c->nranks > 1 && (rc = fgb_comm_halo_heat(c, nullptr, c->fields[src]))) return rc;
+        if ((rc = fgb_k_heat_march(c, nullptr, 0.0, c->fields[src], nullptr, mu0, 1.0))) return rc;
+        if ((rc = g0_staggered(c, mu0, lambda0, -1.0))) return rc;
+        if (c->nranks > 1 && (rc = fgb_comm_halo_u(c))) return rc;
+        return fgb_k_eps(c, c->ubuf, c->fields[dst], E);
+    }
     if (fgb_fused_iso_applicable(c) && !c->bc_active && c->bc_relax == 1.0) {
         // fused: (C-C0):eps and div_h in one sweep, tau never written (calcStressDiff fg:18030 + divOperatorStaggered fg:18853)
         if (c->nranks > 1 && (rc = fgb_comm_halo_iso(c, nullptr, c->fields[src]))) return rc;
@@ -928,8 +943,22 @@ extern "C" int fgb_cg_apply(fgb_ctx* c, int F, int p, int w, double mu0, double 
 // One fused CG operator application: p_new = r + beta*p_old (skipped when r < 0, then p_new must equal p_old),
 // w = -Gamma0:(C-C0):p_new (or the tangent operator at F), pAp = <p_new, p_new - w>.
 // 1 if fgb_cg_step / fgb_cg_update accept w = FGB_W_IMPLICIT on this context (fused linear-elastic staggered path, no BC projector)
-static bool cg_fused_path(const fgb_ctx* c) { return fgb_fused_iso_applicable(c) && !c->bc_active && c->bc_relax == 1.0; }
-extern "C" int fgb_cg_implicit_w_supported(const fgb_ctx* c) { return (c && cg_fused_path(c)) ? 1 : 0; }
+// 0: generic kernels; 1: linear elasticity, isotropic phases, Voigt mixing (fused.cu); 2: heat / porous, scalar phases, any mixing rule
+// (fused_heat.cu; builds the per-voxel conductivity on first use)
+static int fused_kind(fgb_ctx* c, double lambda0) {
+    if (c->bc_active || c->bc_relax != 1.0) return 0;
+    if (fgb_fused_iso_applicable(c)) return 1;
+    if (lambda0 == 0.0 && fgb_fused_heat_applicable(c)) {
+        int diag = 0;
+        if (fgb_heat_tangent(c, &diag) == FGB_OK && diag) return 2;
+    }
+    return 0;
+}
+extern "C" int fgb_cg_implicit_w_supported(const fgb_ctx* c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    return fused_kind(const_cast<fgb_ctx*>(c), 0.0) ? 1 : 0;
+}
 
 extern "C" int fgb_cg_step(fgb_ctx* c, int F, int r, double beta, int p_old, int p_new, int w, double mu0, double lambda0, double* pAp) {
     CHECK_CTX(c); CHECK_FIELD(c, p_old); CHECK_FIELD(c, p_new);
@@ -938,10 +967,34 @@ extern "C" int fgb_cg_step(fgb_ctx* c, int F, int r, double beta, int p_old, int
     if (r >= 0) CHECK_FIELD(c, r);
     if (r < 0 && p_old != p_new) return fgb_fail(c, FGB_EINVAL, "fgb_cg_step without a direction update needs p_new == p_old");
     if (p_new == w) return fgb_fail(c, FGB_EINVAL, "krylovOperator cannot work in place (fg:20581)");
-    if (implicit_w && !(F < 0 && cg_fused_path(c) && r >= 0 && p_old != p_new && pAp))
+    const int fk = (F < 0) ? fused_kind(c, lambda0) : 0;
+    if (implicit_w && !(fk && r >= 0 && p_old != p_new && pAp))
         return fgb_fail(c, FGB_EUNSUPPORTED, "w = FGB_W_IMPLICIT needs the fused linear CG step (see fgb_cg_implicit_w_supported)");
     int rc;
-    if (F < 0 && cg_fused_path(c) && (r < 0 || p_old != p_new)) {
+    if (fk == 2 && (r < 0 || p_old != p_new)) {
+        double zero[9] = {0};
+        if (c->nranks > 1 && (rc = fgb_comm_halo_heat(c, r >= 0 ? c->fields[r] : nullptr, c->fields[p_old]))) return rc;
+        if ((rc = fgb_k_heat_march(c, r >= 0 ? c->fields[r] : nullptr, beta, c->fields[p_old], c->fields[p_new], mu0, 1.0))) return rc;
+        if ((rc = g0_staggered(c, mu0, lambda0, -1.0))) return rc;
+        if (c->nranks > 1 && (rc = fgb_comm_halo_u(c))) return rc;
+        if (implicit_w) {
+            c->reduce_on_device = c->cg_dev;
+            rc = fgb_k_heat_cg_u(c, true, zero, nullptr, nullptr, c->fields[p_new], 0.0, pAp);
+            c->reduce_on_device = false;
+            if (rc) return rc;
+            c->implicit_w_of = p_new;
+            return FGB_OK;
+        }
+        if ((rc = fgb_k_eps(c, c->ubuf, c->fields[w], zero))) return rc;
+        if (pAp) {
+            c->reduce_on_device = c->cg_dev;
+            rc = fgb_k_inner(c, c->fields[p_new], c->fields[p_new], c->fields[w], pAp);
+            c->reduce_on_device = false;
+            return rc;
+        }
+        return FGB_OK;
+    }
+    if (fk == 1 && (r < 0 || p_old != p_new)) {
         double zero[9] = {0};
         if (c->nranks > 1 && (rc = fgb_comm_halo_iso(c, r >= 0 ? c->fields[r] : nullptr, c->fields[p_old]))) return rc;
         if ((rc = fgb_k_dir_stress_div_iso(c, r >= 0 ? c->fields[r] : nullptr, beta, c->fields[p_old], c->fields[p_new], mu0, lambda0, 1.0))) return rc;
@@ -979,7 +1032,8 @@ extern "C" int fgb_cg_update(fgb_ctx* c, int x, int r, int p, int w, double a, d
             return fgb_fail(c, FGB_EINVAL, "fgb_cg_update: no implicit operator result for field %d (call fgb_cg_step with w = FGB_W_IMPLICIT first)", p);
         const double zero[9] = {0};
         c->reduce_on_device = c->cg_dev;
-        const int rc = fgb_k_cg_update_implicit(c, c->ubuf, zero, c->fields[x], c->fields[r], c->fields[p], a, delta);
+        const int rc = (c->dim == 3) ? fgb_k_heat_cg_u(c, false, zero, c->fields[x], c->fields[r], c->fields[p], a, delta)
+                                     : fgb_k_cg_update_implicit(c, c->ubuf, zero, c->fields[x], c->fields[r], c->fields[p], a, delta);
         c->reduce_on_device = false;
         return rc;
     }

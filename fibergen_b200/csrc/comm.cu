@@ -469,6 +469,14 @@ int fgb_comm_halo_tau(fgb_ctx* ctx, const double* tau) {
     return halo_exchange(ctx, lo, 1, hi, 2, pe, 0);
 }
 
+// k_heat_march needs tau_0 at i-1 (fg:18924-18962): component 0 of r, p_old and of the effective conductivity on the left rank's last plane
+int fgb_comm_halo_heat(fgb_ctx* ctx, const double* r, const double* p_old) {
+    const GridDev& g = ctx->g;
+    const size_t pe = (size_t)g.ny * g.nzp;
+    const double* lo[3] = {r ? r : p_old, p_old, ctx->heatK};
+    return halo_exchange(ctx, lo, 3, nullptr, 0, pe, 0);
+}
+
 // k_eps needs u_0 at i+1 and u_0..2 at i-1 (fg:18632-18654)
 int fgb_comm_halo_u(fgb_ctx* ctx) {
     const GridDev& g = ctx->g;

@@ -130,6 +130,9 @@ struct fgb_ctx {
     double bc_relax;
     double bc_MQ[81], bc_MQC0[81];
     double F00[9];
+    double* heatK;              // fused heat path: per-voxel diagonal of the (linear) mixed law, 3 planes (fused_heat.cu)
+    bool heatK_valid;
+    int heatK_diag;
     double* visc_tmp;           // copy of tau for the viscosity Delta operator (fg:21316-21320)
 
     // doubly fine grid of the half_staggered / full_staggered schemes (use_dfg fg:14894): the constitutive sweeps run on a grid
@@ -273,7 +276,14 @@ int fgb_k_dir_stress_div_iso(fgb_ctx* ctx, const double* r, double cgbeta, const
 int fgb_k_eps_dot(fgb_ctx* ctx, const double* u, double* eta, const double* Econst, const double* p, double* pAp);
 int fgb_k_cg_update_implicit(fgb_ctx* ctx, const double* u, const double* Econst, double* x, double* r, const double* p, double a, double* delta);
 
+// fused_heat.cu ------------------------------------------------------------------------------
+int fgb_fused_heat_applicable(const fgb_ctx* ctx);
+int fgb_heat_tangent(fgb_ctx* ctx, int* diag);
+int fgb_k_heat_march(fgb_ctx* ctx, const double* r, double cgbeta, const double* p_old, double* p_new, double mu0, double alpha);
+int fgb_k_heat_cg_u(fgb_ctx* ctx, bool dot_only, const double* Econst, double* x, double* r, const double* p, double a, double* out);
+
 // comm.cu ------------------------------------------------------------------------------------
+int fgb_comm_halo_heat(fgb_ctx* ctx, const double* r, const double* p_old);   // left neighbour's last plane of r_0, p_0 and K_0
 int fgb_comm_free(fgb_ctx* ctx);
 // neighbour planes for the fused isotropic sweep: r/p components 0,1,2 of the left neighbour's last plane, components 5,4 of the
 // right neighbour's first plane, and (once) the phase fractions of both planes; r may be null

@@ -801,7 +801,8 @@ void LSSolver::runCGElasticity(const Vec& E0, const Vec& S0) {
     int p = field(_f2), p2 = field(_f4);                                                    // direction vector, ping-pong
     // the operator result w is only consumed by the residual update: on the fused path it is never written to memory
     // (fgb200.h: FGB_W_IMPLICIT); the exact-residual variant and every other configuration keep the explicit field
-    const int w = (_cg_reinit <= 0 && fgb_cg_implicit_w_supported(_ctx)) ? FGB_W_IMPLICIT : field(_f3);
+    // (the fused heat sweeps assume lambda_0 = 0, which holds unless a <ref> material sets it, fg:15186-15194)
+    const int w = (_cg_reinit <= 0 && fgb_cg_implicit_w_supported(_ctx) && (_dim != 3 || _lambda_0 == 0.0)) ? FGB_W_IMPLICIT : field(_f3);
     check(fgb_set_constant(_ctx, _epsilon, E.data()));
     check(fgb_cg_step(_ctx, -1, -1, 0.0, _epsilon, _epsilon, r, _mu_0, _lambda_0, nullptr)); // krylovOperator(epsilon -> r)
     check(fgb_adjust_residual(_ctx, r, E.data(), _epsilon));

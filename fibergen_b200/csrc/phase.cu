@@ -482,6 +482,7 @@ extern "C" int fgb_init_phase_capsules(fgb_ctx* c, int nfib, const fgb_capsule* 
     }
     A.flag = c->d_flag;
     c->phi_halo_valid = false;
+    c->heatK_valid = false;
     const size_t nvox = (size_t)g.lnx * g.ny * g.nz;
     {
         ProfScope ps(c, "init_phase");
