@@ -387,6 +387,16 @@ def test_fused_heat_path(mixing, method, ee, n):
     from microstructures import sphere_normals
     s, o = build_pair(n, mode="heat", phases=phases, normals=sphere_normals(n) if mixing == "laminate" else None,
                       method=method, gamma_scheme="staggered", mixing_rule=mixing, error_estimator=ee, tol=1e-8)
+    if mixing == "laminate" and n == (9, 7, 5):
+        # odd grid: the normals of the voxels in the sphere's mid-planes have a component that is exactly zero, the reference's
+        # component-wise jump Hessian is singular there and the solution turns NaN (fg:9375, fg:21202) -- identically on the device
+        s.set_strain([1, 0.3, -0.2])
+        o.setStrain([1, 0.3, -0.2])
+        with pytest.raises(fb.FgbError, match="NaN detected"):
+            s.run()
+        with pytest.raises(RuntimeError, match="NaN detected"):
+            o.run()
+        return
     compare(s, o, E=[1, 0.3, -0.2])
     # the same run through the generic kernels gives the same history (A/B of the fusion)
     assert s.lib.fgb_cg_implicit_w_supported(s.ctx()) == 1
