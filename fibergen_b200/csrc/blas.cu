@@ -413,7 +413,7 @@ int fgb_k_extrapolate_poly(fgb_ctx* ctx, int n, const double* const* fields, con
 // Device-resident CG scalars.  The arithmetic is the host loop's (runCGElasticity fg:23211-23245), operation by operation, so that
 // both forms of the loop produce the same bits: sum / nxyz, + tiny, quotient.
 __global__ void k_cg_scalars(int mode, int nranks, const double* __restrict__ sums, double* __restrict__ scal, double nxyz,
-                             double* __restrict__ ring) {
+                             double* __restrict__ ring, const int* __restrict__ flag) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     double s = sums[0];
     for (int r = 1; r < nranks; r++) s = s + sums[r];          // rank order (fgb_allreduce_host)
@@ -428,6 +428,7 @@ __global__ void k_cg_scalars(int mode, int nranks, const double* __restrict__ su
         ring[1] = scal[3];
         ring[2] = scal[2];
         ring[3] = s;
+        ring[4] = (double)*flag;                               // material-law domain errors / peer time-outs raised so far
         const double delta = s + tiny;
         scal[4] = delta;
         scal[1] = delta / scal[0];
@@ -439,10 +440,10 @@ int fgb_k_cg_scalars(fgb_ctx* ctx, int mode, int ring_slot) {
     const double nxyz = (double)ctx->g.nx * ctx->g.ny * ctx->g.nz;
     const double* sums = ctx->nranks > 1 ? ctx->d_gather : ctx->d_result;
     double* ring = ctx->d_scalars + 8;
-    k_cg_scalars<<<1, 32, 0, ctx->stream>>>(mode, ctx->nranks, sums, ctx->d_scalars, nxyz, ring);
+    k_cg_scalars<<<1, 32, 0, ctx->stream>>>(mode, ctx->nranks, sums, ctx->d_scalars, nxyz, ring, ctx->d_flag);
     FGB_CHECK_LAUNCH(ctx, "k_cg_scalars");
     if (mode == 1) {
-        FGB_CUDA(ctx, cudaMemcpyAsync(ctx->h_ring + 4 * ring_slot, ring, sizeof(double) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        FGB_CUDA(ctx, cudaMemcpyAsync(ctx->h_ring + 8 * ring_slot, ring, sizeof(double) * 8, cudaMemcpyDeviceToHost, ctx->stream));
         FGB_CUDA(ctx, cudaEventRecord(ctx->ring_ev[ring_slot], ctx->stream));
     }
     return FGB_OK;

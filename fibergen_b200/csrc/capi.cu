@@ -142,6 +142,7 @@ extern "C" int fgb_create(fgb_ctx** out, int nx, int ny, int nz, double Lx, doub
     c->nccl_comm = nullptr; c->nccl_lib = nullptr; c->sbuf = nullptr; c->xbuf = nullptr; c->xbuf_cap = 0;
     c->halo = nullptr; c->halo_slot = 0; c->d_gather = nullptr; c->visc_tmp = nullptr; c->p2p = false; c->iso_halo = nullptr; c->phi_halo_valid = false;
     c->heatK = nullptr; c->heatK_valid = false; c->heatK_diag = 0;
+    c->nh_cache = nullptr; c->nh_cache_of = -1; c->nh_cache_mu0 = 0;
     c->dfg = 0; c->dfg1 = c->dfg2 = nullptr; c->normals_f = c->orient_f = nullptr;
     for (int i = 0; i < FGB_MAX_PHASES; i++) c->phi_f[i] = nullptr;
     c->halo_base = nullptr; c->iso_set = 0; c->halo_seq = c->iso_seq = 0;
@@ -170,9 +171,9 @@ extern "C" int fgb_create(fgb_ctx** out, int nx, int ny, int nz, double Lx, doub
     c->implicit_w_of = -1;
     CREATE_CUDA(cudaMalloc(&c->d_result, sizeof(double) * 64));
     CREATE_CUDA(cudaMallocHost(&c->h_result, sizeof(double) * 64));
-    CREATE_CUDA(cudaMalloc(&c->d_scalars, sizeof(double) * 16));
-    CREATE_CUDA(cudaMemset(c->d_scalars, 0, sizeof(double) * 16));
-    CREATE_CUDA(cudaMallocHost(&c->h_ring, sizeof(double) * 4 * FGB_CG_RING));
+    CREATE_CUDA(cudaMalloc(&c->d_scalars, sizeof(double) * 32));
+    CREATE_CUDA(cudaMemset(c->d_scalars, 0, sizeof(double) * 32));
+    CREATE_CUDA(cudaMallocHost(&c->h_ring, sizeof(double) * 8 * FGB_CG_RING));
     for (int i = 0; i < FGB_CG_RING; i++) CREATE_CUDA(cudaEventCreateWithFlags(&c->ring_ev[i], cudaEventDisableTiming));
     CREATE_CUDA(cudaMalloc(&c->d_flag, sizeof(int)));
     CREATE_CUDA(cudaMemset(c->d_flag, 0, sizeof(int)));
@@ -198,6 +199,7 @@ extern "C" void fgb_destroy(fgb_ctx* c) {
     if (c->ubuf) cudaFree(c->ubuf);
     if (c->visc_tmp) cudaFree(c->visc_tmp);
     if (c->heatK) cudaFree(c->heatK);
+    if (c->nh_cache) cudaFree(c->nh_cache);
     if (c->normals) cudaFree(c->normals);
     if (c->orient) cudaFree(c->orient);
     for (int i = 0; i < FGB_MAX_PHASES; i++) if (c->phi_f[i]) cudaFree(c->phi_f[i]);
@@ -967,6 +969,38 @@ extern "C" int fgb_cg_step(fgb_ctx* c, int F, int r, double beta, int p_old, int
     if (r >= 0) CHECK_FIELD(c, r);
     if (r < 0 && p_old != p_new) return fgb_fail(c, FGB_EINVAL, "fgb_cg_step without a direction update needs p_new == p_old");
     if (p_new == w) return fgb_fail(c, FGB_EINVAL, "krylovOperator cannot work in place (fg:20581)");
+    if (F >= 0 && c->nh_cache_of == F && c->nh_cache_mu0 == mu0 && r >= 0 && fgb_fused_nh_applicable(c)) {
+        // Neo-Hooke tangent from the per-voxel cache of this Newton iterate (fgb_cg_tangent_prepare): Q = R + beta Q and the tangent
+        // stress in one elementwise sweep, then div_h, G0, and either the explicit or the implicit gradient
+        CHECK_FIELD(c, F);
+        double* sigma = nullptr;
+        double zero[9] = {0};
+        int rc;
+        if (implicit_w) { if ((rc = scratch_field(c, &sigma))) return rc; }
+        else sigma = c->fields[w];
+        if ((rc = fgb_k_nh_dir_tangent(c, c->fields[r], beta, c->fields[p_old], c->fields[p_new], sigma, lambda0))) return rc;
+        if (c->nranks > 1 && (rc = fgb_comm_halo_tau(c, sigma))) return rc;
+        if ((rc = fgb_k_div(c, sigma, c->ubuf))) return rc;
+        if ((rc = g0_staggered(c, mu0, lambda0, -1.0))) return rc;
+        if (c->nranks > 1 && (rc = fgb_comm_halo_u(c))) return rc;
+        if (implicit_w) {
+            if (!pAp) return fgb_fail(c, FGB_EINVAL, "w = FGB_W_IMPLICIT needs pAp");
+            c->reduce_on_device = c->cg_dev;
+            rc = fgb_k_hyper_cg_u(c, true, nullptr, nullptr, c->fields[p_new], 0.0, pAp);
+            c->reduce_on_device = false;
+            if (rc) return rc;
+            c->implicit_w_of = p_new;
+            return FGB_OK;
+        }
+        if ((rc = fgb_k_eps(c, c->ubuf, c->fields[w], zero))) return rc;
+        if (pAp) {
+            c->reduce_on_device = c->cg_dev;
+            rc = fgb_k_inner(c, c->fields[p_new], c->fields[p_new], c->fields[w], pAp);
+            c->reduce_on_device = false;
+            return rc;
+        }
+        return FGB_OK;
+    }
     const int fk = (F < 0) ? fused_kind(c, lambda0) : 0;
     if (implicit_w && !(fk && r >= 0 && p_old != p_new && pAp))
         return fgb_fail(c, FGB_EUNSUPPORTED, "w = FGB_W_IMPLICIT needs the fused linear CG step (see fgb_cg_implicit_w_supported)");
@@ -1032,8 +1066,9 @@ extern "C" int fgb_cg_update(fgb_ctx* c, int x, int r, int p, int w, double a, d
             return fgb_fail(c, FGB_EINVAL, "fgb_cg_update: no implicit operator result for field %d (call fgb_cg_step with w = FGB_W_IMPLICIT first)", p);
         const double zero[9] = {0};
         c->reduce_on_device = c->cg_dev;
-        const int rc = (c->dim == 3) ? fgb_k_heat_cg_u(c, false, zero, c->fields[x], c->fields[r], c->fields[p], a, delta)
-                                     : fgb_k_cg_update_implicit(c, c->ubuf, zero, c->fields[x], c->fields[r], c->fields[p], a, delta);
+        const int rc = (c->dim == 3)   ? fgb_k_heat_cg_u(c, false, zero, c->fields[x], c->fields[r], c->fields[p], a, delta)
+                       : (c->dim == 9) ? fgb_k_hyper_cg_u(c, false, c->fields[x], c->fields[r], c->fields[p], a, delta)
+                                       : fgb_k_cg_update_implicit(c, c->ubuf, zero, c->fields[x], c->fields[r], c->fields[p], a, delta);
         c->reduce_on_device = false;
         return rc;
     }
@@ -1080,8 +1115,26 @@ extern "C" int fgb_cgdev_wait(fgb_ctx* c, int slot, double* out4) {
     CHECK_CTX(c);
     if (slot < 0 || slot >= FGB_CG_RING) return fgb_fail(c, FGB_EINVAL, "ring slot %d out of range 0..%d", slot, FGB_CG_RING - 1);
     FGB_CUDA(c, cudaEventSynchronize(c->ring_ev[slot]));
-    for (int i = 0; i < 4; i++) out4[i] = c->h_ring[4 * slot + i];
+    for (int i = 0; i < 4; i++) out4[i] = c->h_ring[8 * slot + i];
+    if (c->h_ring[8 * slot + 4] != 0.0) return poll_flag(c);          // a material law flagged a domain error (fg:10293) / a peer timed out
     return FGB_OK;
+}
+
+// Newton-CG (runCGHyper fg:22761-22790): F is fixed during the inner CG solve, so everything of the tangent that depends on F only is
+// evaluated once here.  Returns 1 if the fused Neo-Hooke tangent path is now active for inner iterations that pass this F (staggered
+// grid, Voigt mixing, all phases Neo-Hooke, no BC projector; then fgb_cg_step also accepts w = FGB_W_IMPLICIT and p_new == p_old),
+// 0 if the generic tangent sweep will be used, < 0 on error.
+extern "C" int fgb_cg_tangent_prepare(fgb_ctx* c, int F, double mu0, double lambda0) {
+    CHECK_CTX(c); CHECK_FIELD(c, F);
+    (void)lambda0;
+    c->nh_cache_of = -1;
+    if (!fgb_fused_nh_applicable(c)) return 0;
+    int rc = fgb_k_nh_cache(c, c->fields[F], mu0);
+    if (rc) return rc;
+    if ((rc = poll_flag(c))) return rc;
+    c->nh_cache_of = F;
+    c->nh_cache_mu0 = mu0;
+    return 1;
 }
 
 extern "C" int fgb_cg_direction(fgb_ctx* c, int p, int r, double beta) {

@@ -98,7 +98,7 @@ struct fgb_ctx {
     double* d_scalars;          // device-resident CG scalars: [0] gamma, [1] beta, [2] alpha, [3] <p, p - w>, [4] delta
     bool cg_dev;                // fgb_cgdev_*: kernels take beta / alpha from d_scalars, reductions stay on the device
     bool reduce_on_device;      // fgb_reduce_finish leaves the (rank-gathered) sums on the device instead of returning them
-    double* h_ring;             // pinned [FGB_CG_RING][4]: gamma, <p,p-w>, alpha, delta of the last iterations
+    double* h_ring;             // pinned [FGB_CG_RING][8]: gamma, <p,p-w>, alpha, delta, numeric-error flag of the last iterations
     cudaEvent_t ring_ev[8];
     int* d_flag;                // numeric error flag
     int* h_flag;
@@ -130,6 +130,9 @@ struct fgb_ctx {
     double bc_relax;
     double bc_MQ[81], bc_MQC0[81];
     double F00[9];
+    double* nh_cache;           // fused Neo-Hooke tangent: Finv (9) + 3 coefficients per voxel at the Newton iterate (fused_hyper.cu)
+    int nh_cache_of;            // field id the cache was built from (-1: none)
+    double nh_cache_mu0;
     double* heatK;              // fused heat path: per-voxel diagonal of the (linear) mixed law, 3 planes (fused_heat.cu)
     bool heatK_valid;
     int heatK_diag;
@@ -281,6 +284,12 @@ int fgb_fused_heat_applicable(const fgb_ctx* ctx);
 int fgb_heat_tangent(fgb_ctx* ctx, int* diag);
 int fgb_k_heat_march(fgb_ctx* ctx, const double* r, double cgbeta, const double* p_old, double* p_new, double mu0, double alpha);
 int fgb_k_heat_cg_u(fgb_ctx* ctx, bool dot_only, const double* Econst, double* x, double* r, const double* p, double a, double* out);
+
+// fused_hyper.cu -----------------------------------------------------------------------------
+int fgb_fused_nh_applicable(const fgb_ctx* ctx);
+int fgb_k_nh_cache(fgb_ctx* ctx, const double* F, double mu0);
+int fgb_k_nh_dir_tangent(fgb_ctx* ctx, const double* R, double cgbeta, const double* Q_old, double* Q_new, double* sigma, double lambda0);
+int fgb_k_hyper_cg_u(fgb_ctx* ctx, bool dot_only, double* X, double* R, const double* Q, double a, double* out);
 
 // comm.cu ------------------------------------------------------------------------------------
 int fgb_comm_halo_heat(fgb_ctx* ctx, const double* r, const double* p_old);   // left neighbour's last plane of r_0, p_0 and K_0

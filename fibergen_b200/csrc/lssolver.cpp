@@ -203,6 +203,8 @@ LSSolver::LSSolver(int nx, int ny, int nz, double dx, double dy, double dz, int 
     _loadstep_extrapolation_method = "polynomial";
     _first_loadstep = -1;
     _pipelined_cg = true;
+    _eps_stale = false;
+    _eps_F = _eps_X = -1;
     _smooth_levels = -1;                                                                     // fg:14842-14843
     _smooth_tol = 0.001;
     // the reference sizes the prescribed loads in its constructor (mode is known there); here the mode may still change until
@@ -557,21 +559,25 @@ Vec LSSolver::calcBCMean(const Vec& E, const Vec& S) const {
 }
 
 Vec LSSolver::calcMeanStress() {
+    syncEpsilon();
     Vec out(_dim);
     check(fgb_mean_pk1(_ctx, _epsilon, 1.0, out.data()));
     return out;
 }
 Vec LSSolver::calcMeanStrain() {
+    syncEpsilon();
     Vec out(_dim);
     check(fgb_average(_ctx, _epsilon, out.data()));
     return out;
 }
 Vec LSSolver::calcMeanCauchyStress() {
+    syncEpsilon();
     Vec out(9);
     check(fgb_mean_cauchy(_ctx, _epsilon, 1.0, out.data()));
     return out;
 }
 double LSSolver::calcMeanEnergy() {
+    syncEpsilon();
     double w = 0;
     check(fgb_mean_energy(_ctx, _epsilon, &w));
     return w;
@@ -653,6 +659,7 @@ bool LSSolver::run() {
     _residuals.clear();
     _cancel = false;
     _error.clear();
+    _eps_stale = false;
     if (!_ctx) fail("solver not initialised");
     try {
         setBCProjector(_BC_P);
@@ -878,21 +885,34 @@ void LSSolver::runCGElasticityPipelined(const Vec& E, int r, int p, int p2, int 
     }
 }
 
+void LSSolver::syncEpsilon() {
+    // inner Newton-CG iterations keep the current iterate as F + newton_relax*X (fg:23049) and form it when somebody looks
+    if (!_eps_stale) return;
+    _eps_stale = false;
+    check(fgb_xpay(_ctx, _epsilon, _eps_F, _newton_relax, _eps_X));
+}
+
 void LSSolver::runCGHyper(const Vec& E0, const Vec& S0) {
     // fg:22699-23130
-    const int F = field(_f1), X = field(_f2), R = field(_f3), Q = field(_f4), W = field(_f5);
+    const int F = field(_f1), X = field(_f2), R = field(_f3), Q = field(_f4);
     Vec dE = E0 - dyad4(_BC_P, calcMeanStrain());
     check(fgb_add_constant(_ctx, _epsilon, dE.data()));
     std::unique_ptr<ErrorEstimator> ee_outer(create_error_estimator(_outer_error_estimator));
     size_t iter_outer = 0;
     double gamma0 = -1;
     Vec zero(_dim, 0.0);
+    // the current iterate must be in _epsilon whenever an estimator or a user callback can look at it
+    const bool observed = _cb != nullptr || (_error_estimator != "residual" && _error_estimator != "none");
     for (;;) {
         if (gamma0 < 0 || _update_ref == "always") calcRefMaterial();
         check(fgb_copy(_ctx, _epsilon, F));
         check(fgb_calc_stress(_ctx, F, X, 0.0, 0.0, 1.0));                                  // X = P(F)
         Vec X0 = dyad4(_BC_M, S0);
         check(fgb_gamma(_ctx, X, X0.data(), _mu_0, _lambda_0, -1.0, 0.0));                  // X = -Gamma0 X, <X> = X0
+        // everything of the tangent that depends on F only, once per Newton iteration; > 0: fused Neo-Hooke sweeps, W stays implicit
+        const int fused = _pipelined_cg ? fgb_cg_tangent_prepare(_ctx, F, _mu_0, _lambda_0) : 0;
+        check(fused);
+        const int W = fused ? FGB_W_IMPLICIT : field(_f5);
         check(fgb_cg_apply(_ctx, F, X, R, _mu_0, _lambda_0, nullptr));                      // R = ApplyOperator(F, X)
         check(fgb_copy(_ctx, R, Q));
         double gamma;
@@ -901,26 +921,53 @@ void LSSolver::runCGHyper(const Vec& E0, const Vec& S0) {
         if (gamma0 < 0) gamma0 = gamma;
         std::unique_ptr<ErrorEstimator> ee(create_error_estimator());
         size_t iter = 0;
-        for (;;) {
-            double alpha;
-            check(fgb_cg_apply(_ctx, F, Q, W, _mu_0, _lambda_0, &alpha));
-            alpha += SMALL;
-            if (alpha <= 0) {
-                std::ostringstream o;
-                o << "indefinite operator (alpha=" << alpha << ") canceling CG!";
-                fail(o.str());
+        if (_pipelined_cg) {
+            // inner CG with gamma, beta, alpha on the device (see runCGElasticityPipelined): the operator application of iteration
+            // k+1 is enqueued before the host waits for delta_k
+            _eps_F = F; _eps_X = X;
+            check(fgb_cgdev_begin(_ctx, gamma));
+            check(fgb_cgdev_step(_ctx, F, R, Q, Q, W, _mu_0, _lambda_0));                   // Q = R + 0*Q
+            for (size_t k = 0;; k++) {
+                const int slot = (int)(k % 8);
+                check(fgb_cgdev_update(_ctx, X, R, Q, W, slot));                            // X += alpha*Q ; R -= alpha*(Q - W)
+                _eps_stale = true;                                                           // next F = current F + dF (fg:23049)
+                if (observed) syncEpsilon();
+                ee->update_cg(gamma, gamma0);
+                const bool stop = converged(iter, ee->abs_error(), ee->rel_error(), false);
+                if (!stop) check(fgb_cgdev_step(_ctx, F, R, Q, Q, W, _mu_0, _lambda_0));
+                double s[4];
+                check(fgb_cgdev_wait(_ctx, slot, s));                                        // also raises law domain errors (fg:10293)
+                if (s[1] + SMALL <= 0) {
+                    std::ostringstream o;
+                    o << "indefinite operator (alpha=" << (s[1] + SMALL) << ") canceling CG!";
+                    fail(o.str());
+                }
+                if (stop) break;
+                gamma = s[3] + SMALL;
             }
-            alpha = gamma / alpha;
-            double delta;
-            check(fgb_cg_update(_ctx, X, R, Q, W, alpha, &delta));                          // X += alpha*Q ; R -= alpha*(Q-W)
-            check(fgb_xpay(_ctx, _epsilon, F, _newton_relax, X));                           // next F = current F + dF (fg:23049)
-            check(fgb_check_numeric(_ctx));
-            ee->update_cg(gamma, gamma0);
-            if (converged(iter, ee->abs_error(), ee->rel_error(), false)) break;
-            delta += SMALL;
-            const double beta = delta / gamma;
-            gamma = delta;
-            check(fgb_cg_direction(_ctx, Q, R, beta));
+            syncEpsilon();
+        } else {
+            for (;;) {
+                double alpha;
+                check(fgb_cg_apply(_ctx, F, Q, W, _mu_0, _lambda_0, &alpha));
+                alpha += SMALL;
+                if (alpha <= 0) {
+                    std::ostringstream o;
+                    o << "indefinite operator (alpha=" << alpha << ") canceling CG!";
+                    fail(o.str());
+                }
+                alpha = gamma / alpha;
+                double delta;
+                check(fgb_cg_update(_ctx, X, R, Q, W, alpha, &delta));                      // X += alpha*Q ; R -= alpha*(Q-W)
+                check(fgb_xpay(_ctx, _epsilon, F, _newton_relax, X));                       // next F = current F + dF (fg:23049)
+                check(fgb_check_numeric(_ctx));
+                ee->update_cg(gamma, gamma0);
+                if (converged(iter, ee->abs_error(), ee->rel_error(), false)) break;
+                delta += SMALL;
+                const double beta = delta / gamma;
+                gamma = delta;
+                check(fgb_cg_direction(_ctx, Q, R, beta));
+            }
         }
         ee_outer->update();
         if (converged(iter_outer, ee_outer->abs_error(), ee_outer->rel_error())) break;
@@ -954,6 +1001,7 @@ int LSSolver::fieldComponents(const std::string& name) const {
 
 void LSSolver::getField(const std::string& name, double* const* comps) {
     // get_raw_field fg:15396-15557: derived fields are evaluated on the device from the converged strain field
+    syncEpsilon();
     if (name == "epsilon") check(fgb_field_download(_ctx, _epsilon, comps));
     else if (name == "sigma") {                                                             // calcStress(epsilon, sigma) fg:15500
         const int t = field(_f5);

@@ -95,6 +95,7 @@ PROTOTYPES = {
     "fgb_cg_update": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, c_dp]),
     "fgb_cg_implicit_w_supported": (C.c_int, [C.c_void_p]),
     "fgb_cg_direction": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double]),
+    "fgb_cg_tangent_prepare": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double]),
     "fgb_cgdev_begin": (C.c_int, [C.c_void_p, C.c_double]),
     "fgb_cgdev_step": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]),
     "fgb_cgdev_update": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),

@@ -244,6 +244,12 @@ int  fgb_cg_update(fgb_ctx* ctx, int x, int r, int p, int w, double a, double* d
 #define FGB_W_IMPLICIT (-2)
 int  fgb_cg_implicit_w_supported(const fgb_ctx* ctx);
 int  fgb_cg_direction(fgb_ctx* ctx, int p, int r, double beta);
+/* Newton-CG (runCGHyper fg:22761-22790): the deformation gradient F of the outer iteration is fixed during the inner CG solve; this
+ * evaluates everything of the tangent that depends on F only (per-voxel inverse, log-determinant, mixed coefficients) once.
+ * Returns 1 if fgb_cg_step / fgb_cgdev_step calls that pass this F now take the fused Neo-Hooke sweeps (staggered grid, Voigt mixing,
+ * all phases Neo-Hooke, no BC projector; w = FGB_W_IMPLICIT and p_new == p_old are then accepted), 0 if they take the generic
+ * calcStressDeriv sweep, < 0 on error.  Any change of F or of the reference material needs a new call. */
+int  fgb_cg_tangent_prepare(fgb_ctx* ctx, int F, double mu0, double lambda0);
 /* The same iteration with gamma, beta and alpha resident on the device (no host synchronisation inside an iteration):
  *   fgb_cgdev_begin : gamma = <r, r> + tiny of the start residual, beta = 0
  *   fgb_cgdev_step  : p_new = r + beta*p_old ; w = operator(p_new) ; alpha = gamma / (<p_new, p_new - w> + tiny)      (fg:23245, 23209-23218)

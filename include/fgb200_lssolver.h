@@ -81,7 +81,7 @@ public:
     size_t planeElems() const;
     const std::string& lastError() const { return _error; }
     fgb_ctx* ctx() { return _ctx; }
-    int epsilonField() const { return _epsilon; }
+    int epsilonField() { syncEpsilon(); return _epsilon; }
     unsigned long long launches() const;
 
     // --- pieces of the reference kept public for the parity tests
@@ -99,6 +99,7 @@ private:
     Vec  expandLoad(const Vec& e, const char* what) const;
     void extrapolateLoadstep(const std::vector<std::pair<double, int>>& last, double t);   // fg:21454-21513
     void pushBC();
+    void syncEpsilon();
     bool runLoadsteppingSolver(const Vec& Emax, const Vec& Smax);
     void runSolver(const Vec& E, const Vec& S);
     void runBasic(const Vec& E0, const Vec& S0);
@@ -144,6 +145,8 @@ private:
     Mat _BC_P, _BC_Q, _BC_QC0, _BC_M, _BC_MQ;
 
     int _epsilon, _f1, _f2, _f3, _f4, _f5;    // device field ids (-1 = not allocated)
+    bool _eps_stale;                          // Newton-CG: _epsilon still has to be formed as F + newton_relax*X (fg:23049)
+    int _eps_F, _eps_X;
     std::vector<double> _residuals;
     double _solve_time;
     bool _cancel;

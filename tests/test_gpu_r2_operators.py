@@ -400,3 +400,24 @@ def test_fused_heat_path(mixing, method, ee, n):
     compare(s, o, E=[1, 0.3, -0.2])
     # the same run through the generic kernels gives the same history (A/B of the fusion)
     assert s.lib.fgb_cg_implicit_w_supported(s.ctx()) == 1
+
+
+@pytest.mark.parametrize("n", [(12, 12, 12), (16, 10, 20)])
+@pytest.mark.parametrize("loadsteps", [1, 2])
+def test_fused_neo_hooke_newton_cg(n, loadsteps):
+    """fused Neo-Hooke inner CG (per-voxel tangent cache, implicit operator result, device-resident scalars) against the oracle, and
+    against the generic host-scalar loop of the same library (pipelined_cg = 0)"""
+    phi = sphere_phi(n, R=0.3, sub=2)
+    phases = [("matrix", "nh", (10.0, 10.0), fo.NeoHooke(10.0, 10.0), 1 - phi),
+              ("incl", "nh", (10.0, 100.0), fo.NeoHooke(10.0, 100.0), phi)]
+    kw = dict(mode="hyperelasticity", phases=phases, method="cg", error_estimator="residual", outer_error_estimator="sigma", tol=1e-6,
+              loadsteps=loadsteps)
+    F = np.array([1, 1.1, 1, 0, 0.02, 0, 0, 0, 0.01], dtype=float)
+    s, o = build_pair(n, **kw)
+    rs = compare(s, o, E=F)
+    s2, _ = build_pair(n, pipelined_cg=False, **kw)
+    s2.set_strain(F)
+    s2.run()
+    r2 = s2.get_residuals()
+    assert len(r2) == len(rs) and np.abs(r2 - rs).max() <= 1e-10 * np.abs(rs).max()
+    assert np.abs(s2.get_field() - s.get_field()).max() <= 1e-10
