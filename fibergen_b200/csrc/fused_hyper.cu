@@ -85,63 +85,82 @@ __global__ void __launch_bounds__(256) k_nh_dir_tangent(const double* __restrict
     }
 }
 
-// the 9 components of grad_h u at voxel (i,j,k) (epsOperatorStaggeredHyper fg:18784-18841, E = 0); halos as k_eps (stencil.cu)
+// the 9 components of grad_h u (epsOperatorStaggeredHyper fg:18784-18841, E = 0); two voxels (k, k+1) per thread so that X, R, Q and
+// u move as 16-byte accesses; halos as k_eps (stencil.cu)
 template <int DOT_ONLY>
 __global__ void __launch_bounds__(256, 3) k_hyper_cg_u(const double* __restrict__ u, const double* __restrict__ Q, double* __restrict__ X,
                                                     double* __restrict__ R, double a, GridDev g, double* __restrict__ partials,
                                                     const double* __restrict__ halo_lo, const double* __restrict__ halo_hi, size_t hslot,
                                                     const double* __restrict__ scal) {
     if (!DOT_ONLY && scal) a = scal[2];
-    const unsigned nvox = (unsigned)g.lnx * (unsigned)g.ny * (unsigned)g.nz;
+    const unsigned nzh = (unsigned)(g.nz + 1) / 2;
+    const unsigned npairs = (unsigned)g.lnx * (unsigned)g.ny * nzh;
     const size_t us = 2 * (size_t)g.unzcs;
     const double* u0p = u;
     const double* u1p = u + g.uplane;
     const double* u2p = u + 2 * g.uplane;
     double acc = 0;
-    for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += gridDim.x * blockDim.x) {
-        const unsigned row_ = v / (unsigned)g.nz;
-        const int k = (int)(v - row_ * (unsigned)g.nz);
+    for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v < npairs; v += gridDim.x * blockDim.x) {
+        const unsigned row_ = v / nzh;
+        const int k = 2 * (int)(v - row_ * nzh);
         const int i = (int)(row_ / (unsigned)g.ny);
         const int j = (int)(row_ - (unsigned)i * (unsigned)g.ny);
+        const bool second = k + 1 < g.nz;
         const int im = (i == 0) ? g.lnx - 1 : i - 1, ip = (i + 1 == g.lnx) ? 0 : i + 1;
         const int jm = (j == 0) ? g.ny - 1 : j - 1, jp = (j + 1 == g.ny) ? 0 : j + 1;
-        const int km = (k == 0) ? g.nz - 1 : k - 1, kp = (k + 1 == g.nz) ? 0 : k + 1;
-        const size_t o = (size_t)row_ * us + k;
+        const int km = (k == 0) ? g.nz - 1 : k - 1;
+        const int kp2 = (k + 2 >= g.nz) ? k + 2 - g.nz : k + 2;
+        const size_t rowo = (size_t)row_ * us;
+        const size_t o = rowo + k;
         const size_t o_im = ((size_t)im * g.ny + j) * us + k, o_ip = ((size_t)ip * g.ny + j) * us + k;
         const size_t o_jm = ((size_t)i * g.ny + jm) * us + k, o_jp = ((size_t)i * g.ny + jp) * us + k;
-        const size_t o_km = (size_t)row_ * us + km, o_kp = (size_t)row_ * us + kp;
         const size_t oh = (size_t)j * us + k;
         const bool lo_h = halo_lo != nullptr && i == 0, hi_h = halo_hi != nullptr && i + 1 == g.lnx;
-        const double u0 = u0p[o], u1 = u1p[o], u2 = u2p[o];
-        const double u0_ip = hi_h ? halo_hi[oh] : u0p[o_ip];
-        const double u1_im = lo_h ? halo_lo[hslot + oh] : u1p[o_im];
-        const double u2_im = lo_h ? halo_lo[2 * hslot + oh] : u2p[o_im];
-        double e[9];
-        e[0] = (u0_ip - u0) * g.hx;
-        e[1] = (u1p[o_jp] - u1) * g.hy;
-        e[2] = (u2p[o_kp] - u2) * g.hz;
-        e[3] = (u1 - u1p[o_km]) * g.hz;
-        e[4] = (u0 - u0p[o_km]) * g.hz;
-        e[5] = (u0 - u0p[o_jm]) * g.hy;
-        e[6] = (u2 - u2p[o_jm]) * g.hy;
-        e[7] = (u2 - u2_im) * g.hx;
-        e[8] = (u1 - u1_im) * g.hx;
+#define LD2(ptr) (*reinterpret_cast<const double2*>(ptr))
+        const double2 u0 = LD2(u0p + o), u1 = LD2(u1p + o), u2 = LD2(u2p + o);
+        const double2 u0_ip = hi_h ? LD2(halo_hi + oh) : LD2(u0p + o_ip);
+        const double2 u1_im = lo_h ? LD2(halo_lo + hslot + oh) : LD2(u1p + o_im);
+        const double2 u2_im = lo_h ? LD2(halo_lo + 2 * hslot + oh) : LD2(u2p + o_im);
+        const double2 u1_jp = LD2(u1p + o_jp), u0_jm = LD2(u0p + o_jm), u2_jm = LD2(u2p + o_jm);
+#undef LD2
+        const double u0_km = u0p[rowo + km], u1_km = u1p[rowo + km];
+        const double u2_kp2 = u2p[rowo + kp2];
+        const double u2_k1 = second ? u2.y : u2p[rowo];
+        double e0[9], e1[9];
+        e0[0] = (u0_ip.x - u0.x) * g.hx;   e1[0] = (u0_ip.y - u0.y) * g.hx;
+        e0[1] = (u1_jp.x - u1.x) * g.hy;   e1[1] = (u1_jp.y - u1.y) * g.hy;
+        e0[2] = (u2_k1 - u2.x) * g.hz;     e1[2] = (u2_kp2 - u2.y) * g.hz;
+        e0[3] = (u1.x - u1_km) * g.hz;     e1[3] = (u1.y - u1.x) * g.hz;
+        e0[4] = (u0.x - u0_km) * g.hz;     e1[4] = (u0.y - u0.x) * g.hz;
+        e0[5] = (u0.x - u0_jm.x) * g.hy;   e1[5] = (u0.y - u0_jm.y) * g.hy;
+        e0[6] = (u2.x - u2_jm.x) * g.hy;   e1[6] = (u2.y - u2_jm.y) * g.hy;
+        e0[7] = (u2.x - u2_im.x) * g.hx;   e1[7] = (u2.y - u2_im.y) * g.hx;
+        e0[8] = (u1.x - u1_im.x) * g.hx;   e1[8] = (u1.y - u1_im.y) * g.hx;
         const size_t eo = (size_t)row_ * g.nzp + k;
-        double s = 0;
+        double s0 = 0, s1 = 0;
 #pragma unroll
         for (int d = 0; d < 9; d++) {
             const size_t oo = (size_t)d * g.plane + eo;
-            const double q = __ldg(Q + oo);
+            const double2 q = *reinterpret_cast<const double2*>(Q + oo);
             if (DOT_ONLY) {
-                s += q * (q - e[d]);
-            } else {
-                X[oo] = X[oo] + a * q;
-                const double rv = R[oo] + (-a) * (q - e[d]);
-                R[oo] = rv;
-                s += rv * rv;
+                s0 += q.x * (q.x - e0[d]);
+                s1 += q.y * (q.y - e1[d]);
+                continue;
             }
+            double2 xv = *reinterpret_cast<double2*>(X + oo);
+            double2 rv = *reinterpret_cast<double2*>(R + oo);
+            xv.x = xv.x + a * q.x;
+            xv.y = xv.y + a * q.y;
+            rv.x = rv.x + (-a) * (q.x - e0[d]);
+            rv.y = rv.y + (-a) * (q.y - e1[d]);
+            if (!second) { xv.y = 0.0; rv.y = 0.0; }
+            *reinterpret_cast<double2*>(X + oo) = xv;
+            *reinterpret_cast<double2*>(R + oo) = rv;
+            s0 += rv.x * rv.x;
+            s1 += rv.y * rv.y;
         }
-        acc += s;
+        acc += s0;
+        if (second) acc += s1;
     }
     double vals[1] = {acc};
     block_reduce_store<1, 0>(vals, partials);
@@ -195,8 +214,8 @@ int fgb_k_nh_dir_tangent(fgb_ctx* ctx, const double* R, double cgbeta, const dou
 
 int fgb_k_hyper_cg_u(fgb_ctx* ctx, bool dot_only, double* X, double* R, const double* Q, double a, double* out) {
     const GridDev& g = ctx->g;
-    const size_t nvox = (size_t)g.lnx * g.ny * g.nz;
-    const unsigned grid = fgb_wave_grid(ctx, dot_only ? (const void*)k_hyper_cg_u<1> : (const void*)k_hyper_cg_u<0>, 256, nvox, ctx->red_blocks);
+    const size_t npairs = (size_t)g.lnx * g.ny * ((g.nz + 1) / 2);
+    const unsigned grid = fgb_wave_grid(ctx, dot_only ? (const void*)k_hyper_cg_u<1> : (const void*)k_hyper_cg_u<0>, 256, npairs, ctx->red_blocks);
     {
         ProfScope ps(ctx, dot_only ? "eps_dot_implicit" : "cg_update_implicit");
         const double* lo = (ctx->nranks > 1) ? ctx->halo : nullptr;

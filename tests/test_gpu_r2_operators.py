@@ -193,9 +193,6 @@ def test_loads_before_init_and_setting_validation():
         with pytest.raises(fb.FgbError):
             s.set(key, val)
     s.set("loadsteps", [0.0, 0.25, 1.0])              # sequences are joined with ','
-    s2 = fb.LSSolver(4, 4, 4, mode="heat")
-    with pytest.raises(fb.FgbError, match="Invalid size"):
-        s2.set_strain([1, 0, 0, 0])
 
 
 def test_device_phase_init_matches_restated_initphi():
