@@ -221,12 +221,23 @@ struct GreenDev {
     const double* pois[3];       // poisson_solve fg:23454: (n/L)^2 (cos(2 pi i / n) - 1) per index
 };
 
+// a / b from a reciprocal estimate r ~ 1/b by one Markstein correction step: the correctly rounded quotient (as the reference's
+// division) except in astronomically rare half-way cases, at 3 FMAs instead of a second division sequence
+__device__ __forceinline__ double div_by_rcp(double a, double b, double r) {
+    const double q = a * r;
+    const double rem = fma(-q, b, a);
+    return fma(rem, r, q);
+}
+
 // G0OperatorFourierStaggeredGeneral, fg:19834-19927
 __device__ __forceinline__ void green_staggered(const GreenDev& G, int ii, int jj, int kk, double2* f) {
     const double s0 = __ldg(G.kpm[0] + ii), s1 = __ldg(G.kpm[1] + jj), s2 = __ldg(G.kpm[2] + kk);
     const double norm = s0 * s0 + s1 * s1 + s2 * s2;
-    const double c1 = G.c10 / norm;
-    const double c2 = G.c20 / (norm * norm);
+    // c1 = c10/norm, c2 = c20/(norm*norm) (fg:19899-19900): one reciprocal serves both quotients
+    const double r = __drcp_rn(norm);
+    const double n2 = norm * norm;
+    const double c1 = div_by_rcp(G.c10, norm, r);
+    const double c2 = div_by_rcp(G.c20, n2, r * r);
     const double2 kp0 = __ldg(G.kp[0] + ii), kp1 = __ldg(G.kp[1] + jj), kp2 = __ldg(G.kp[2] + kk);
     const double2 fkp = cadd(cadd(cmul(f[0], kp0), cmul(f[1], kp1)), cmul(f[2], kp2));
     const double2 c2fkp = cscale(c2, fkp);

@@ -134,11 +134,18 @@ __global__ void __launch_bounds__(Max<R1, R2>::v* T) k_fftx_green_p2(double2* __
             for (int k1 = 0; k1 < R1; k1++) v[k1] = Sc[(s * R1 + k1) * T + t];
             p2::RegFFT<R1, +1>::run(v);
             if (valid) {
+                if (!pt.n && xo.seglen >= N) {
+                    // unsegmented destination (single GPU): no per-element division
+                    double2* b = base + c * xo.cstride + (long)blockIdx.y * xo.ostride + inner;
 #pragma unroll
-                for (int nb = 0; nb < R1; nb++) {
-                    const int e = s + R2 * nb;
-                    double2* b = pt.n ? pt.p[e / xo.seglen] : base;
-                    b[c * xo.cstride + (long)blockIdx.y * xo.ostride + inner + xo.at(e)] = v[nb];
+                    for (int nb = 0; nb < R1; nb++) b[(long)(s + R2 * nb) * xo.estride] = v[nb];
+                } else {
+#pragma unroll
+                    for (int nb = 0; nb < R1; nb++) {
+                        const int e = s + R2 * nb;
+                        double2* b = pt.n ? pt.p[e / xo.seglen] : base;
+                        b[c * xo.cstride + (long)blockIdx.y * xo.ostride + inner + xo.at(e)] = v[nb];
+                    }
                 }
             }
         }
@@ -279,14 +286,19 @@ static int launch_x_green(fgb_ctx* ctx, double2* base, const GreenDev& G, long e
         if (nx == 512) XG3(8, 8, 8, 4);
         else if (nx == 1024) XG3(16, 8, 8, 2);
         else if (NC > 3 || xg_p3) {
+            static const bool p3_t8 = getenv("FGB_XG_P3_T8") != nullptr;          // A/B: 8-lane three-pass tile at nx = 256
             if (nx == 64) XG3(4, 4, 4, 8);
             else if (nx == 128) XG3(8, 4, 4, 8);
+            else if (nx == 256 && p3_t8 && NC <= 3) XG3(8, 8, 4, 8);
             else if (nx == 256) XG3(8, 8, 4, 4);
         }
 #undef XG3
         if (rc != -1) return rc;
     }
     if constexpr (NC <= 3) {
+        static const bool t4 = getenv("FGB_XG_T4") != nullptr;                    // A/B: 4-lane two-pass tile (4 CTAs per SM)
+        if (t4 && nx == 256) rc = launch_xg_p2<256, 16, 16, NC, KIND, 4>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt);
+        if (rc != -1) return rc;
         switch (nx) {
             case 64: rc = launch_xg_p2<64, 8, 8, NC, KIND, 8>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt); break;
             case 128: rc = launch_xg_p2<128, 16, 8, NC, KIND, 8>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt); break;

@@ -374,6 +374,7 @@ static MarchTile march_tile(const fgb_ctx* ctx) {
     t.kchunks = (g.nz + t.threads - 1) / t.threads;
     const double resident = (t.threads > 256) ? 1.0 : 2.0;          // CTAs per SM (launch bounds of k_dsd_march)
     t.BJ = (g.ny % 4 == 0) ? 4 : (g.ny % 2 == 0) ? 2 : 1;
+    if (const char* e = getenv("FGB_MARCH_BJ")) { const int b = atoi(e); if ((b == 1 || b == 2 || b == 4) && g.ny % b == 0) t.BJ = b; }
     t.SEG = 16;
     if (const char* e = getenv("FGB_MARCH_SEG")) t.SEG = atoi(e);
     else {

@@ -412,7 +412,8 @@ def test_fused_neo_hooke_newton_cg(n, loadsteps):
     F = np.array([1, 1.1, 1, 0, 0.02, 0, 0, 0, 0.01], dtype=float)
     s, o = build_pair(n, **kw)
     rs = compare(s, o, E=F)
-    s2, _ = build_pair(n, pipelined_cg=False, **kw)
+    s2, _ = build_pair(n, **kw)
+    s2.set("pipelined_cg", False)
     s2.set_strain(F)
     s2.run()
     r2 = s2.get_residuals()
