@@ -209,8 +209,8 @@ __device__ __forceinline__ void diag_from(const IsoPhases& M, const double* phi,
     if (gamma != 0) { t0 += gamma * tr; t1 += gamma * tr; t2 += gamma * tr; }
 }
 
-template <int UPDATE, int NP, int BJ, int HALO, int ZW, int NT>
-__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_dsd_march(const double* __restrict__ r, const double* __restrict__ p_old, double* __restrict__ p_new,
+template <int UPDATE, int NP, int BJ, int HALO, int ZW, int NT, int MB>
+__global__ void __launch_bounds__(NT, MB) k_dsd_march(const double* __restrict__ r, const double* __restrict__ p_old, double* __restrict__ p_new,
                                                    double* __restrict__ u, GridDev g, IsoPhases M, double cgbeta, double beta, double gamma,
                                                    int SEG, const double* __restrict__ halo, const double* __restrict__ scal) {
     if (scal) cgbeta = scal[1];          // device-resident CG scalar (fgb_cgdev_*)
@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_dsd_march(const doubl
 // marching tiles: block size along z, rows per thread, and the x segment length.  Each segment pays one warm-up plane, and the
 // grid should fill whole waves of 2 CTAs per SM.
 struct MarchTile {
-    int threads, kchunks, BJ, SEG, segs;
+    int threads, kchunks, BJ, SEG, segs, mb;
 };
 static MarchTile march_tile(const fgb_ctx* ctx) {
     const GridDev& g = ctx->g;
@@ -372,9 +372,12 @@ static MarchTile march_tile(const fgb_ctx* ctx) {
     t.threads = (g.nz > 256 && g.nz <= 512 && !getenv("FGB_MARCH_NT256")) ? 512 : 256;
     while (t.threads > 32 && t.threads / 2 >= g.nz) t.threads /= 2;
     t.kchunks = (g.nz + t.threads - 1) / t.threads;
-    const double resident = (t.threads > 256) ? 1.0 : 2.0;          // CTAs per SM (launch bounds of k_dsd_march)
-    t.BJ = (g.ny % 4 == 0) ? 4 : (g.ny % 2 == 0) ? 2 : 1;
+    // two rows per thread: fewer registers, 3 CTAs per SM (measured at 256^3: 0.645 ms with 4 rows, 0.513 ms with 2)
+    t.BJ = (g.ny % 2 == 0) ? 2 : 1;
     if (const char* e = getenv("FGB_MARCH_BJ")) { const int b = atoi(e); if ((b == 1 || b == 2 || b == 4) && g.ny % b == 0) t.BJ = b; }
+    t.mb = 3;
+    if (const char* e = getenv("FGB_MARCH_MB")) t.mb = atoi(e) == 2 ? 2 : 3;
+    const double resident = (t.threads > 256) ? 1.0 : (t.BJ == 4 ? 2.0 : (t.BJ == 2 ? (double)t.mb : 4.0));          // CTAs per SM (launch bounds of k_dsd_march)
     t.SEG = 16;
     if (const char* e = getenv("FGB_MARCH_SEG")) t.SEG = atoi(e);
     else {
@@ -402,12 +405,21 @@ static int launch_march(fgb_ctx* ctx, const double* r, const double* p_old, doub
     const double* scal = (UPDATE && ctx->cg_dev) ? ctx->d_scalars : nullptr;
     const int threads = mt.threads, kchunks = mt.kchunks, SEG = mt.SEG;
     const int segs = mt.segs;
-#define LAUNCH_MARCH5(BJ_, H_, Z_, NT_)                                                                              \
+#define LAUNCH_MARCH6(BJ_, H_, Z_, NT_, MB_)                                                                         \
     do {                                                                                                             \
         const size_t smem = sizeof(double) * 2 * 3 * BJ_ * NT_;                                                     \
         if (smem > 48 * 1024)                                                                                        \
-            FGB_CUDA(ctx, cudaFuncSetAttribute(k_dsd_march<UPDATE, NP, BJ_, H_, Z_, NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_dsd_march<UPDATE, NP, BJ_, H_, Z_, NT_><<<grid, threads, smem, ctx->stream>>>(r, p_old, p_new, ctx->ubuf, g, M, cgbeta, beta, gamma, SEG, halo, scal); \
+            FGB_CUDA(ctx, cudaFuncSetAttribute(k_dsd_march<UPDATE, NP, BJ_, H_, Z_, NT_, MB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_dsd_march<UPDATE, NP, BJ_, H_, Z_, NT_, MB_><<<grid, threads, smem, ctx->stream>>>(r, p_old, p_new, ctx->ubuf, g, M, cgbeta, beta, gamma, SEG, halo, scal); \
+    } while (0)
+    // resident CTAs per SM asked of the compiler: 256-thread tiles 2 (4 rows), 3 or 2 (2 rows, FGB_MARCH_MB), 4 (1 row); 512-thread tiles 1
+#define LAUNCH_MARCH5(BJ_, H_, Z_, NT_)                                                \
+    do {                                                                               \
+        if (NT_ == 512) LAUNCH_MARCH6(BJ_, H_, Z_, NT_, 1);                            \
+        else if (BJ_ == 4) LAUNCH_MARCH6(BJ_, H_, Z_, NT_, 2);                         \
+        else if (BJ_ == 2 && mt.mb == 2) LAUNCH_MARCH6(BJ_, H_, Z_, NT_, 2);           \
+        else if (BJ_ == 2) LAUNCH_MARCH6(BJ_, H_, Z_, NT_, 3);                         \
+        else LAUNCH_MARCH6(BJ_, H_, Z_, NT_, 4);                                       \
     } while (0)
 #define LAUNCH_MARCH(BJ_)                                     \
     do {                                                      \
@@ -428,6 +440,7 @@ static int launch_march(fgb_ctx* ctx, const double* r, const double* p_old, doub
     else LAUNCH_MARCH(1);
 #undef LAUNCH_MARCH
 #undef LAUNCH_MARCH5
+#undef LAUNCH_MARCH6
     FGB_CHECK_LAUNCH(ctx, "k_dsd_march");
     return FGB_OK;
 }

@@ -232,7 +232,8 @@ int fgb_k_heat_march(fgb_ctx* ctx, const double* r, double cgbeta, const double*
     int threads = 256;
     while (threads > 32 && threads / 2 >= g.nz) threads /= 2;
     const int kchunks = (g.nz + threads - 1) / threads;
-    const int BJ = (g.ny % 4 == 0) ? 4 : (g.ny % 2 == 0) ? 2 : 1;
+    int BJ = (g.ny % 4 == 0) ? 4 : (g.ny % 2 == 0) ? 2 : 1;
+    if (const char* e = getenv("FGB_HEAT_BJ")) { const int b = atoi(e); if ((b == 1 || b == 2 || b == 4) && g.ny % b == 0) BJ = b; }
     // segments: whole waves of 3 CTAs per SM, one warm-up plane each
     int SEG = g.lnx;
     {
