@@ -372,11 +372,12 @@ static MarchTile march_tile(const fgb_ctx* ctx) {
     t.threads = (g.nz > 256 && g.nz <= 512 && !getenv("FGB_MARCH_NT256")) ? 512 : 256;
     while (t.threads > 32 && t.threads / 2 >= g.nz) t.threads /= 2;
     t.kchunks = (g.nz + t.threads - 1) / t.threads;
-    // two rows per thread: fewer registers, 3 CTAs per SM (measured at 256^3: 0.645 ms with 4 rows, 0.513 ms with 2)
+    // two rows per thread (measured at 256^3: 0.645 ms with 4 rows, 0.516 ms with 2, 0.572 ms with 1; at 512^3: 5.04 / 4.24 ms)
     t.BJ = (g.ny % 2 == 0) ? 2 : 1;
     if (const char* e = getenv("FGB_MARCH_BJ")) { const int b = atoi(e); if ((b == 1 || b == 2 || b == 4) && g.ny % b == 0) t.BJ = b; }
-    t.mb = 3;
-    if (const char* e = getenv("FGB_MARCH_MB")) t.mb = atoi(e) == 2 ? 2 : 3;
+    // (measured at 256^3, 2 rows: 0.516 ms when the compiler may use 128 registers, 0.630 ms when held to 80 for a third resident CTA)
+    t.mb = 2;
+    if (const char* e = getenv("FGB_MARCH_MB")) t.mb = atoi(e) == 3 ? 3 : 2;
     const double resident = (t.threads > 256) ? 1.0 : (t.BJ == 4 ? 2.0 : (t.BJ == 2 ? (double)t.mb : 4.0));          // CTAs per SM (launch bounds of k_dsd_march)
     t.SEG = 16;
     if (const char* e = getenv("FGB_MARCH_SEG")) t.SEG = atoi(e);
