@@ -39,7 +39,8 @@ E_M, NU_M, E_F, NU_F = 1.665, 0.36, 73.0, 0.18
 # algorithmic bytes per voxel-iteration, SURVEY.md 8(d) / BASELINE.md section 2; "moved": what this implementation actually moves
 # where it differs (the CG operator result w is never stored on the fused path: 72 B less)
 B_ALG = {"c1": 296.0, "c2": 728.0, "c3": 336.0, "c4": 1064.0}
-B_MOVED = {"c2": 656.0}
+# c2: the z passes are sweeps of their own here (+2*48 B over the survey's fused count) and w is implicit (-72 B): 752 B
+B_MOVED = {"c2": 752.0, "c3": 344.0, "c4": 1200.0}
 
 # algorithmic bytes per voxel of each kernel (d tensor comps, u vector comps, 2 phases); d, u substituted per config
 def kernel_bytes(d, u, nph=2):
@@ -183,6 +184,14 @@ def run_cuda(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    try:
+        # run (and first-touch the pinned staging buffers) on the CPUs next to this rank's GPU: with 8 ranks the device-to-host copies
+        # of the solution otherwise all land on one memory node (11 GB/s per GPU in round 1)
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+    except Exception:
+        pass
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the CUDA arm has no CPU fallback (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local_rank)

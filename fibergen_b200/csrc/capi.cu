@@ -2,6 +2,35 @@
 #include "fgb_internal.h"
 #include <cstdarg>
 #include <cmath>
+#include <nvtx3/nvToolsExt.h>
+
+// NVTX range of a kernel scope: named after the reference's Timer of the member(s) the kernel replaces (fg:1643-1737,
+// e.g. "calc stress" fg:18136, "fftVector" fg:18483, "G0OperatorFourierStaggered" fg:19836), so that a timeline reads like the
+// reference's <print_timings/> table.  Fused kernels carry all the names they cover.
+static const char* nvtx_name(const char* scope) {
+    static const struct { const char* scope; const char* timer; } map[] = {
+        {"calc_stress", "calc stress"}, {"calc_stress_deriv", "calc stress deriv"}, {"calc_stress_const", "calcStressConst"},
+        {"calc_polarization", "calc polarization"}, {"div_staggered", "divOperatorStaggered"}, {"eps_staggered", "epsOperatorStaggered"},
+        {"div_vector", "divVector"}, {"fft_z_r2c", "fftVector / forward FFT double (z)"}, {"fft_y_fwd", "fftVector / forward FFT double (y)"},
+        {"fft_y_fwd_p2p", "fftVector / forward FFT double (y) + slab transpose"}, {"fft_x_fwd", "fftTensor / forward FFT double (x)"},
+        {"fft_x_bwd", "fftInvTensor / backward FFT double (x)"},
+        {"fft_x_green", "forward FFT (x) + G0OperatorFourierStaggered / GammaOperatorFourierCollocated + backward FFT (x)"},
+        {"fft_y_bwd", "fftInvVector / backward FFT double (y)"}, {"fft_z_c2r", "fftInvVector / backward FFT double (z)"},
+        {"inner_product", "innerProductL2"}, {"component_dot", "component_dot"}, {"xpay", "xpay"}, {"xpaymz", "xpaymz"},
+        {"set_constant", "setConstant"}, {"adjust_residual", "adjustResidual"}, {"cg_update", "xpay + xpaymz + innerProductL2"},
+        {"cg_direction_stress_div", "xpay + calc stress + divOperatorStaggered"}, {"stress_div", "calc stress + divOperatorStaggered"},
+        {"eps_dot", "epsOperatorStaggered + innerProductL2"}, {"eps_dot_implicit", "epsOperatorStaggered + innerProductL2 (implicit)"},
+        {"cg_update_implicit", "epsOperatorStaggered + xpay + xpaymz + innerProductL2"},
+        {"heat_dir_flux_div", "xpay + calc stress + divOperatorStaggeredHeat"}, {"heat_flux_div", "calc stress + divOperatorStaggeredHeat"},
+        {"nh_dir_tangent", "xpay + calc stress deriv"}, {"nh_tangent", "calc stress deriv"}, {"nh_tangent_cache", "calc stress deriv (F-dependent part)"},
+        {"mean_pk1", "meanPK1"}, {"mean_energy", "meanW"}, {"mean_cauchy", "meanCauchy"}, {"ref_material", "getRefMaterial"},
+        {"prolongate_to_dfg", "prolongate_to_dfg"}, {"restrict_from_dfg", "restrict_from_dfg"}, {"init_phase", "phase initialization"},
+        {"halo_exchange", "halo exchange (slab partition)"}, {"heat_tangent", "laminate solve_newton (once per phase change)"},
+    };
+    for (const auto& m : map)
+        if (!strcmp(m.scope, scope)) return m.timer;
+    return scope;
+}
 
 static std::string g_create_error;
 
@@ -37,6 +66,7 @@ static cudaEvent_t get_event(fgb_ctx* c) {
 }
 
 ProfScope::ProfScope(fgb_ctx* ctx, const char* n) : c(ctx), name(n) {
+    nvtxRangePushA(nvtx_name(n));
     if (!c->profiling) return;
     ProfPending p;
     p.name = n;
@@ -46,6 +76,7 @@ ProfScope::ProfScope(fgb_ctx* ctx, const char* n) : c(ctx), name(n) {
     g_pending[c].push_back(p);
 }
 ProfScope::~ProfScope() {
+    nvtxRangePop();
     if (!c->profiling) return;
     cudaEventRecord(g_pending[c].back().e1, c->stream);
 }

@@ -10,8 +10,15 @@
 #include <limits>
 #include <sstream>
 #include <stdexcept>
+#include <nvtx3/nvToolsExt.h>
 
 namespace fgb {
+
+// NVTX range with the name of the reference's Timer for the same scope (fg:1643-1737; "runCGElasticity" fg:23155, "CG loop", ...)
+struct NvtxRange {
+    explicit NvtxRange(const char* n) { nvtxRangePushA(n); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 static const double EPS = std::numeric_limits<double>::epsilon();
 static const double SMALL = std::numeric_limits<double>::min();   // boost::numeric::bounds<T>::smallest()
@@ -603,6 +610,7 @@ ErrorEstimator* LSSolver::create_error_estimator(const std::string& name_) {
 
 void LSSolver::calcRefMaterial() {
     // fg:22283-22313 + getRefMaterial fg:12153-12236
+    NvtxRange nv("calc ref material");
     double lmin, lmax;
     check(fgb_ref_material(_ctx, _epsilon, _mode == "viscosity" ? 1 : 0, &lmin, &lmax));
     if (lmin < 0) lmin = 0;                                                                 // fg:12179-12218
@@ -766,6 +774,7 @@ void LSSolver::runSolver(const Vec& E, const Vec& S) {
 
 void LSSolver::runBasic(const Vec& E0, const Vec& S0) {
     // fg:21716-21805
+    NvtxRange nv("running solver (basic)");
     size_t iter = 1;
     std::unique_ptr<ErrorEstimator> ee(create_error_estimator());
     bool update_ref = (_update_ref != "never");
@@ -784,6 +793,7 @@ void LSSolver::runBasic(const Vec& E0, const Vec& S0) {
 
 void LSSolver::runPolarization(const Vec& E0, const Vec& S0) {
     // fg:21808-21851
+    NvtxRange nv("running solver (polarization)");
     size_t iter = 1;
     std::unique_ptr<ErrorEstimator> ee(create_error_estimator());
     if (_update_ref != "never") calcRefMaterial();
@@ -801,6 +811,7 @@ void LSSolver::runPolarization(const Vec& E0, const Vec& S0) {
 
 void LSSolver::runCGElasticity(const Vec& E0, const Vec& S0) {
     // fg:23153-23247
+    NvtxRange nv("runCGElasticity");
     if (_update_ref != "never") calcRefMaterial();
     Vec E = calcBCMean(E0, S0);
     std::unique_ptr<ErrorEstimator> ee(create_error_estimator());
@@ -867,6 +878,7 @@ void LSSolver::runCGElasticityPipelined(const Vec& E, int r, int p, int p2, int 
     // only (fg:23223-23226), which the update of iteration k-1 produced: the operator application of iteration k+1 is enqueued
     // before the host waits for delta_k, so the device never idles and an iteration costs one (hidden) host synchronisation.
     (void)E;
+    NvtxRange nv("CG loop");
     const double gamma0 = gamma;
     check(fgb_cgdev_begin(_ctx, gamma));
     check(fgb_cgdev_step(_ctx, -1, r, p, p2, w, _mu_0, _lambda_0));
@@ -894,6 +906,7 @@ void LSSolver::syncEpsilon() {
 
 void LSSolver::runCGHyper(const Vec& E0, const Vec& S0) {
     // fg:22699-23130
+    NvtxRange nv("runCGHyper");
     const int F = field(_f1), X = field(_f2), R = field(_f3), Q = field(_f4);
     Vec dE = E0 - dyad4(_BC_P, calcMeanStrain());
     check(fgb_add_constant(_ctx, _epsilon, dE.data()));
