@@ -184,14 +184,15 @@ def run_cuda(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    try:
-        # run (and first-touch the pinned staging buffers) on the CPUs next to this rank's GPU: with 8 ranks the device-to-host copies
-        # of the solution otherwise all land on one memory node (11 GB/s per GPU in round 1)
-        import pynvml
-        pynvml.nvmlInit()
-        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
-    except Exception:
-        pass
+    if world > 1:
+        try:
+            # run (and first-touch the pinned staging buffers) on the CPUs next to this rank's GPU: with 8 ranks the device-to-host
+            # copies of the solution otherwise all land on one memory node (11 GB/s per GPU in round 1)
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+        except Exception:
+            pass
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the CUDA arm has no CPU fallback (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local_rank)
@@ -470,6 +471,7 @@ def cpu_baseline_and_parity(n, box, phi, res_dev, iters=2):
     cpu = None
     try:
         from oracle import fg_cpu
+        fg_cpu.set_threads(cores)
         r = fg_cpu.cg_iterations(n, box, phi, (lame(E_M, NU_M)[::-1], lame(E_F, NU_F)[::-1]), [1, 0, 0, 0, 0, 0], warm=1, steps=iters)
         res_o = r["residuals"]
         cpu = {"value": n[0] * n[1] * n[2] * iters / r["seconds"], "unit": UNIT, "cores": r["threads"], "kind": "port",
@@ -502,11 +504,12 @@ def run_reference(args):
     Cs, Ds, R, Lc = config2_fibres()
     s = base / 256.0                       # the same cell sampled on a base^3 grid
     fibres, box = fiber_list(n, Cs * s, Ds, R * s, Lc * s, material=1)
+    cores = os.cpu_count() or 1
+    from oracle import fg_cpu
+    fg_cpu.set_threads(cores)              # torchrun exports OMP_NUM_THREADS=1: use all the host threads, as asked of this arm
     phi = fp.init_phi(n, box, fibres, 2)[0][1]
     K, W = args.steps, max(args.warmup, 1)
-    cores = os.cpu_count() or 1
     try:
-        from oracle import fg_cpu
         r = fg_cpu.cg_iterations(n, box, phi, (lame(E_M, NU_M)[::-1], lame(E_F, NU_F)[::-1]), [1, 0, 0, 0, 0, 0], warm=W, steps=K)
         dt, cores = r["seconds"], r["threads"]
         how = "OpenMP C++ restatement (oracle/fg_cpu.cpp: threaded elementwise sweeps + its own threaded FFT), %d threads" % cores

@@ -339,6 +339,9 @@ struct Solver {
 
 extern "C" {
 
+// number of OpenMP threads for everything in libfgoracle (torchrun exports OMP_NUM_THREADS=1 to its children)
+void fgcpu_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+
 // Runs warm + steps CG iterations of runCGElasticity (fg:23153-23247) from eps = E and returns the residual history
 // sqrt(gamma_k/gamma_0) (ResidualErrorEstimator fg:14397, one entry per iteration), the wall time of the last `steps` iterations,
 // the mean stress <P(eps)> of the last iterate and the reference material.  phi: nph unpadded planes (nx*ny*nz doubles, x slowest).

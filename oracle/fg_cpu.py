@@ -8,6 +8,14 @@ import numpy as np
 from . import fg_phase as _fp
 
 
+def set_threads(n):
+    """OpenMP threads used by libfgoracle (phase initialisation and CG restatement)"""
+    lib = _fp.load()
+    lib.fgcpu_set_threads.argtypes = [C.c_int]
+    lib.fgcpu_set_threads.restype = None
+    lib.fgcpu_set_threads(int(n))
+
+
 def cg_iterations(n, L, phi_fibre, materials, E, warm=1, steps=2):
     """two-phase problem: matrix fraction 1 - phi_fibre, materials = ((mu_m, lam_m), (mu_f, lam_f)); returns a dict with the
     residual history of warm + steps iterations, the seconds of the last `steps`, the thread count, mean stress and mu_0"""
