@@ -1,7 +1,15 @@
 #!/bin/bash
 # single-GPU measurement pass of round 2 (run under gpurun): tests, the four bench configurations, the CPU arm, ncu launch list and captures
+# usage: r2_measure.sh bench | ncu   (two calls: gpurun copies back at most 64 MiB)
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
+if [ "$1" = "ncu" ]; then
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_cg_update_u6|k_dsd_march|k_fftx_green|k_fftz_p2|k_ffts_p2" -s 16 -c 8 -o gpurun_out/prof_r02 -f python bench.py --steps 4 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/ncu_f.log 2>&1
+timeout 600 ncu --set full --clock-control none -k regex:"k_heat_march|k_heat_cg_u" -s 4 -c 3 -o gpurun_out/prof_r02_c3 -f python bench.py --config c3 --grid 256 --steps 4 --warmup 3 --no-e2e > gpurun_out/ncu_f3.log 2>&1
+timeout 600 ncu --set full --clock-control none -k regex:"k_nh_dir_tangent|k_hyper_cg_u" -s 4 -c 3 -o gpurun_out/prof_r02_c4 -f python bench.py --config c4 --steps 4 --warmup 3 --no-e2e > gpurun_out/ncu_f4.log 2>&1
+ls -la gpurun_out/*.ncu-rep
+exit 0
+fi
 timeout 900 python -m pytest tests -m gpu -q 2>&1 | grep -v "^$" | tail -15 | cut -c1-250 > gpurun_out/r2_tests_final.log
 tail -3 gpurun_out/r2_tests_final.log
 for c in c2 c1 c3 c4; do
@@ -9,9 +17,6 @@ for c in c2 c1 c3 c4; do
 done
 timeout 600 python bench.py --impl reference --steps 4 --warmup 1 > gpurun_out/bench_r02_reference_arm.json 2> gpurun_out/bench_r02_reference_arm.err
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_r02.csv python bench.py --steps 4 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/ncu_l.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_cg_update_u6|k_dsd_march|k_fftx_green|k_fftz_p2|k_ffts_p2" -s 16 -c 8 -o gpurun_out/prof_r02 -f python bench.py --steps 4 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/ncu_f.log 2>&1
-timeout 600 ncu --set full --clock-control none -k regex:"k_heat_march|k_heat_cg_u" -s 4 -c 3 -o gpurun_out/prof_r02_c3 -f python bench.py --config c3 --grid 256 --steps 4 --warmup 3 --no-e2e > gpurun_out/ncu_f3.log 2>&1
-timeout 600 ncu --set full --clock-control none -k regex:"k_nh_dir_tangent|k_hyper_cg_u" -s 4 -c 3 -o gpurun_out/prof_r02_c4 -f python bench.py --config c4 --steps 4 --warmup 3 --no-e2e > gpurun_out/ncu_f4.log 2>&1
 python - <<'PY'
 import json
 for c in ("c2", "c1", "c3", "c4"):
