@@ -4,10 +4,15 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 if [ "$1" = "ncu" ]; then
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_cg_update_u6|k_dsd_march|k_fftx_green|k_fftz_p2|k_ffts_p2" -s 16 -c 8 -o gpurun_out/prof_r02 -f python bench.py --steps 4 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/ncu_f.log 2>&1
-timeout 600 ncu --set full --clock-control none -k regex:"k_heat_march|k_heat_cg_u" -s 4 -c 3 -o gpurun_out/prof_r02_c3 -f python bench.py --config c3 --grid 256 --steps 4 --warmup 3 --no-e2e > gpurun_out/ncu_f3.log 2>&1
-timeout 600 ncu --set full --clock-control none -k regex:"k_nh_dir_tangent|k_hyper_cg_u" -s 4 -c 3 -o gpurun_out/prof_r02_c4 -f python bench.py --config c4 --steps 4 --warmup 3 --no-e2e > gpurun_out/ncu_f4.log 2>&1
-ls -la gpurun_out/*.ncu-rep
+# the reports stay on the box (they exceed the 64 MiB that are copied back); their raw / source pages are exported as CSV
+T=/tmp/fgb_prof; mkdir -p $T
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_cg_update_u6|k_dsd_march|k_fftx_green|k_fftz_p2|k_ffts_p2" -s 16 -c 8 -o $T/prof_r02 -f python bench.py --steps 4 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/ncu_f.log 2>&1
+timeout 600 ncu --set full --clock-control none -k regex:"k_heat_march|k_heat_cg_u" -s 4 -c 3 -o $T/prof_r02_c3 -f python bench.py --config c3 --grid 256 --steps 4 --warmup 3 --no-e2e > gpurun_out/ncu_f3.log 2>&1
+timeout 600 ncu --set full --clock-control none -k regex:"k_nh_dir_tangent|k_hyper_cg_u" -s 4 -c 3 -o $T/prof_r02_c4 -f python bench.py --config c4 --steps 4 --warmup 3 --no-e2e > gpurun_out/ncu_f4.log 2>&1
+for r in prof_r02 prof_r02_c3 prof_r02_c4; do ncu -i $T/$r.ncu-rep --page raw --csv > gpurun_out/${r}_raw.csv 2>/dev/null; done
+ncu -i $T/prof_r02.ncu-rep --page source --csv --kernel-name regex:k_fftx_green > gpurun_out/prof_r02_src_fftx_green.csv 2>/dev/null
+ncu -i $T/prof_r02.ncu-rep --page source --csv --kernel-name regex:k_dsd_march > gpurun_out/prof_r02_src_dsd_march.csv 2>/dev/null
+ls -la gpurun_out/*.csv
 exit 0
 fi
 timeout 900 python -m pytest tests -m gpu -q 2>&1 | grep -v "^$" | tail -15 | cut -c1-250 > gpurun_out/r2_tests_final.log
