@@ -7,6 +7,9 @@
 #include "fft_pow2_3.cuh"
 #include "fft_launch.cuh"
 #include <cstdlib>
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
 
 using p2::Max;
 
@@ -217,6 +220,105 @@ __global__ void __launch_bounds__(p3::Plan<R1, R2, R3, T>::TPP* T, MINB)
     }
 }
 
+// The same pass for a CTA PAIR (thread-block cluster of 2 along the tile index) whose output goes to peer GPUs: with T lanes per
+// CTA a row segment is only T*16 bytes (64 at nx = 1024, where a wider tile does not fit), and 64-byte stores reach ~430 GB/s
+// over NVLink against ~690 GB/s for 128-byte ones.  Each CTA parks one component's output in a shared-memory stage, and after a
+// cluster barrier stores HALF of the x range with 2T lanes -- T from its own stage, T from its partner's through distributed
+// shared memory -- so every segment that crosses NVLink is 2T*16 = 128 bytes.
+template <int R1, int R2, int R3, int NC, int KIND, int T>
+__global__ void __launch_bounds__(p3::Plan<R1, R2, R3, T>::TPP* T, 1)
+    k_fftx_green_p3c(double2* __restrict__ base, const double2* __restrict__ tw, GreenDev G, long estride, int ninner, long ostride,
+                     long cstride, int jbase, PencilMap xo, PeerTable pt) {
+    using P = p3::Plan<R1, R2, R3, T>;
+    constexpr int N = P::N, M = P::M, NT = P::TPP * T;
+    extern __shared__ double2 smem_x3[];
+    double2* tw_s = smem_x3;
+    double2* B1 = smem_x3 + N;
+    double2* B2 = B1 + P::BUF1;
+    double2* stage = B2 + P::BUF2;          // [N][T]
+    cg::cluster_group cl = cg::this_cluster();
+    const unsigned cr = cl.block_rank();
+    const int tid = threadIdx.x;
+    for (int i = tid; i < N; i += NT) tw_s[i] = tw[i];
+    const int t = tid % T, s = tid / T;
+    const int inner = blockIdx.x * T + t;
+    const bool valid = inner < ninner;
+    double2* g = base + (long)blockIdx.y * ostride + inner;
+    __syncthreads();
+
+    double2 w[NC][R3];
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        double2 v[R1];
+        if (s < M) {
+#pragma unroll
+            for (int n1 = 0; n1 < R1; n1++) v[n1] = valid ? g[c * cstride + (long)(M * n1 + s) * estride] : make_double2(0, 0);
+        }
+        P::template forward<-1>(v, w[c], s, t, B1, B2, tw_s);
+    }
+    if (s < R1 * R2 && valid) {
+        const int jj = jbase + blockIdx.y;
+        const int kk = inner;
+#pragma unroll
+        for (int k3 = 0; k3 < R3; k3++) {
+            const int ii = s + R1 * R2 * k3;
+            double2 f[NC];
+#pragma unroll
+            for (int c = 0; c < NC; c++) f[c] = w[c][k3];
+            if (ii == 0 && jj == 0 && kk == 0) {
+#pragma unroll
+                for (int c = 0; c < NC; c++) f[c] = make_double2(G.dc[c], 0.0);
+            } else {
+                green_apply<KIND>(G, ii, jj, kk, f);
+            }
+#pragma unroll
+            for (int c = 0; c < NC; c++) w[c][k3] = f[c];
+        }
+    }
+    __syncthreads();
+    // the pair's 2T lanes: lanes [0, T) live in CTA 0's stage, [T, 2T) in CTA 1's
+    const int lane2 = tid % (2 * T), eo = tid / (2 * T);
+    const double2* src = cl.map_shared_rank(stage, lane2 / T) + (lane2 % T);
+    const int inner2 = (int)(blockIdx.x - cr) * T + lane2;
+    constexpr int EPI = NT / (2 * T);          // x indices per sweep of the CTA
+    constexpr int NIT = (N / 2) / EPI;
+    // split cluster barrier: "arrive" right after the stores of a component, "wait" only before the stage is written again, so the
+    // partner's stores overlap this CTA's next inverse transform
+#define CL_ARRIVE() asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory")
+#define CL_WAIT() asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory")
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        double2 o[R1];
+        P::inverse(w[c], o, s, t, B1, B2, tw_s);
+        if (c) CL_WAIT();          // the partner has read the previous component out of this CTA's stage
+        if (s < M) {
+#pragma unroll
+            for (int na = 0; na < R1; na++) stage[(s + M * na) * T + t] = o[na];
+        }
+        CL_ARRIVE();
+        CL_WAIT();
+        if (inner2 < ninner) {
+            const int e0 = (int)cr * (N / 2) + eo;
+#pragma unroll
+            for (int h = 0; h < NIT; h += 4) {
+                double2 q[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) q[u] = src[(size_t)(e0 + (h + u) * EPI) * T];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int e = e0 + (h + u) * EPI;
+                    double2* b = pt.n ? pt.p[e / xo.seglen] : base;
+                    b[c * xo.cstride + (long)blockIdx.y * xo.ostride + inner2 + xo.at(e)] = q[u];
+                }
+            }
+        }
+        CL_ARRIVE();
+    }
+    CL_WAIT();          // no CTA leaves while its partner may still read its stage
+#undef CL_ARRIVE
+#undef CL_WAIT
+}
+
 // ---- x with Green operator ---------------------------------------------------------------------------------
 template <int N, int R1, int R2, int NC, int KIND, int T>
 static int launch_xg_p2(fgb_ctx* ctx, double2* base, const GreenDev& G, long estride, int ninner, int nouter, long ostride, long cstride,
@@ -258,6 +360,33 @@ static int launch_xg_p3(fgb_ctx* ctx, double2* base, const GreenDev& G, long est
     return FGB_OK;
 }
 
+template <int R1, int R2, int R3, int NC, int KIND, int T>
+static int launch_xg_p3c(fgb_ctx* ctx, double2* base, const GreenDev& G, long estride, int ninner, int nouter, long ostride, long cstride,
+                         int jbase, const PencilMap& xo, const PeerTable& pt) {
+    using P = p3::Plan<R1, R2, R3, T>;
+    constexpr int NT = P::TPP * T;
+    const size_t smem = (size_t)(P::N + P::SMEM_ELEMS + (size_t)P::N * T) * sizeof(double2);
+    if (smem > ctx->smem_optin) return -1;
+    auto kern = k_fftx_green_p3c<R1, R2, R3, NC, KIND, T>;
+    FGB_CUDA(ctx, set_smem(kern, smem));
+    const unsigned tiles = (unsigned)((ninner + T - 1) / T);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((tiles + 1) / 2 * 2, nouter, 1);          // whole pairs; a CTA past the last tile only serves the barriers
+    cfg.blockDim = dim3(NT, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    FGB_CUDA(ctx, cudaLaunchKernelEx(&cfg, kern, base, (const double2*)ctx->plan[0].tw, G, estride, ninner, ostride, cstride, jbase, xo, pt));
+    FGB_CHECK_LAUNCH(ctx, "k_fftx_green_p3c");
+    return FGB_OK;
+}
+
 template <int NC, int KIND>
 static int launch_x_green(fgb_ctx* ctx, double2* base, const GreenDev& G, long estride, int ninner, int nouter, long ostride, long cstride,
                           int jbase, const PencilMap& xo, const PeerTable& pt) {
@@ -279,7 +408,13 @@ static int launch_x_green(fgb_ctx* ctx, double2* base, const GreenDev& G, long e
         if constexpr (NC <= 3) {
             if (pt.n > 0 && !narrow) {
                 if (nx == 512) rc = launch_xg_p3<8, 8, 8, NC, KIND, 8, 1>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt);
-                else if (nx == 1024) rc = launch_xg_p3<16, 8, 8, NC, KIND, 4, 1>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt);
+                else if (nx == 1024) {
+                    // FGB_XG_CLUSTER: CTA pairs exchanging through distributed shared memory, 128-byte segments.  Not the default: at 2 GPUs
+                    // (1024^3) the exchange costs more than the wider segments return, 22.3 vs 15.7 ms
+                    static const bool use_cl = getenv("FGB_XG_CLUSTER") != nullptr;
+                    if (use_cl) rc = launch_xg_p3c<16, 8, 8, NC, KIND, 4>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt);
+                    if (rc == -1) rc = launch_xg_p3<16, 8, 8, NC, KIND, 4, 1>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt);
+                }
             }
         }
         if (rc != -1) return rc;

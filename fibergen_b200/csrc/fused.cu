@@ -209,6 +209,13 @@ __device__ __forceinline__ void diag_from(const IsoPhases& M, const double* phi,
     if (gamma != 0) { t0 += gamma * tr; t1 += gamma * tr; t2 += gamma * tr; }
 }
 
+static __device__ __forceinline__ void l2_prefetch(const double* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+template <bool B>
+struct BoolTag {
+    static constexpr bool value = B;
+};
+
 template <int UPDATE, int NP, int BJ, int HALO, int ZW, int NT, int MB>
 __global__ void __launch_bounds__(NT, MB) k_dsd_march(const double* __restrict__ r, const double* __restrict__ p_old, double* __restrict__ p_new,
                                                    double* __restrict__ u, GridDev g, IsoPhases M, double cgbeta, double beta, double gamma,
@@ -218,8 +225,12 @@ __global__ void __launch_bounds__(NT, MB) k_dsd_march(const double* __restrict__
     // [r_lo 3][p_lo 3][r_hi 2][p_hi 2][phi_lo MAXP][phi_hi MAXP], each ny*nzp doubles (comm.cu: fgb_comm_halo_iso)
     const size_t pe = (size_t)g.ny * g.nzp;
     const int j0 = blockIdx.x * BJ;
-    const int i0 = blockIdx.y * SEG;
-    const int i1 = min(i0 + SEG, g.lnx);
+    // slab partition: the last plane (whose x neighbour is the hi halo) is the work of an extra row of CTAs, the "tail"; the
+    // regular segments cover planes [0, lnx-1) and never look at the hi halo.  (Taking the halo branch inside the loop, or
+    // peeling the last plane after the loop, left halo state live across the loop and cost the slab variant 15-25 %.)
+    const bool tail = HALO && (blockIdx.y + 1 == gridDim.y);
+    const int i0 = tail ? g.lnx - 1 : blockIdx.y * SEG;
+    const int i1 = tail ? g.lnx : min(i0 + SEG, HALO ? g.lnx - 1 : g.lnx);
     const int k = blockIdx.z * blockDim.x + threadIdx.x;
     const bool active = k < g.nz;
     const int kc = active ? k : 0;                      // inactive lanes shadow k = 0 (no stores)
@@ -266,7 +277,9 @@ __global__ void __launch_bounds__(NT, MB) k_dsd_march(const double* __restrict__
             t4n[jr] = shear_from<NP>(M, phin[jr], e4, beta);
         }
     }
-    for (int i = i0; i < i1; i++) {
+    // one plane of the march; LAST = the plane i+1 is the neighbour rank's (hi halo)
+    auto plane_step = [&](const int i, auto last_tag) __attribute__((always_inline)) {
+        constexpr bool LAST = decltype(last_tag)::value;
         const int ip = (i + 1 == g.lnx) ? 0 : i + 1;
         // halo rows of plane i
         double t1_m, t5_p, t3_p;
@@ -280,6 +293,30 @@ __global__ void __launch_bounds__(NT, MB) k_dsd_march(const double* __restrict__
             phi_load<NP>(M, o, ph);
             t5_p = shear_from<NP>(M, ph, pval<UPDATE>(r, p_old, 5 * P + o, cgbeta), beta);
             t3_p = shear_from<NP>(M, ph, pval<UPDATE>(r, p_old, 3 * P + o, cgbeta), beta);
+        }
+        // z row split over several CTAs: the two end threads read their outside neighbour from memory after the barrier; asking for
+        // those lines now takes the DRAM latency off the critical path of the plane
+        if (!ZW) {
+            if (edge_hi) {
+#pragma unroll
+                for (int jr = 0; jr < BJ; jr++) {
+                    const size_t o = ROW(i, j0 + jr) + kp;
+#pragma unroll
+                    for (int q = 0; q < NP; q++) l2_prefetch(M.phi[q] + o);
+                    l2_prefetch(p_old + 4 * P + o); l2_prefetch(p_old + 3 * P + o);
+                    if (UPDATE) { l2_prefetch(r + 4 * P + o); l2_prefetch(r + 3 * P + o); }
+                }
+            }
+            if (edge_lo) {
+#pragma unroll
+                for (int jr = 0; jr < BJ; jr++) {
+                    const size_t o = ROW(i, j0 + jr) + km;
+#pragma unroll
+                    for (int q = 0; q < NP; q++) l2_prefetch(M.phi[q] + o);
+                    l2_prefetch(p_old + o); l2_prefetch(p_old + P + o); l2_prefetch(p_old + 2 * P + o);
+                    if (UPDATE) { l2_prefetch(r + o); l2_prefetch(r + P + o); l2_prefetch(r + 2 * P + o); }
+                }
+            }
         }
         // own rows of plane i: components 0..3 from memory, 4 and 5 carried from the previous step
         double tc[BJ][6];
@@ -299,7 +336,7 @@ __global__ void __launch_bounds__(NT, MB) k_dsd_march(const double* __restrict__
         for (int jr = 0; jr < BJ; jr++) {
             const size_t o = ROW(ip, j0 + jr) + kc;
             double e5, e4;
-            if (HALO && i + 1 == g.lnx) {
+            if (LAST) {
                 const size_t oh = (size_t)(j0 + jr) * g.nzp + kc;
 #pragma unroll
                 for (int q = 0; q < NP; q++) phin[jr][q] = __ldg(halo + (10 + FGB_MAX_PHASES + q) * pe + oh);
@@ -357,6 +394,12 @@ __global__ void __launch_bounds__(NT, MB) k_dsd_march(const double* __restrict__
             }
             t0_prev[jr] = tc[jr][0];
         }
+    };
+    if (tail) {
+        plane_step(i0, BoolTag<true>{});
+    } else {
+#pragma unroll 1
+        for (int i = i0; i < i1; i++) plane_step(i, BoolTag<false>{});
     }
 #undef ROW
 }
@@ -369,7 +412,10 @@ struct MarchTile {
 static MarchTile march_tile(const fgb_ctx* ctx) {
     const GridDev& g = ctx->g;
     MarchTile t;
-    t.threads = (g.nz > 256 && g.nz <= 512 && !getenv("FGB_MARCH_NT256")) ? 512 : 256;
+    // 512-thread CTAs (one per SM) when they waste no more lanes than 256-thread ones: a 257..512-voxel z row then stays inside one
+    // CTA, and a longer row has half as many CTA ends (whose threads fetch their outside neighbour from memory)
+    const int waste512 = (g.nz + 511) / 512 * 512 - g.nz, waste256 = (g.nz + 255) / 256 * 256 - g.nz;
+    t.threads = (g.nz > 256 && waste512 <= waste256 && !getenv("FGB_MARCH_NT256")) ? 512 : 256;
     while (t.threads > 32 && t.threads / 2 >= g.nz) t.threads /= 2;
     t.kchunks = (g.nz + t.threads - 1) / t.threads;
     // two rows per thread (measured at 256^3: 0.645 ms with 4 rows, 0.516 ms with 2, 0.572 ms with 1; at 512^3: 5.04 / 4.24 ms)
@@ -393,7 +439,9 @@ static MarchTile march_tile(const fgb_ctx* ctx) {
     }
     if (g.lnx < t.SEG) t.SEG = g.lnx;
     if (t.SEG < 1) t.SEG = 1;
-    t.segs = (g.lnx + t.SEG - 1) / t.SEG;
+    // slab partition: regular segments over planes [0, lnx-1) plus one row of tail CTAs for the last plane (k_dsd_march)
+    const bool slab = ctx->nranks > 1 || getenv("FGB_MARCH_FAKE_HALO");
+    t.segs = slab ? (g.lnx - 1 + t.SEG - 1) / t.SEG + 1 : (g.lnx + t.SEG - 1) / t.SEG;
     return t;
 }
 
@@ -402,6 +450,17 @@ static int launch_march(fgb_ctx* ctx, const double* r, const double* p_old, doub
                         double gamma) {
     const GridDev& g = ctx->g;
     const double* halo = (ctx->nranks > 1) ? ctx->iso_halo : nullptr;
+    // timing experiments only (wrong results): run the slab variant of the kernel on one GPU against a zero halo
+    static const bool fake_halo = getenv("FGB_MARCH_FAKE_HALO") != nullptr;
+    if (!halo && fake_halo) {
+        static double* fh = nullptr;
+        if (!fh) {
+            const size_t nb = sizeof(double) * (10 + 2 * FGB_MAX_PHASES) * (size_t)g.ny * g.nzp;
+            FGB_CUDA(ctx, cudaMalloc(&fh, nb));
+            FGB_CUDA(ctx, cudaMemset(fh, 0, nb));
+        }
+        halo = fh;
+    }
     const MarchTile mt = march_tile(ctx);
     const double* scal = (UPDATE && ctx->cg_dev) ? ctx->d_scalars : nullptr;
     const int threads = mt.threads, kchunks = mt.kchunks, SEG = mt.SEG;
@@ -416,18 +475,22 @@ static int launch_march(fgb_ctx* ctx, const double* r, const double* p_old, doub
     // resident CTAs per SM asked of the compiler: 256-thread tiles 2 (4 rows), 3 or 2 (2 rows, FGB_MARCH_MB), 4 (1 row); 512-thread tiles 1
 #define LAUNCH_MARCH5(BJ_, H_, Z_, NT_)                                                \
     do {                                                                               \
-        if (NT_ == 512) LAUNCH_MARCH6(BJ_, H_, Z_, NT_, 1);                            \
-        else if (BJ_ == 4) LAUNCH_MARCH6(BJ_, H_, Z_, NT_, 2);                         \
-        else if (BJ_ == 2 && mt.mb == 2) LAUNCH_MARCH6(BJ_, H_, Z_, NT_, 2);           \
-        else if (BJ_ == 2) LAUNCH_MARCH6(BJ_, H_, Z_, NT_, 3);                         \
-        else LAUNCH_MARCH6(BJ_, H_, Z_, NT_, 4);                                       \
+        if constexpr (NT_ == 512) LAUNCH_MARCH6(BJ_, H_, Z_, NT_, 1);                  \
+        else if constexpr (BJ_ == 4) LAUNCH_MARCH6(BJ_, H_, Z_, NT_, 2);               \
+        else if constexpr (BJ_ == 2) {                                                 \
+            if (mt.mb == 2) LAUNCH_MARCH6(BJ_, H_, Z_, NT_, 2);                        \
+            else LAUNCH_MARCH6(BJ_, H_, Z_, NT_, 3);                                   \
+        } else LAUNCH_MARCH6(BJ_, H_, Z_, NT_, 4);                                     \
     } while (0)
 #define LAUNCH_MARCH(BJ_)                                     \
     do {                                                      \
         dim3 grid(g.ny / BJ_, segs, kchunks);                 \
-        if (threads > 256) {                                  \
+        if (threads > 256 && kchunks == 1) {                  \
             if (halo) LAUNCH_MARCH5(BJ_, 1, 1, 512);          \
             else LAUNCH_MARCH5(BJ_, 0, 1, 512);               \
+        } else if (threads > 256) {                           \
+            if (halo) LAUNCH_MARCH5(BJ_, 1, 0, 512);          \
+            else LAUNCH_MARCH5(BJ_, 0, 0, 512);               \
         } else if (halo) {                                    \
             if (kchunks == 1) LAUNCH_MARCH5(BJ_, 1, 1, 256);  \
             else LAUNCH_MARCH5(BJ_, 1, 0, 256);               \

@@ -1,5 +1,5 @@
 """Kernel micro-benchmark for A/B runs of environment-selected kernel variants (not a test): times the kernels of one fused CG
-iteration of config 2 with the library's own events.   python tests/kbench.py [n]"""
+iteration of config 2 with the library's own events.   python tests/kbench.py [n | nx ny nz]"""
 import os
 import sys
 
@@ -12,10 +12,11 @@ import fibergen_b200 as fb
 from microstructures import config2_fibres, fiber_list
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+dims = (int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (n, n, n)
 Cs, Ds, R, Lc = config2_fibres()
-sc = n / 256.0
-fibs, box = fiber_list((n, n, n), Cs * sc, Ds, R * sc, Lc * sc)
-s = fb.LSSolver(n, n, n, mode="elasticity", method="cg", error_estimator="residual", tol=1e-300, maxiter=14)
+sc = min(dims) / 256.0
+fibs, box = fiber_list(dims, Cs * sc, Ds, R * sc, Lc * sc)
+s = fb.LSSolver(dims[0], dims[1], dims[2], mode="elasticity", method="cg", error_estimator="residual", tol=1e-300, maxiter=14)
 s.add_material("m", "iso", 0.6121, 1.5739)
 s.add_material("f", "iso", 30.93, 17.4)
 s.init()
