@@ -209,7 +209,9 @@ __device__ __forceinline__ void diag_from(const IsoPhases& M, const double* phi,
     if (gamma != 0) { t0 += gamma * tr; t1 += gamma * tr; t2 += gamma * tr; }
 }
 
-static __device__ __forceinline__ void l2_prefetch(const double* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+static __device__ __forceinline__ void cp_async8(double* smem_dst, const double* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(src) : "memory");
+}
 
 template <bool B>
 struct BoolTag {
@@ -243,8 +245,9 @@ __global__ void __launch_bounds__(NT, MB) k_dsd_march(const double* __restrict__
     // NT = 512 (one CTA per SM) keeps a 257..512-voxel z row inside one CTA, so that no thread takes the slow edge path
     extern __shared__ double zx[];          // [2][3 * BJ][NT]
     const int tid = threadIdx.x;
-    const bool edge_hi = !ZW && ((tid == (int)blockDim.x - 1) || (kc + 1 >= g.nz));
-    const bool edge_lo = !ZW && ((tid == 0) || (kc == 0));
+    const bool edge_hi = !ZW && active && ((tid == (int)blockDim.x - 1) || (k + 1 >= g.nz));          // one thread per CTA end
+    const bool edge_lo = !ZW && (tid == 0);
+    double* ex = zx + 2 * 3 * BJ * NT;          // !ZW: [2][BJ][10] raw values of the outside z neighbours (hi end, lo end)
     const int nb_hi = ZW ? ((kc + 1 == g.nz) ? 0 : tid + 1) : min(tid + 1, (int)blockDim.x - 1);
     const int nb_lo = ZW ? ((kc == 0) ? g.nz - 1 : tid - 1) : max(tid - 1, 0);
 #define ROW(i, j) (((size_t)(i) * g.ny + (j)) * g.nzp)
@@ -294,29 +297,33 @@ __global__ void __launch_bounds__(NT, MB) k_dsd_march(const double* __restrict__
             t5_p = shear_from<NP>(M, ph, pval<UPDATE>(r, p_old, 5 * P + o, cgbeta), beta);
             t3_p = shear_from<NP>(M, ph, pval<UPDATE>(r, p_old, 3 * P + o, cgbeta), beta);
         }
-        // z row split over several CTAs: the two end threads read their outside neighbour from memory after the barrier; asking for
-        // those lines now takes the DRAM latency off the critical path of the plane
+        // z row split over several CTAs: the two end threads need their outside neighbour from memory.  They start 8-byte
+        // asynchronous copies of the raw values into a shared-memory scratch now (no registers, no waiting) and pick them up after
+        // the barrier, so the DRAM latency overlaps the plane's own loads instead of following them
         if (!ZW) {
             if (edge_hi) {
 #pragma unroll
                 for (int jr = 0; jr < BJ; jr++) {
                     const size_t o = ROW(i, j0 + jr) + kp;
+                    double* d = ex + jr * 10;
 #pragma unroll
-                    for (int q = 0; q < NP; q++) l2_prefetch(M.phi[q] + o);
-                    l2_prefetch(p_old + 4 * P + o); l2_prefetch(p_old + 3 * P + o);
-                    if (UPDATE) { l2_prefetch(r + 4 * P + o); l2_prefetch(r + 3 * P + o); }
+                    for (int q = 0; q < NP; q++) cp_async8(d + q, M.phi[q] + o);
+                    cp_async8(d + 3, p_old + 4 * P + o); cp_async8(d + 4, p_old + 3 * P + o);
+                    if (UPDATE) { cp_async8(d + 5, r + 4 * P + o); cp_async8(d + 6, r + 3 * P + o); }
                 }
             }
             if (edge_lo) {
 #pragma unroll
                 for (int jr = 0; jr < BJ; jr++) {
                     const size_t o = ROW(i, j0 + jr) + km;
+                    double* d = ex + (BJ + jr) * 10;
 #pragma unroll
-                    for (int q = 0; q < NP; q++) l2_prefetch(M.phi[q] + o);
-                    l2_prefetch(p_old + o); l2_prefetch(p_old + P + o); l2_prefetch(p_old + 2 * P + o);
-                    if (UPDATE) { l2_prefetch(r + o); l2_prefetch(r + P + o); l2_prefetch(r + 2 * P + o); }
+                    for (int q = 0; q < NP; q++) cp_async8(d + q, M.phi[q] + o);
+                    cp_async8(d + 3, p_old + o); cp_async8(d + 4, p_old + P + o); cp_async8(d + 5, p_old + 2 * P + o);
+                    if (UPDATE) { cp_async8(d + 6, r + o); cp_async8(d + 7, r + P + o); cp_async8(d + 8, r + 2 * P + o); }
                 }
             }
+            asm volatile("cp.async.commit_group;" ::: "memory");
         }
         // own rows of plane i: components 0..3 from memory, 4 and 5 carried from the previous step
         double tc[BJ][6];
@@ -366,18 +373,24 @@ __global__ void __launch_bounds__(NT, MB) k_dsd_march(const double* __restrict__
             double t3_kp = zb[(3 * jr + 1) * NT + nb_hi];
             double t2_km = zb[(3 * jr + 2) * NT + nb_lo];
             if (edge_hi) {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                const double* d = ex + jr * 10;
                 double ph[NP];
-                const size_t o = ROW(i, j0 + jr) + kp;
-                phi_load<NP>(M, o, ph);
-                t4_kp = shear_from<NP>(M, ph, pval<UPDATE>(r, p_old, 4 * P + o, cgbeta), beta);
-                t3_kp = shear_from<NP>(M, ph, pval<UPDATE>(r, p_old, 3 * P + o, cgbeta), beta);
+#pragma unroll
+                for (int q = 0; q < NP; q++) ph[q] = d[q];
+                const double e4 = UPDATE ? d[5] + cgbeta * d[3] : d[3], e3 = UPDATE ? d[6] + cgbeta * d[4] : d[4];
+                t4_kp = shear_from<NP>(M, ph, e4, beta);
+                t3_kp = shear_from<NP>(M, ph, e3, beta);
             }
             if (edge_lo) {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                const double* d = ex + (BJ + jr) * 10;
                 double ph[NP], d0, d1;
-                const size_t o = ROW(i, j0 + jr) + km;
-                phi_load<NP>(M, o, ph);
-                diag_from<NP>(M, ph, pval<UPDATE>(r, p_old, o, cgbeta), pval<UPDATE>(r, p_old, P + o, cgbeta),
-                              pval<UPDATE>(r, p_old, 2 * P + o, cgbeta), beta, gamma, d0, d1, t2_km);
+#pragma unroll
+                for (int q = 0; q < NP; q++) ph[q] = d[q];
+                const double e0 = UPDATE ? d[6] + cgbeta * d[3] : d[3], e1 = UPDATE ? d[7] + cgbeta * d[4] : d[4];
+                const double e2 = UPDATE ? d[8] + cgbeta * d[5] : d[5];
+                diag_from<NP>(M, ph, e0, e1, e2, beta, gamma, d0, d1, t2_km);
             }
             const double t1_jm = (jr == 0) ? t1_m : tc[jr > 0 ? jr - 1 : 0][1];
             const double t5_jp = (jr == BJ - 1) ? t5_p : tc[jr < BJ - 1 ? jr + 1 : jr][5];
@@ -467,7 +480,7 @@ static int launch_march(fgb_ctx* ctx, const double* r, const double* p_old, doub
     const int segs = mt.segs;
 #define LAUNCH_MARCH6(BJ_, H_, Z_, NT_, MB_)                                                                         \
     do {                                                                                                             \
-        const size_t smem = sizeof(double) * 2 * 3 * BJ_ * NT_;                                                     \
+        const size_t smem = sizeof(double) * (2 * 3 * BJ_ * NT_ + (Z_ ? 0 : 2 * BJ_ * 10));                         \
         if (smem > 48 * 1024)                                                                                        \
             FGB_CUDA(ctx, cudaFuncSetAttribute(k_dsd_march<UPDATE, NP, BJ_, H_, Z_, NT_, MB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         k_dsd_march<UPDATE, NP, BJ_, H_, Z_, NT_, MB_><<<grid, threads, smem, ctx->stream>>>(r, p_old, p_new, ctx->ubuf, g, M, cgbeta, beta, gamma, SEG, halo, scal); \

@@ -83,7 +83,7 @@ def test_basic_sphere(scheme, ee):
     assert len(rs) > 5
 
 
-@pytest.mark.parametrize("n", [(32, 32, 32), (24, 20, 18), (16, 16, 1), (15, 9, 7), (6, 10, 300), (4, 8, 600)])
+@pytest.mark.parametrize("n", [(32, 32, 32), (24, 20, 18), (16, 16, 1), (15, 9, 7), (6, 10, 300), (4, 8, 600), (4, 8, 513), (4, 6, 1024)])
 @pytest.mark.parametrize("ee", ["residual", "epsilon"])
 def test_cg_staggered(n, ee):
     """BASELINE config 2 shape (CG, staggered, Voigt mixing) on grids the oracle finishes in seconds"""
