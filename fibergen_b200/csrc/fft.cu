@@ -549,7 +549,8 @@ int fgb_fft_strided(fgb_ctx* ctx, int axis, const double* src_, double* dst_, co
         return FGB_OK;
     }
     // 1024 with stores into peer memory: 8-lane tiles (128-byte segments over NVLink); the two-pass kernel only fits 4 lanes
-    if (n == 1024 && pt.n > 0 && !no_p3) {
+    static const bool s1024_p3 = getenv("FGB_S1024_P3") != nullptr;          // A/B: the three-pass 8-lane kernel for local 1024-point passes too
+    if (n == 1024 && (pt.n > 0 || s1024_p3) && !no_p3) {
         launch_s_p3<16, 8, 8, 8>(ctx, src, dst, tw, mi, mo, ninner, nouter, ncomp, dir, pt);
         FGB_CHECK_LAUNCH(ctx, "k_ffts_p3");
         return FGB_OK;

@@ -222,23 +222,32 @@ __global__ void __launch_bounds__(p3::Plan<R1, R2, R3, T>::TPP* T, MINB)
 
 // The same pass for a CTA PAIR (thread-block cluster of 2 along the tile index) whose output goes to peer GPUs: with T lanes per
 // CTA a row segment is only T*16 bytes (64 at nx = 1024, where a wider tile does not fit), and 64-byte stores reach ~430 GB/s
-// over NVLink against ~690 GB/s for 128-byte ones.  Each CTA parks one component's output in a shared-memory stage, and after a
-// cluster barrier stores HALF of the x range with 2T lanes -- T from its own stage, T from its partner's through distributed
-// shared memory -- so every segment that crosses NVLink is 2T*16 = 128 bytes.
+// over NVLink against ~690 GB/s for 128-byte ones.  The two CTAs exchange one component's output through shared memory (half of
+// it with asynchronous stores into the partner's: distributed shared memory + mbarrier), and each stores HALF of the x range with the
+// 2T lanes of the pair -- so every segment that crosses NVLink is 2T*16 = 128 bytes.
 template <int R1, int R2, int R3, int NC, int KIND, int T>
 __global__ void __launch_bounds__(p3::Plan<R1, R2, R3, T>::TPP* T, 1)
     k_fftx_green_p3c(double2* __restrict__ base, const double2* __restrict__ tw, GreenDev G, long estride, int ninner, long ostride,
                      long cstride, int jbase, PencilMap xo, PeerTable pt) {
     using P = p3::Plan<R1, R2, R3, T>;
     constexpr int N = P::N, M = P::M, NT = P::TPP * T;
+    static_assert((N / 2) % M == 0, "the pass-1 distribution must not straddle the two halves of the x range");
     extern __shared__ double2 smem_x3[];
     double2* tw_s = smem_x3;
     double2* B1 = smem_x3 + N;
     double2* B2 = B1 + P::BUF1;
     double2* stage = B2 + P::BUF2;          // [N][T]
+    __shared__ unsigned long long xbar;          // counts the bytes the partner CTA sends into this CTA's stage
     cg::cluster_group cl = cg::this_cluster();
     const unsigned cr = cl.block_rank();
     const int tid = threadIdx.x;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&xbar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // both barriers of the pair exist before either CTA sends (no stores are in flight yet, so this release is cheap)
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
     for (int i = tid; i < N; i += NT) tw_s[i] = tw[i];
     const int t = tid % T, s = tid / T;
     const int inner = blockIdx.x * T + t;
@@ -276,46 +285,76 @@ __global__ void __launch_bounds__(p3::Plan<R1, R2, R3, T>::TPP* T, 1)
         }
     }
     __syncthreads();
-    // the pair's 2T lanes: lanes [0, T) live in CTA 0's stage, [T, 2T) in CTA 1's
+    // the pair's stage: CTA h holds x indices [h N/2, (h+1) N/2) with all 2T lanes of the pair, [N/2][2T].  A thread hands its
+    // R1 outputs of a component to the CTA that will store them: its own half with ordinary shared-memory stores, the partner's
+    // half with st.async into the partner's shared memory, which counts the bytes on the partner's mbarrier.  Nothing on this
+    // path is a release fence: a fence would also order the peer stores in flight, i.e. wait for their NVLink round trip (measured:
+    // release/acquire cluster barriers around the exchange made the pass 40 % slower than the 64-byte version it replaces).
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&xbar);
+    const unsigned partner = cr ^ 1u;
+    unsigned rstage, rbar;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rstage) : "r"((unsigned)__cvta_generic_to_shared(stage)), "r"(partner));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(bar), "r"(partner));
     const int lane2 = tid % (2 * T), eo = tid / (2 * T);
-    const double2* src = cl.map_shared_rank(stage, lane2 / T) + (lane2 % T);
     const int inner2 = (int)(blockIdx.x - cr) * T + lane2;
     constexpr int EPI = NT / (2 * T);          // x indices per sweep of the CTA
     constexpr int NIT = (N / 2) / EPI;
-    // split cluster barrier: "arrive" right after the stores of a component, "wait" only before the stage is written again, so the
-    // partner's stores overlap this CTA's next inverse transform
-#define CL_ARRIVE() asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory")
+    constexpr unsigned TX_BYTES = (N / 2) * T * sizeof(double2);          // what the partner sends per component
+#define CL_ARRIVE_RELAXED() asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory")
 #define CL_WAIT() asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory")
 #pragma unroll
     for (int c = 0; c < NC; c++) {
         double2 o[R1];
         P::inverse(w[c], o, s, t, B1, B2, tw_s);
-        if (c) CL_WAIT();          // the partner has read the previous component out of this CTA's stage
+        if (c) CL_WAIT();          // both CTAs have read the previous component out of their stages
+        if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(TX_BYTES) : "memory");
         if (s < M) {
 #pragma unroll
-            for (int na = 0; na < R1; na++) stage[(s + M * na) * T + t] = o[na];
+            for (int na = 0; na < R1; na++) {
+                // x index e = s + M na with s < M and M | N/2: the owner CTA and the slot offset are compile-time per na
+                const unsigned slot = (unsigned)((s + (M * na) % (N / 2)) * (2 * T) + (int)cr * T + t);
+                if ((unsigned)((M * na) / (N / 2)) == cr) {
+                    stage[slot] = o[na];
+                } else {
+                    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];" ::"r"(
+                                     rstage + slot * (unsigned)sizeof(double2)),
+                                 "l"(__double_as_longlong(o[na].x)), "l"(__double_as_longlong(o[na].y)), "r"(rbar)
+                                 : "memory");
+                }
+            }
         }
-        CL_ARRIVE();
-        CL_WAIT();
+        __syncthreads();          // this CTA's own half
+        {                         // the partner's half has landed (phase parity = component parity)
+            asm volatile(
+                "{\n"
+                ".reg .pred p;\n"
+                "XBAR_WAIT:\n"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                "@p bra XBAR_DONE;\n"
+                "bra XBAR_WAIT;\n"
+                "XBAR_DONE:\n"
+                "}\n" ::"r"(bar),
+                "r"((unsigned)(c & 1))
+                : "memory");
+        }
         if (inner2 < ninner) {
-            const int e0 = (int)cr * (N / 2) + eo;
 #pragma unroll
             for (int h = 0; h < NIT; h += 4) {
                 double2 q[4];
 #pragma unroll
-                for (int u = 0; u < 4; u++) q[u] = src[(size_t)(e0 + (h + u) * EPI) * T];
+                for (int u = 0; u < 4; u++) q[u] = stage[(size_t)(eo + (h + u) * EPI) * (2 * T) + lane2];
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
-                    const int e = e0 + (h + u) * EPI;
+                    const int e = (int)cr * (N / 2) + eo + (h + u) * EPI;
                     double2* b = pt.n ? pt.p[e / xo.seglen] : base;
                     b[c * xo.cstride + (long)blockIdx.y * xo.ostride + inner2 + xo.at(e)] = q[u];
                 }
             }
         }
-        CL_ARRIVE();
+        CL_ARRIVE_RELAXED();          // "done reading my stage": carries no data
     }
-    CL_WAIT();          // no CTA leaves while its partner may still read its stage
-#undef CL_ARRIVE
+    CL_WAIT();          // no CTA leaves while its partner may still write into its stage
+#undef CL_ARRIVE_RELAXED
 #undef CL_WAIT
 }
 
@@ -406,7 +445,8 @@ static int launch_x_green(fgb_ctx* ctx, double2* base, const GreenDev& G, long e
         // FGB_XG_NARROW_PEER selects the single-GPU tile shapes for comparison.
         static const bool narrow = getenv("FGB_XG_NARROW_PEER") != nullptr;
         if constexpr (NC <= 3) {
-            if (pt.n > 0 && !narrow) {
+            static const bool force_wide = getenv("FGB_XG_FORCE_PEER_TILES") != nullptr;          // profiling on one GPU
+            if ((pt.n > 0 || force_wide) && !narrow) {
                 if (nx == 512) rc = launch_xg_p3<8, 8, 8, NC, KIND, 8, 1>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt);
                 else if (nx == 1024) {
                     // FGB_XG_CLUSTER: CTA pairs exchanging through distributed shared memory, 128-byte segments.  Not the default: at 2 GPUs
@@ -419,7 +459,11 @@ static int launch_x_green(fgb_ctx* ctx, double2* base, const GreenDev& G, long e
         }
         if (rc != -1) return rc;
         if (nx == 512) XG3(8, 8, 8, 4);
-        else if (nx == 1024) XG3(16, 8, 8, 2);
+        else if (nx == 1024) {
+            // 4 lanes, one CTA per SM: 0.900 ms against 0.947 ms for 2 lanes / 2 CTAs (1024x128x256, one GPU)
+            if constexpr (NC <= 3) rc = launch_xg_p3<16, 8, 8, NC, KIND, 4, 1>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt);
+            else XG3(16, 8, 8, 2);
+        }
         else if (NC > 3 || xg_p3) {
             static const bool p3_t8 = getenv("FGB_XG_P3_T8") != nullptr;          // A/B: 8-lane three-pass tile at nx = 256
             if (nx == 64) XG3(4, 4, 4, 8);

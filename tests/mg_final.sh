@@ -1,5 +1,5 @@
 #!/bin/bash
-# final multi-GPU measurements of round 2 (run under gpurun --gpus N): usage mg_final.sh N [weak] [strong]
+# final multi-GPU measurements of round 2 (run under gpurun --gpus N): usage mg_final.sh N [weak] [strong] [strongcl] [check] [checkcl]
 cd "$(dirname "$0")/.."
 N=$1; shift
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
@@ -9,6 +9,11 @@ for mode in "$@"; do
     timeout 300 $TR --master-port 29561 bench.py --gpus $N --steps 20 --warmup 3 > gpurun_out/bench_r02_${N}gpu_weak.json 2> gpurun_out/bench_r02_${N}gpu_weak.err
   elif [ "$mode" = "strong" ]; then
     timeout 400 $TR --master-port 29562 bench.py --gpus $N --scaling strong --grid 1024 --warmup 3 > gpurun_out/bench_r02_${N}gpu_strong1024.json 2> gpurun_out/bench_r02_${N}gpu_strong1024.err
+  elif [ "$mode" = "strongcl" ]; then          # A/B: CTA-pair x pass (128-byte peer segments at nx = 1024)
+    FGB_XG_CLUSTER=1 timeout 400 $TR --master-port 29564 bench.py --gpus $N --scaling strong --grid 1024 --warmup 3 > gpurun_out/bench_r02_${N}gpu_strong1024_cluster.json 2> gpurun_out/bench_r02_${N}gpu_strong1024_cluster.err
+  elif [ "$mode" = "checkcl" ]; then
+    FGB_XG_CLUSTER=1 timeout 400 $TR --master-port 29565 tests/mgpu_check.py > gpurun_out/mgpu_check_${N}gpu_cluster.log 2>&1
+    grep -c " OK" gpurun_out/mgpu_check_${N}gpu_cluster.log; grep "MISMATCH" gpurun_out/mgpu_check_${N}gpu_cluster.log
   elif [ "$mode" = "check" ]; then
     timeout 400 $TR --master-port 29563 tests/mgpu_check.py > gpurun_out/mgpu_check_${N}gpu.log 2>&1
     grep -c " OK" gpurun_out/mgpu_check_${N}gpu.log; grep "MISMATCH" gpurun_out/mgpu_check_${N}gpu.log
