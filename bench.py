@@ -332,7 +332,7 @@ def run_cuda(args):
     if top and kernels[top]["gbs"]:
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp) and cfg == "c2":
+        if os.path.exists(tp) and cfg == "c2" and nloc == 256 ** 3:          # the capture is of 256^3 voxels per GPU
             try:
                 traffic = json.load(open(tp)).get(top)
             except Exception:
