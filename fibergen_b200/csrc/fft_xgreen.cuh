@@ -449,10 +449,12 @@ static int launch_x_green(fgb_ctx* ctx, double2* base, const GreenDev& G, long e
             if ((pt.n > 0 || force_wide) && !narrow) {
                 if (nx == 512) rc = launch_xg_p3<8, 8, 8, NC, KIND, 8, 1>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt);
                 else if (nx == 1024) {
-                    // FGB_XG_CLUSTER: CTA pairs exchanging through distributed shared memory, 128-byte segments.  Not the default: at 2 GPUs
-                    // (1024^3) the exchange costs more than the wider segments return, 22.3 vs 15.7 ms
-                    static const bool use_cl = getenv("FGB_XG_CLUSTER") != nullptr;
-                    if (use_cl) rc = launch_xg_p3c<16, 8, 8, NC, KIND, 4>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt);
+                    // CTA pairs exchanging through distributed shared memory, 128-byte segments over NVLink.  The exchange costs
+                    // ~40 % more SM time per tile, so it pays only when nearly everything leaves the GPU: 1024^3 on 8 GPUs 5.83 vs
+                    // 6.68 ms (default from 8 ranks on), on 2 GPUs 21.6 vs 15.5 ms.  FGB_XG_CLUSTER / FGB_XG_NO_CLUSTER force it.
+                    static const bool use_cl = getenv("FGB_XG_CLUSTER") != nullptr, no_cl = getenv("FGB_XG_NO_CLUSTER") != nullptr;
+                    if ((use_cl || pt.n >= 8) && !no_cl)
+                        rc = launch_xg_p3c<16, 8, 8, NC, KIND, 4>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt);
                     if (rc == -1) rc = launch_xg_p3<16, 8, 8, NC, KIND, 4, 1>(ctx, base, G, estride, ninner, nouter, ostride, cstride, jbase, xo, pt);
                 }
             }
